@@ -1,0 +1,267 @@
+/* liboisat -- C-ABI of the B200-native OI-SAT-GMI assimilation hot path.
+ *
+ * The reference (ahsouri/OI-SAT-GMI) is pure Python: it has no FFI layer, the
+ * boundary of its hot path is a set of plain Python functions
+ * (oisatgmi/interpolator.py:100, amf_recal.py:121, ak_conv_mopitt.py:8,
+ * ak_conv_gosat.py:8, averaging.py:26, optimal_interpolation.py:6).  The
+ * drop-in modules in oisatgmi_b200/ keep those signatures and call the entry
+ * points below through ctypes; INTEGRATION.md shows the binding a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative OISAT_E_* code otherwise;
+ *     oisat_last_error() gives the thread-local message of the last failure;
+ *   - every array argument is a CALLER-OWNED DEVICE pointer unless the name
+ *     starts with `h_` (host); extents are explicit int64; `stream` is a
+ *     cudaStream_t passed as void*;
+ *   - no hidden host synchronisation, no allocation in hot calls (scratch is
+ *     caller-provided, sized by the *_workspace functions), no global state
+ *     beyond the error string;
+ *   - two-dimensional operands are "level-major": element (level l, item i)
+ *     lives at base[l * stride + i].
+ */
+#ifndef OISAT_H_
+#define OISAT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OISAT_ABI_VERSION 1
+
+enum {
+  OISAT_OK = 0,
+  OISAT_E_ARG = -1,     /* bad argument */
+  OISAT_E_CUDA = -2,    /* CUDA runtime/driver error */
+  OISAT_E_UNSUPPORTED = -3
+};
+
+/* element types of input arrays, as delivered by the reference's readers
+ * (float16 for most L2 fields, reader.py:846-883; float32 for lat/lon and the
+ * model fields, reader.py:138-152) */
+enum { OISAT_F16 = 1, OISAT_F32 = 2, OISAT_F64 = 3, OISAT_U8 = 4, OISAT_I32 = 5 };
+
+/* per-field value transforms applied while gathering (interpolator.py:186:
+ * sigma is squared IN THE INPUT DTYPE before the float64 mask multiply) */
+enum { OISAT_OP_NONE = 0, OISAT_OP_SQUARE_NATIVE = 1 };
+
+/* post-transform of a gridded row (interpolator.py:188: sqrt of the gridded variance) */
+enum { OISAT_POST_NONE = 0, OISAT_POST_SQRT = 1 };
+
+typedef struct oisat_field {
+  const void* data;     /* device: [nlev][lev_stride] of `dtype`                 */
+  int32_t dtype;        /* OISAT_F16 / F32 / F64                                  */
+  int32_t op;           /* OISAT_OP_*                                             */
+  int32_t post;         /* OISAT_POST_*                                           */
+  int32_t nlev;         /* 1 for 2-D fields                                       */
+  int64_t lev_stride;   /* elements between consecutive levels (= pixel count)   */
+  double box_weight;    /* 1/(kx*ky), or 1/(kx*ky)^2 for variances (:40-46)       */
+} oisat_field;
+
+const char* oisat_last_error(void);
+int oisat_abi_version(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t oisat_launch_count(void);
+
+/* ---- K0: proximity predicate -------------------------------------------------
+ * keep[j*W+i] = 1 iff some pixel lies within `radius` of fine-grid node
+ * (xs[i], ys[j]), i.e. NOT (dists > radius) of interpolator.py:145-150,16 /
+ * filler_gosat.py:132-137,17.  Euclidean distance in degrees, float64,
+ * sqrt(dx*dx+dy*dy) evaluated without FMA contraction so the predicate is
+ * bit-identical to scipy's cKDTree distance.  `keep` must be zeroed by the caller.
+ * xs/ys must be (approximately) uniformly spaced and ascending. */
+int oisat_distmask(const void* px_lon, const void* px_lat, int32_t coord_dtype, int64_t n_px,
+                   const double* xs, int64_t W, const double* ys, int64_t H,
+                   double radius, uint8_t* keep, void* stream);
+
+/* good[p] = (quality_flag[p] > thresh)  (interpolator.py:126-128) */
+int oisat_quality_mask(const void* qflag, int32_t dtype, int64_t n_px, double thresh,
+                       uint8_t* good, void* stream);
+
+/* ---- K2: apply a geometry plan to many fields ---------------------------------
+ * The plan is a per-output-cell stencil: cell c receives, for every row r,
+ *   out[r][oidx(c)] = post( sum_{k<nwin} box_weight * ( (0 + w[3k][c]*z0) + w[3k+1][c]*z1 ) + w[3k+2][c]*z2 )
+ * with z = op(field value at vertex vert[3k+j][c]) or NaN when the vertex pixel
+ * is not `good` -- the composition of LinearNDInterpolator (interpolator.py:13-15),
+ * the box filter (:66-76) and the nearest-node sampling (:78-91), SURVEY.md App. E.
+ * vert/w are [3*nwin][n_cells] (stencil-major, cell-minor).  out_index==NULL
+ * writes compactly (oidx(c)=c), otherwise oidx(c)=out_index[c] (dense scatter;
+ * the caller pre-fills `out` with NaN).  `h_fields` is a HOST array. */
+int oisat_interp_apply(const int32_t* vert, const double* w, int32_t nwin, int64_t n_cells,
+                       const uint8_t* good, const oisat_field* h_fields, int32_t n_fields,
+                       double* out, int64_t out_stride, const int32_t* out_index,
+                       void* stream);
+
+/* ---- K3: per-cell vertical operators -----------------------------------------
+ * Common layout: item i uses satellite column sat_index[i] (NULL: i) of the
+ * level-major satellite arrays (stride sat_stride) and model column
+ * ctm_index[i] (NULL: sat column) of the level-major model arrays (stride
+ * ctm_stride).  Results are written at the satellite column.
+ *
+ * ctm_mode 0: native model fields, float32 (delta_p, profile, p_mid): the
+ *             partial column, its log-pressure and the column sum are evaluated
+ *             in float32 exactly as numpy does (amf_recal.py:51-56,108,116);
+ * ctm_mode 1: model fields already resampled to the satellite grid and held as
+ *             float64 (amf_recal.py:58-83): `ctm_a` is p_mid, `ctm_b` the
+ *             partial column / profile, `ctm_c` (AK operators) the air column. */
+
+/* AMF recalculation, amf_recal.py:93-119,175-183.  trop may be NULL. */
+int oisat_vertical_amf(int64_t n_items, const int32_t* sat_index, const int32_t* ctm_index,
+                       const double* vcd, const double* amf, const double* trop,
+                       const double* p_sat, const double* sw, int32_t n_sat_lev, int64_t sat_stride,
+                       const void* ctm_pmid, const void* ctm_b, const void* ctm_dp,
+                       int32_t ctm_mode, int32_t n_ctm_lev, int64_t ctm_stride,
+                       double* new_amf, double* ctm_vcd, double* vcd_out, void* stream);
+
+/* model column without scattering weights (O3), amf_recal.py:160-171 */
+int oisat_vertical_column(int64_t n_items, const int32_t* sat_index, const int32_t* ctm_index,
+                          const double* vcd, const double* trop,
+                          const void* ctm_pmid, const void* ctm_b, const void* ctm_dp,
+                          int32_t ctm_mode, int32_t n_ctm_lev, int64_t ctm_stride,
+                          double* ctm_vcd, void* stream);
+
+/* MOPITT averaging-kernel convolution, ak_conv_mopitt.py:118-142.
+ * ak has n_sat_lev+1 rows (row 0 = surface). */
+int oisat_vertical_mopitt(int64_t n_items, const int32_t* sat_index, const int32_t* ctm_index,
+                          const double* vcd, const double* ap_col, const double* ap_sfc,
+                          const double* p_sat, const double* ak, const double* ap_prof,
+                          int32_t n_sat_lev, int64_t sat_stride,
+                          const void* ctm_pmid, const void* ctm_prof, const void* ctm_dp_or_air,
+                          int32_t ctm_mode, int32_t n_ctm_lev, int64_t ctm_stride,
+                          double* ctm_vcd, double* ctm_xcol, void* stream);
+
+/* GOSAT averaging-kernel convolution, ak_conv_gosat.py:118-141 (keyed on x_col). */
+int oisat_vertical_gosat(int64_t n_items, const int32_t* sat_index, const int32_t* ctm_index,
+                         const double* x_col, const double* p_sat, const double* ak,
+                         const double* ap_prof, const double* pw,
+                         int32_t n_sat_lev, int64_t sat_stride,
+                         const void* ctm_pmid, const void* ctm_prof,
+                         int32_t ctm_mode, int32_t n_ctm_lev, int64_t ctm_stride,
+                         double* ctm_xcol, void* stream);
+
+/* ---- K6: model -> satellite-grid resampling ---------------------------------
+ * out[l][i] = mean over the (ky,kx) window (symmetric edge reflection) anchored at
+ * node nn[i] of level l of `src` (float32 or float64, [nlev][H*W]), NaN when
+ * nn_ok[i]==0: interpolator._upscaler used with the grids' roles swapped
+ * (amf_recal.py:58-83, ak_conv_mopitt.py:79-110).  Output float64.
+ * src_op derives the resampled quantity on the fly from float32 model fields,
+ * in float32 like numpy does: OISAT_SRC_PARTIAL_COLUMN: src = delta_p, src2 =
+ * mixing ratio (amf_recal.py:51-56); OISAT_SRC_AIR_COLUMN: src = delta_p
+ * (ak_conv_mopitt.py:68). */
+enum { OISAT_SRC_VALUE = 0, OISAT_SRC_PARTIAL_COLUMN = 1, OISAT_SRC_AIR_COLUMN = 2 };
+int oisat_grid_resample(const void* src, const void* src2, int32_t src_op, int32_t dtype,
+                        int32_t nlev, int64_t H, int64_t W,
+                        int32_t ky, int32_t kx, double box_weight,
+                        const int32_t* nn, const uint8_t* nn_ok, int64_t n_out,
+                        double* out, int64_t out_stride, void* stream);
+
+/* ---- K4: temporal accumulation (averaging.py:64-108, 11-24) ------------------
+ * acc is [10][n_cell] float64: rows 0-4 running sums of (sat vcd, sigma^2,
+ * model vcd, aux1, aux2), rows 5-9 the matching counts (exact integers held as
+ * float64 so one all-reduce covers the block).  Granules are added one call at
+ * a time IN ORDER, which reproduces numpy's sequential axis-0 nanmean bit for
+ * bit.  Any of the five inputs may be NULL (treated as all-NaN). */
+int oisat_accum_add(double* acc, int64_t n_cell, const double* vcd, const double* sigma,
+                    const double* ctm_vcd, const double* aux1, const double* aux2, void* stream);
+
+/* means and the error sqrt(sum sigma^2 / n^2); outputs may alias nothing in acc */
+int oisat_accum_finalize(const double* acc, int64_t n_cell, double* sat_vcd, double* sat_err,
+                         double* ctm_vcd, double* aux1, double* aux2, void* stream);
+
+/* ---- K5: optimal interpolation (optimal_interpolation.py:14-52, driver.py:65-114)
+ * prepare: y = clip((y - bias_a)/bias_b, 0) in place (driver.py:65-106 then
+ *          optimal_interpolation.py:14), Sa = (xa*err_pct/100)^2, So = sigma^2. */
+int oisat_oi_prepare(const double* xa, double* y, const double* sigma, int64_t n,
+                     double bias_a, double bias_b, double err_pct,
+                     double* Sa, double* So, void* stream);
+
+/* sweep: for every regularisation factor r (HOST array h_factors, n_factors<=128)
+ * the sum and count of the finite entries of AK_r = 1 - Sb_r/(Sa r), summed in
+ * numpy's pairwise order so that nanmean(AK) is reproduced bit for bit.
+ * sums/counts: [n_factors] float64 device outputs.  `work` holds
+ * oisat_oi_sweep_workspace(n, n_factors) bytes. */
+int64_t oisat_oi_sweep_workspace(int64_t n, int32_t n_factors);
+int oisat_oi_sweep(const double* Sa, const double* So, int64_t n,
+                   const double* h_factors, int32_t n_factors,
+                   double* sums, double* counts, void* work, int64_t work_bytes, void* stream);
+
+/* apply the chosen factor: xb = xa + K (y - xa), AK, increment, sqrt(Sb) */
+int oisat_oi_apply(const double* xa, const double* y, const double* Sa, const double* So,
+                   int64_t n, double factor, double* xb, double* ak, double* inc, double* err,
+                   void* stream);
+
+/* ---- fused month pipeline for float16 `satellite_amf` products ----------------
+ * (OMI NO2/HCHO, TROPOMI NO2: the BASELINE configurations)
+ *
+ * pack: reader-layout fields ([nlev][n_px] float16, level-major) -> one
+ * pixel-major record per pixel so that a vertex gather is a few 128-bit loads:
+ *   rows = [SW_0..SW_{L-1}, p_0..p_{L-1}, vcd, sigma^2, tropopause?]; nchunk =
+ *   ceil(nrow/8) 16-byte chunks per record; row r sits in chunk r % nchunk at
+ *   element r / nchunk (DESIGN.md "packed record").
+ * sigma is squared in float16 here (interpolator.py:186).  `good` folds the
+ * quality flag (interpolator.py:126-128). */
+int64_t oisat_pack_record_halfs(int32_t n_sat_lev, int32_t has_trop);
+int oisat_pack_granule(const void* sw, const void* p_mid, int32_t n_sat_lev,
+                       const void* vcd, const void* sigma, const void* trop /* may be NULL */,
+                       int64_t n_px, void* records, void* stream);
+
+/* fused gather-interpolation + AMF recalculation over a batch of granules.
+ * One "pair" = (granule, model cell) that the geometry plan marks as reachable.
+ * Pairs are grouped in tiles of <=32 consecutive cells of one model row.
+ * Per pair the kernel gathers the 3*nwin stencil vertices from the granule's
+ * packed records, forms the gridded column in float64, reads the model column
+ * of the matched time slot, evaluates amf_recal.py:93-119,175-183 and writes
+ * staged[q][pair] for q = (vcd', sigma, model vcd, new amf, old amf).
+ * All descriptor arrays are device arrays; see DESIGN.md for the tile table. */
+typedef struct oisat_fused_args {
+  /* tile table */
+  int64_t n_tiles;
+  const int32_t* tile_granule;   /* [n_tiles] granule id                              */
+  const int32_t* tile_cell0;     /* [n_tiles] model cell index of lane 0 of the tile  */
+  const int64_t* tile_pair0;     /* [n_tiles] first pair of the tile                  */
+  const uint32_t* tile_mask;     /* [n_tiles] bit l set: cell0+l is a pair            */
+  /* per-pair stencil, PAIR-major: entry k of pair p at [p*3*nwin + k] */
+  int64_t n_pairs;
+  int32_t nwin;
+  const int32_t* vert;
+  const double* w;
+  double box_weight;             /* 1/(kx*ky)                                         */
+  double box_weight_err;         /* 1/(kx*ky)^2, variance of the window mean          */
+  /* per-granule tables, [n_granules] */
+  int32_t n_granules;
+  const int64_t* gran_record0;   /* first record (pixel) of the granule in `records`  */
+  const int64_t* gran_px0;       /* first pixel of the granule in good/amf            */
+  const int32_t* gran_slot;      /* matched model time slot                           */
+  /* pixel data */
+  const void* records;           /* packed float16 records                            */
+  const uint8_t* good;           /* [total px]                                        */
+  const void* amf;               /* [total px] */
+  int32_t amf_dtype;
+  int32_t n_sat_lev;
+  int32_t has_trop;
+  /* model fields, float32 [n_slots][n_ctm_lev][n_cell] */
+  const float* ctm_pmid;
+  const float* ctm_prof;
+  const float* ctm_dp;
+  int32_t n_ctm_lev;
+  int64_t n_cell;
+  /* output: staged[5][n_pairs] */
+  double* staged;
+} oisat_fused_args;
+
+int oisat_fused_amf(const oisat_fused_args* h_args, void* stream);
+
+/* ordered segmented reduction of the staged pair values into the accumulators:
+ * for model cell c the pairs seg_pair[seg_start[c] .. seg_start[c+1]) are listed
+ * in granule order, so the running sums equal numpy's sequential nanmean
+ * bit for bit (no floating-point atomics).  acc layout as oisat_accum_add. */
+int oisat_accum_pairs(double* acc, int64_t n_cell, const int64_t* seg_start,
+                      const int64_t* seg_pair, const double* staged, int64_t n_pairs,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OISAT_H_ */

@@ -1,0 +1,113 @@
+"""ctypes binding of liboisat.so (declared in include/oisat.h).
+
+The product path has no CPU fallback: if the shared library is missing the
+first call raises, loudly, with the build command.  Loading the library does
+not touch CUDA (static cudart initialises lazily), so importing this module in
+joblib worker processes or on a CPU-only box is safe.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "liboisat.so")
+
+F16, F32, F64, U8, I32 = 1, 2, 3, 4, 5
+OP_NONE, OP_SQUARE_NATIVE = 0, 1
+POST_NONE, POST_SQRT = 0, 1
+SRC_VALUE, SRC_PARTIAL_COLUMN, SRC_AIR_COLUMN = 0, 1, 2
+
+vp, i32, i64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+
+
+class Field(C.Structure):
+    """struct oisat_field"""
+    _fields_ = [("data", vp), ("dtype", i32), ("op", i32), ("post", i32), ("nlev", i32),
+                ("lev_stride", i64), ("box_weight", f64)]
+
+
+class FusedArgs(C.Structure):
+    """struct oisat_fused_args"""
+    _fields_ = [
+        ("n_tiles", i64), ("tile_granule", vp), ("tile_cell0", vp), ("tile_pair0", vp),
+        ("tile_mask", vp),
+        ("n_pairs", i64), ("nwin", i32), ("vert", vp), ("w", vp), ("box_weight", f64),
+        ("box_weight_err", f64),
+        ("n_granules", i32), ("gran_record0", vp), ("gran_px0", vp), ("gran_slot", vp),
+        ("records", vp), ("good", vp), ("amf", vp), ("amf_dtype", i32), ("n_sat_lev", i32),
+        ("has_trop", i32),
+        ("ctm_pmid", vp), ("ctm_prof", vp), ("ctm_dp", vp), ("n_ctm_lev", i32), ("n_cell", i64),
+        ("staged", vp),
+    ]
+
+
+# name -> (restype, argtypes); mirrors include/oisat.h one to one
+PROTOTYPES = {
+    "oisat_last_error": (C.c_char_p, []),
+    "oisat_abi_version": (C.c_int, []),
+    "oisat_launch_count": (i64, []),
+    "oisat_distmask": (C.c_int, [vp, vp, i32, i64, vp, i64, vp, i64, f64, vp, vp]),
+    "oisat_quality_mask": (C.c_int, [vp, i32, i64, f64, vp, vp]),
+    "oisat_interp_apply": (C.c_int, [vp, vp, i32, i64, vp, C.POINTER(Field), i32, vp, i64, vp, vp]),
+    "oisat_vertical_amf": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, i32,
+                                     i32, i64, vp, vp, vp, vp]),
+    "oisat_vertical_column": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, vp, vp]),
+    "oisat_vertical_mopitt": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, vp, vp, vp,
+                                        i32, i32, i64, vp, vp, vp]),
+    "oisat_vertical_gosat": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, i32, i64, vp, vp, i32, i32,
+                                       i64, vp, vp]),
+    "oisat_grid_resample": (C.c_int, [vp, vp, i32, i32, i32, i64, i64, i32, i32, f64, vp, vp, i64,
+                                      vp, i64, vp]),
+    "oisat_accum_add": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp]),
+    "oisat_accum_finalize": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp]),
+    "oisat_oi_prepare": (C.c_int, [vp, vp, vp, i64, f64, f64, f64, vp, vp, vp]),
+    "oisat_oi_sweep_workspace": (i64, [i64, i32]),
+    "oisat_oi_sweep": (C.c_int, [vp, vp, i64, C.POINTER(f64), i32, vp, vp, vp, i64, vp]),
+    "oisat_oi_apply": (C.c_int, [vp, vp, vp, vp, i64, f64, vp, vp, vp, vp, vp]),
+    "oisat_pack_record_halfs": (i64, [i32, i32]),
+    "oisat_pack_granule": (C.c_int, [vp, vp, i32, vp, vp, vp, i64, vp, vp]),
+    "oisat_fused_amf": (C.c_int, [C.POINTER(FusedArgs), vp]),
+    "oisat_accum_pairs": (C.c_int, [vp, i64, vp, vp, vp, i64, vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class OisatError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library (raises if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise OisatError(
+                "liboisat.so is missing (%s): the CUDA extension is the product path and there "
+                "is no CPU fallback.  Build it with `python -m oisatgmi_b200.csrc.build`."
+                % LIB_PATH)
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(h, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        if h.oisat_abi_version() != 1:
+            raise OisatError("liboisat ABI mismatch")
+        _lib = h
+        return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise OisatError("liboisat error %d: %s" % (rc, lib().oisat_last_error().decode()))
+
+
+def launch_count() -> int:
+    return int(lib().oisat_launch_count())

@@ -1,0 +1,152 @@
+"""Host side shared by the three vertical-operator drop-ins (amf_recal,
+ak_conv_mopitt, ak_conv_gosat): model time matching, device residency of the
+model fields, model -> satellite-grid resampling (K6) and the K3 launches.
+
+Only the cells with a finite retrieval are shipped to the device (compact
+level-major blocks, [nlev][n_valid]); results are scattered back into NaN-filled
+grids of the reference's shapes on the host.
+"""
+from __future__ import annotations
+
+import weakref
+
+import numpy as np
+
+from . import _dev, _lib, plan as _plan
+
+
+def flatten_time(t):
+    """YYYYMMDD.fraction-of-day (amf_recal.py:7-16)."""
+    return (t.year * 10000 + t.month * 100 + t.day + t.hour / 24.0 + t.minute / 60.0 / 24.0
+            + t.second / 3600.0 / 24.0)
+
+
+def hour_only_time(t):
+    """Fraction of the day (amf_recal.py:18-24)."""
+    return t.hour / 24.0 + t.minute / 60.0 / 24.0 + t.second / 3600.0 / 24.0
+
+
+def ctm_clock(ctm_data):
+    stamps, fracs = [], []
+    for c in ctm_data:
+        stamps.extend(flatten_time(t) for t in c.time)
+        fracs.extend(hour_only_time(t) for t in c.time)
+    return np.array(stamps), np.array(fracs)
+
+
+def closest_slot(ctm_data, stamps, fracs, t_sat):
+    """(flat index, day, hour) of the model slot nearest to the overpass
+    (amf_recal.py:26-37): nearest hour of day for a monthly-mean model, nearest
+    YYYYMMDD.frac stamp otherwise."""
+    if not ctm_data[0].averaged:
+        k = int(np.argmin(np.abs(flatten_time(t_sat) - stamps)))
+        return k, int(np.floor(k / 8.0)), int(k % 8)
+    k = int(np.argmin(np.abs(hour_only_time(t_sat) - fracs)))
+    return k, 0, k
+
+
+def closest_day(ctm_data, stamps, t_sat):
+    """ak_conv_mopitt.py:41-52: day-resolution match (hours ignored)."""
+    if ctm_data[0].averaged == False:  # noqa: E712
+        stamp = t_sat.year * 10000 + t_sat.month * 100 + t_sat.day
+        k = int(np.argmin(np.abs(stamp - stamps)))
+        return k, int(np.floor(k))
+    return 0, 0
+
+
+class _DeviceCache:
+    """Model fields stay on the device while the numpy array they came from is
+    alive (keyed by id + a weak reference guard)."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, arr: np.ndarray, tag, make):
+        key = (id(arr), tag)
+        hit = self._store.get(key)
+        if hit is not None and hit[0]() is arr:
+            return hit[1]
+        val = make()
+        try:
+            ref = weakref.ref(arr)
+        except TypeError:
+            return val
+        self._store[key] = (ref, val)
+        if len(self._store) > 64:
+            self._store = {k: v for k, v in self._store.items() if v[0]() is not None}
+        return val
+
+
+_cache = _DeviceCache()
+
+
+def clear_cache():
+    _cache._store.clear()
+
+
+def ctm_slot_device(field4d_or_3d: np.ndarray, slot):
+    """One (nlev, ny*nx) float32 slab of a model field on the device."""
+    def make():
+        a = field4d_or_3d if slot is None else field4d_or_3d[slot]
+        a = np.asarray(a).squeeze()
+        if a.dtype != np.float32:
+            a = a.astype(np.float64)
+        return _dev.to_device(np.ascontiguousarray(a).reshape(a.shape[0], -1))
+    return _cache.get(field4d_or_3d, ("slot", slot), make)
+
+
+def ctm_time_mean_device(field4d: np.ndarray):
+    """np.nanmean over the time axis (ak_conv_mopitt.py:69-77), computed once."""
+    def make():
+        m = np.nanmean(field4d, axis=0).squeeze()
+        return _dev.to_device(np.ascontiguousarray(m).reshape(m.shape[0], -1))
+    return _cache.get(field4d, ("tmean",), make)
+
+
+def resample_to_sat(requests, ctm_data, granule):
+    """K6: model fields -> satellite grid (amf_recal.py:58-83,
+    ak_conv_mopitt.py:79-110).  `requests` is a list of (src, src2, op) with
+    device [nlev][ny*nx] tensors; op selects the value itself, the float32
+    partial column of (delta_p, profile) or the float32 air column of delta_p.
+    Outputs float64 [nlev][n_sat] device tensors."""
+    L = _lib.lib()
+    sat = {"Longitude": granule.longitude_center, "Latitude": granule.latitude_center}
+    dlon_s, dlat_s = _plan.grid_spacing(sat)
+    thr = np.sqrt(dlon_s ** 2 + dlat_s ** 2)
+    clon, clat = ctm_data[0].longitude, ctm_data[0].latitude
+    dlon_c, dlat_c = _plan.grid_spacing({"Longitude": clon, "Latitude": clat})
+    gs = np.sqrt(dlon_c ** 2 + dlat_c ** 2)
+    if not ((dlon_s >= gs) or (dlat_s >= gs)):
+        # _upscaler's pass-through branch: the reference would then try to store a
+        # model-shaped array into a satellite-shaped one and raise
+        raise ValueError("model grid cannot be resampled to a finer satellite grid")
+    ky, kx = _plan.box_extent(dlon_s, dlat_s, gs)
+    d, idx = _plan.nearest_node_table(clon, clat, sat["Longitude"], sat["Latitude"])
+    ok = ~(d > thr * 2.0)
+    nn = _cache.get(idx, ("nn",), lambda: _dev.to_device(idx.astype(np.int32)))
+    okd = _dev.to_device(ok.astype(np.uint8))
+    H, W = clon.shape
+    outs = []
+    for src, src2, op in requests:
+        nlev = src.shape[0]
+        out = _dev.empty((nlev, idx.size))
+        _lib.check(L.oisat_grid_resample(src.data_ptr(), _dev.ptr(src2), op, _dev.dtype_code(src),
+                                         nlev, H, W, ky, kx, 1.0 / (kx * ky), nn.data_ptr(),
+                                         okd.data_ptr(), idx.size, out.data_ptr(), idx.size,
+                                         _dev.stream()))
+        outs.append(out)
+    return outs
+
+
+def compact(arr, valid_flat, nlev=None):
+    """Columns of the valid cells as a contiguous float64 [nlev][n_valid] block."""
+    a = np.asarray(arr, dtype=np.float64)
+    if nlev is None:
+        return np.ascontiguousarray(a.reshape(-1)[valid_flat])
+    return np.ascontiguousarray(a.reshape(nlev, -1)[:, valid_flat])
+
+
+def scatter(shape, valid_flat, values):
+    out = np.full(int(np.prod(shape)), np.nan)
+    out[valid_flat] = values
+    return out.reshape(shape)

@@ -1,0 +1,84 @@
+"""Orchestration glue on the hot path: the `oisatgmi` class of
+/root/reference/oisatgmi/driver.py:17-114 with the same method names and
+attributes (`recal_amf`, `conv_ak`, `average`, `bias_correct`, `oi`), wired to
+the GPU drop-ins.  File I/O (`read_data`, driver.py:22-34), reporting and NetCDF
+output are out of scope: `read_data`
+delegates to the reference's own reader when that package is importable, and
+`attach` accepts an in-memory reader object (anything with `.ctm_data` and
+`.sat_data`), which is what the tests and bench.py use.
+"""
+from __future__ import annotations
+
+from .ak_conv_gosat import ak_conv_gosat
+from .ak_conv_mopitt import ak_conv_mopitt
+from .amf_recal import amf_recal
+from .averaging import averaging
+from .optimal_interpolation import OI
+
+# validation-based affine corrections y -> (y - a) / b, driver.py:65-106
+BIAS_CORRECTION = {
+    ("TROPOMI", "NO2"): (0.32, 0.66),
+    ("TROPOMI", "HCHO"): (0.90, 0.59),
+    ("OMI", "NO2"): (0.32, 0.63),
+    ("OMI", "HCHO"): (0.821, 0.79),
+}
+
+
+class oisatgmi(object):
+
+    def __init__(self) -> None:
+        pass
+
+    def attach(self, reader_obj, gasname: str):
+        self.reader_obj = reader_obj
+        self.gasname = gasname
+
+    def read_data(self, ctm_type, ctm_path, ctm_gas_name, ctm_frequency, sat_type, sat_path,
+                  YYYYMM, averaging=False, read_ak=True, trop=False, num_job=1, mcip_dir=None,
+                  tempo_hour=None):
+        try:
+            from oisatgmi.reader import readers  # the reference's file readers
+        except Exception as exc:  # netCDF4/h5py are not part of this package
+            raise RuntimeError(
+                "file readers are outside the accelerated hot path; install the reference "
+                "package for read_data(), or hand in-memory data to attach()") from exc
+        reader_obj = readers()
+        reader_obj.add_ctm_data(ctm_type, ctm_path, mcip_dir=mcip_dir)
+        reader_obj.read_ctm_data(YYYYMM, ctm_gas_name, frequency_opt=ctm_frequency,
+                                 averaging=averaging, num_job=num_job)
+        reader_obj.add_satellite_data(sat_type, sat_path)
+        reader_obj.read_satellite_data(YYYYMM, read_ak=read_ak, trop=trop, num_job=num_job,
+                                       tempo_hour=tempo_hour)
+        self.reader_obj = reader_obj
+        self.gasname = ctm_gas_name[0]
+
+    def recal_amf(self):
+        self.reader_obj.sat_data = amf_recal(self.reader_obj.ctm_data, self.reader_obj.sat_data)
+
+    def conv_ak(self, sensor: str):
+        if sensor == 'MOPITT':
+            self.reader_obj.sat_data = ak_conv_mopitt(self.reader_obj.ctm_data,
+                                                      self.reader_obj.sat_data)
+        if sensor == 'GOSAT':
+            self.reader_obj.sat_data = ak_conv_gosat(self.reader_obj.ctm_data,
+                                                     self.reader_obj.sat_data)
+
+    def average(self, startdate: str, enddate: str, gasname=None):
+        (self.sat_averaged_vcd, self.sat_averaged_error, self.ctm_averaged_vcd, self.aux1,
+         self.aux2, self.avg_time) = averaging(startdate, enddate, self.reader_obj)
+        if gasname == 'O3':
+            self.ctm_averaged_vcd = self.ctm_averaged_vcd / (2.69e16 * 1e-15)  # driver.py:62-63
+
+    def bias_correct(self, sat_type, gasname):
+        if (sat_type, gasname) in BIAS_CORRECTION:
+            a, b = BIAS_CORRECTION[(sat_type, gasname)]
+            self.sat_averaged_vcd = (self.sat_averaged_vcd - a) / b
+
+    def oi(self, sensor: str, error_ctm=50.0):
+        if sensor != 'GOSAT':
+            xa, y = self.ctm_averaged_vcd, self.sat_averaged_vcd
+        else:
+            xa, y = self.aux2, self.aux1  # driver.py:113-114
+        (self.ctm_averaged_vcd_corrected, self.ak_OI, self.increment_OI, self.error_OI) = OI(
+            xa, y, (xa * error_ctm / 100.0) ** 2, self.sat_averaged_error ** 2,
+            regularization_on=True)

@@ -157,11 +157,12 @@ OMI_NO2_PRESSURES = np.array(
 # (reader.py:954-957); regenerated here analytically to the same shape: the
 # synthetic generator only needs a monotone 48-edge hybrid table.
 def _hybrid_table(nedge, ptop=0.01):
+    """Monotone hybrid table: p_k = a_k + b_k * ps, surface (b=1, a=0) to a pure
+    pressure top (b=0, a=ptop); strictly positive and decreasing for any ps."""
     k = np.arange(nedge, dtype=np.float64) / (nedge - 1)
-    b = np.clip(1.0 - 1.55 * k, 0.0, None) ** 1.3
-    b[0] = 1.0
-    a = 230.0 * np.sin(np.pi * np.clip(k * 1.05, 0, 1)) ** 1.5 * (1.0 - b)
-    a[-1] = ptop
+    b = np.clip(1.0 - k / 0.65, 0.0, None) ** 1.3
+    p_ref = 1000.0 * np.exp(-k * np.log(1000.0 / ptop))
+    a = (1.0 - b) * p_ref
     return a, b
 
 
@@ -251,7 +252,10 @@ def make_mopitt_granule(seed, fill_fraction=0.4, time=None, region=None):
     vcd[~stripe] = np.nan
     vcd16 = vcd.astype(np.float16)
     dry = 2.1e25 * (1.0 + 0.02 * _smooth2d(rng, shape, scale=2.0))
-    x_col = (1e6 * vcd16 / (dry * 1e-15)).astype(np.float32)
+    with np.errstate(over="ignore", invalid="ignore"):
+        # as in reader.py:1167 the product is formed in float16 and overflows to
+        # inf: MOPITT's x_col is not a usable quantity in the reference either
+        x_col = (1e6 * vcd16 / (dry * 1e-15)).astype(np.float32)
     L = 9
     press = np.array([900.0, 800.0, 700.0, 600.0, 500.0, 400.0, 300.0, 200.0, 100.0])
     p_mid = np.broadcast_to(press.astype(np.float16)[:, None, None], (L,) + shape).copy()

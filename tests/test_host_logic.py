@@ -1,0 +1,144 @@
+"""Host-side logic that needs no GPU: geometry-plan composition, the knee
+selector, time matching, pair/tile tables, and the C-ABI surface."""
+import os
+import re
+import ctypes
+
+import numpy as np
+import pytest
+
+import cases
+import emu
+from oisatgmi_b200 import _lib, kneedle, plan, synth
+from util import assert_field
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ----------------------------------------------------------------- C-ABI surface
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "oisat.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(oisat_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_functions()
+    assert len(names) >= 20
+    h = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(h, n)]
+    assert not missing, missing
+    assert set(names) == set(_lib.PROTOTYPES), sorted(set(names) ^ set(_lib.PROTOTYPES))
+    L = _lib.lib()   # loading and the calls below need no GPU
+    assert L.oisat_abi_version() == 1
+    assert L.oisat_pack_record_halfs(47, 0) == 96
+    assert L.oisat_pack_record_halfs(35, 1) == 80
+    assert L.oisat_oi_sweep_workspace(207936, 99) > 0
+
+
+def test_bad_arguments_are_reported_not_crashed():
+    L = _lib.lib()
+    rc = L.oisat_distmask(None, None, _lib.F32, 10, None, 4, None, 4, 0.5, None, None)
+    assert rc == -1 and b"null pointer" in L.oisat_last_error()
+    with pytest.raises(_lib.OisatError):
+        _lib.check(rc)
+
+
+def test_no_cuda_no_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from oisatgmi_b200 import optimal_interpolation
+    a = np.ones((4, 4))
+    with pytest.raises(_lib.OisatError):
+        optimal_interpolation.OI(a.copy(), a.copy(), a.copy(), a.copy())
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.Field) == 40
+    # oisat_fused_args: see include/oisat.h; natural alignment, no packing
+    assert ctypes.sizeof(_lib.FusedArgs) % 8 == 0
+    assert _lib.FusedArgs.box_weight_err.offset == _lib.FusedArgs.box_weight.offset + 8
+
+
+# ------------------------------------------------------------------ geometry plan
+@pytest.mark.parametrize("name", ["omi_no2", "tropomi_no2"])
+def test_plan_reproduces_oracle_gridding(name):
+    from oracle import interp as ointerp
+    c = cases.amf_case(name)
+    g = c["granules"][0]
+    o = ointerp.interpolator(1, c["grid_size"], cases.clone(g), c["coords"],
+                             flag_thresh=c["flag_thresh"])
+    gpl = plan.grid_plan(c["coords"], c["grid_size"])
+    keep = emu.distmask(g.longitude_center, g.latitude_center, gpl, 2 * c["grid_size"])
+    gp = plan.granule_plan(g.longitude_center, g.latitude_center, gpl, 2 * c["grid_size"],
+                           keep=keep, cache=False)
+    good = (g.quality_flag > c["flag_thresh"]).ravel()
+    f64 = lambda a: np.asarray(a).astype(np.float64).ravel()  # noqa: E731
+    assert_field(emu.apply_stencil(gp, f64(g.vcd), good), o.vcd, "vcd", rtol=1e-14)
+    assert_field(emu.apply_stencil(gp, f64(g.uncertainty ** 2), good, error=True), o.uncertainty,
+                 "uncertainty", rtol=1e-14)
+    assert_field(emu.apply_stencil(gp, f64(g.scattering_weights[3]), good),
+                 o.scattering_weights[3], "sw[3]", rtol=1e-14)
+    # restricted point location (only nodes K0 keeps) gives the same plan as the full walk
+    old = plan.FULL_WALK_MAX_NODES
+    try:
+        plan.FULL_WALK_MAX_NODES = 0
+        gp2 = plan.granule_plan(g.longitude_center, g.latitude_center, gpl, 2 * c["grid_size"],
+                                keep=keep, cache=False)
+    finally:
+        plan.FULL_WALK_MAX_NODES = old
+    assert np.array_equal(gp.cells, gp2.cells) and np.array_equal(gp.vert, gp2.vert)
+    assert np.array_equal(gp.w, gp2.w)
+
+
+def test_box_window_matches_convolve2d():
+    from scipy import signal
+    rng = np.random.default_rng(0)
+    Z = rng.standard_normal((9, 11))
+    for ky, kx in [(2, 2), (5, 6), (1, 3), (1, 1)]:
+        ref = signal.convolve2d(Z, np.ones((ky, kx)) / (ky * kx), boundary="symm", mode="same")
+        node = np.arange(Z.size)
+        win = plan.box_window(9, 11, node, ky, kx)
+        got = Z.ravel()[win].mean(axis=1).reshape(Z.shape)
+        np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-15)
+
+
+def test_degenerate_granule_returns_none():
+    gpl = plan.grid_plan(cases.coords(), 0.25)
+    lon = np.linspace(-100, -90, 12).astype(np.float32)   # collinear: Qhull raises
+    lat = np.full(12, 40.0, np.float32)
+    keep = emu.distmask(lon, lat, gpl, 0.5)
+    assert plan.granule_plan(lon, lat, gpl, 0.5, keep=keep, cache=False) is None
+
+
+# ------------------------------------------------------------------------- knee
+def test_kneedle_matches_oracle_restatement():
+    from oracle.kneedle import KneeLocator
+    rng = np.random.default_rng(5)
+    x = np.arange(0.1, 10, 0.1)
+    for trial in range(200):
+        a = rng.uniform(0.05, 5.0)
+        y = x / (x + a) * rng.uniform(0.2, 1.0) + rng.uniform(0, 0.2)
+        if trial % 3 == 0:
+            y = y + rng.normal(0, 1e-3, y.shape)      # wiggles: several local maxima
+        want = KneeLocator(x, y, direction="increasing").knee
+        got = kneedle.knee_increasing_concave(x, y)
+        assert (want is None and got is None) or want == got
+        idx = kneedle.knee_index(x, y)
+        assert idx == (0 if want is None else int(np.argwhere(x == want)[0][0]))
+    assert kneedle.knee_increasing_concave(x, np.full_like(x, np.nan)) is None
+
+
+# ----------------------------------------------------------------- time matching
+def test_time_matching_follows_reference_rules():
+    import datetime as dt
+    from oisatgmi_b200 import _vertical as v
+    ctm = cases.ctm()
+    stamps, fracs = v.ctm_clock(ctm)
+    k, day, hour = v.closest_slot(ctm, stamps, fracs, dt.datetime(2005, 6, 9, 13, 40))
+    assert (day, hour) == (0, 4)      # slots at 01:30, 04:30, ... -> 13:30 is index 4
+    ctm[0].averaged = False
+    k, day, hour = v.closest_slot(ctm, stamps, fracs, dt.datetime(2005, 6, 1, 23, 0))
+    assert (day, hour) == (0, 7)
+    assert v.closest_day(ctm, stamps, dt.datetime(2005, 6, 20))[1] == 7  # day stamp vs slot stamps
