@@ -94,7 +94,7 @@ class MonthPipeline:
         g.has_trop = np.size(sat.tropopause) != 1
         up = lambda a: _dev.to_device(np.ascontiguousarray(a).reshape(-1), pin=pin)  # noqa: E731
         g.dev = {
-            "lon": up(_dev.native_float(lon)), "lat": up(_dev.native_float(lat)),
+            "lon": up(_plan.coord_array(lon)), "lat": up(_plan.coord_array(lat)),
             "vcd": up(sat.vcd), "sigma": up(sat.uncertainty),
             "amf": up(_dev.native_float(np.asarray(sat.amf))),
             "qflag": up(_dev.native_float(np.asarray(sat.quality_flag).squeeze())),

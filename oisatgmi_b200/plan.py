@@ -207,6 +207,15 @@ class GranulePlan:
         return self._dev
 
 
+def coord_array(a):
+    """Pixel coordinates for K0: float32/float64 as delivered, anything else
+    (e.g. the filler's float16 mesh) widened exactly to float64."""
+    a = np.asarray(a)
+    if a.dtype not in (np.float32, np.float64):
+        a = a.astype(np.float64)
+    return np.ascontiguousarray(a).ravel()
+
+
 def triangulate(lon, lat):
     pts = np.zeros((np.size(lat), 2))
     pts[:, 0] = np.asarray(lon).flatten()
@@ -248,8 +257,7 @@ def granule_plan(lon, lat, gplan: GridPlan, radius: float, lonlat_dev=None, cach
     keep_dev = None
     if keep is None:
         if lonlat_dev is None:
-            lonlat_dev = (_dev.to_device(_dev.native_float(lon).ravel()),
-                          _dev.to_device(_dev.native_float(lat).ravel()))
+            lonlat_dev = (_dev.to_device(coord_array(lon)), _dev.to_device(coord_array(lat)))
         keep_dev = distance_mask(lonlat_dev[0], lonlat_dev[1], gplan, radius)  # async
     try:
         tri = triangulate(lon, lat)  # Qhull runs while K0 is in flight
@@ -279,8 +287,9 @@ def granule_plan(lon, lat, gplan: GridPlan, radius: float, lonlat_dev=None, cach
         cells = np.flatnonzero(valid)
         nodes = cells[:, None]
     sel = pos[nodes]                              # (n, nwin)
-    vert = np.ascontiguousarray(verts[sel].reshape(len(cells), -1).T)   # (3*nwin, n)
-    w = np.ascontiguousarray(wts[sel].reshape(len(cells), -1).T)
+    S = 3 * gplan.nwin
+    vert = np.ascontiguousarray(verts[sel].reshape(len(cells), S).T)   # (3*nwin, n)
+    w = np.ascontiguousarray(wts[sel].reshape(len(cells), S).T)
     plan = GranulePlan(gplan, cells, vert.astype(np.int32), w, keep)
     if cache:
         _granule_plans[key] = plan

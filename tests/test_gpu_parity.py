@@ -22,7 +22,8 @@ def _compare(store, want, tight=()):
     worst = {}
     for k in keys:
         rtol = 1e-12 if k.startswith(tight) else RTOL_FP64
-        assert_field(store[k], want[k], k, rtol=rtol)
+        scale = want["avg.ctm_vcd"] if k.endswith(("increment_OI", ".inc")) else None
+        assert_field(store[k], want[k], k, rtol=rtol, scale=scale)
         worst[k.split(".")[0]] = max(worst.get(k.split(".")[0], 0.0), max_rel(store[k], want[k]))
     return worst
 
@@ -127,7 +128,9 @@ def test_accumulator_matches_numpy_nanmean_bit_for_bit():
 
 def test_constant_field_and_unit_weights_properties():
     """Known answers: a constant field grids to the same constant; SW == 1 gives
-    AMF == 1 exactly; So -> inf returns the prior."""
+    AMF == 1 up to the float32 rounding of the reference's column sum
+    (amf_recal.py:116: the denominator is a float32 nansum, the numerator a
+    float64 one); So -> inf returns the prior."""
     from oisatgmi_b200 import amf_recal, interpolator, optimal_interpolation as oi
     c = cases.amf_case("omi_no2")
     g = cases.clone(c["granules"][0])
@@ -139,7 +142,7 @@ def test_constant_field_and_unit_weights_properties():
     assert np.max(np.abs(r.scattering_weights[:, f] - 1.0)) < 1e-14
     out = amf_recal.amf_recal(c["ctm"], [r])[0]
     f = np.isfinite(out.new_amf)
-    assert f.sum() > 200 and np.max(np.abs(out.new_amf[f] - 1.0)) < 1e-12
+    assert f.sum() > 200 and np.max(np.abs(out.new_amf[f] - 1.0)) < 5e-7
     xa = np.full((5, 5), 3.0)
     res = oi.OI(xa.copy(), xa * 2, (xa * 0.5) ** 2, np.full((5, 5), np.inf), regularization_on=False)
     assert np.array_equal(res[0], xa)
