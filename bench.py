@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""Benchmark of the OI-SAT-GMI hot path on B200 (contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): OMI HCHO, one month, AMF recalculation from
+scattering weights, OI against the 0.5 x 0.625 x 72 GMI grid.  Synthetic
+OMI-shaped granules (1644 x 60 px, 47 levels, reader dtypes) on `--days` x
+`--orbits` orbits (default 29 x 15 = 435 granules, 42.9 M px, 9.3 GB of reader
+arrays resident in HBM -- far larger than the 126 MB L2, so no flush is needed).
+The 15 orbit geometries/fields of one day are generated once and re-used for the
+other days (distinct device buffers, distinct time stamps); the GPU work per
+granule is unchanged, only host-side generation time is saved.
+
+A "step" = one pass of the whole month: quality mask + pixel-major packing of
+every granule, the fused gather-interpolate + AMF kernel, the ordered
+accumulation, (all-reduce when N > 1), means, bias correction, the 99-factor OI
+sweep, the knee on the host and the OI update.  `value` = L2 pixels / s with the
+reader arrays and the geometry plans already in HBM.  `e2e` = the same metric
+for one DAY batch from host memory, everything included: geometry plans built
+from scratch (K0 on the GPU, Qhull + walk on all host cores), pinned host ->
+device copies of the reader arrays, all kernels, device -> host copy of the
+gridded results.
+"""
+from __future__ import annotations
+
+import argparse
+import datetime
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P_OMI = 1644 * 60
+GRID_SIZE = 0.25
+FLAG_THRESH = 0.0
+PRODUCT = "OMI_HCHO"
+N_LEV = 47
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--days", type=int, default=29)
+    ap.add_argument("--orbits", type=int, default=15)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------- workload
+def orbit_geo(i, n_orbits):
+    """Equator-crossing longitudes of the day's orbits (24.7 degrees apart)."""
+    return dict(node_lon_deg=150.0 - i * (360.0 / 14.6))
+
+
+def make_day(seed0, n_orbits):
+    from oisatgmi_b200 import synth
+    grans = []
+    for i in range(n_orbits):
+        t = datetime.datetime(2005, 6, 1) + datetime.timedelta(seconds=1800 + i * 5933)
+        grans.append(synth.make_amf_granule(seed0 + i, PRODUCT, geo=orbit_geo(i, n_orbits),
+                                            bad_fraction=0.2, time=t))
+    return grans
+
+
+def make_model(seed=11):
+    from oisatgmi_b200 import synth
+    return [synth.make_ctm(seed, synth.ctm_coordinates(), averaged=True)]
+
+
+# ----------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 - 0.15 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(np.max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------- CPU reference
+def _cpu_sample(seed, level_counts=(1, 3)):
+    """One OMI HCHO granule through the oracle port (= the reference's algorithm)
+    with a reduced number of levels, timed; the per-field cost is constant
+    (every field goes through the same LinearNDInterpolator + convolve2d +
+    KD-tree calls, interpolator.py:162-209), so two level counts give the fixed
+    and the per-field cost and the full 97-field granule is their extrapolation."""
+    import copy
+    from oisatgmi_b200 import synth
+    from oracle import averaging as oavg, interp as ointerp, oi as ooi, vertical as overt
+    import types
+    coords = synth.ctm_coordinates()
+    model = [synth.make_ctm(11, coords, nslots=1, averaged=True)]
+    g = synth.make_amf_granule(seed, PRODUCT, geo=orbit_geo(seed % 15, 15), bad_fraction=0.2)
+    times, fields = [], []
+    last = None
+    for lv in level_counts:
+        h = copy.deepcopy(g)
+        h.pressure_mid = h.pressure_mid[:lv]
+        h.scattering_weights = h.scattering_weights[:lv]
+        t0 = time.perf_counter()
+        last = ointerp.interpolator(1, GRID_SIZE, h, coords, flag_thresh=FLAG_THRESH)
+        times.append(time.perf_counter() - t0)
+        fields.append(3 + 2 * lv)
+    per_field = (times[1] - times[0]) / (fields[1] - fields[0])
+    fixed = times[0] - fields[0] * per_field
+    interp_full = fixed + (3 + 2 * N_LEV) * per_field
+    t0 = time.perf_counter()
+    overt.amf_recal(model, [last])
+    t_amf = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    avg = oavg.averaging("2005-06-01", "2005-07-01", types.SimpleNamespace(sat_data=[last]))
+    t_avg = time.perf_counter() - t0          # per-granule share of the temporal mean
+    t0 = time.perf_counter()
+    xa = np.array(avg[2])
+    ooi.OI(xa, np.array(avg[0]), (xa * 0.5) ** 2, np.array(avg[1]) ** 2)
+    t_oi = (time.perf_counter() - t0) / 435.0  # one OI per month of 435 granules
+    return dict(measured_s=sum(times) + t_amf + t_avg, interp_full_s=interp_full, amf_s=t_amf,
+                avg_s=t_avg, oi_s=t_oi, per_field_s=per_field, fixed_s=fixed)
+
+
+def cpu_baseline(workers=1, seed0=100):
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    if workers <= 1:
+        parts = [_cpu_sample(seed0)]
+    else:
+        with mp.get_context("spawn").Pool(workers) as pool:
+            parts = pool.map(_cpu_sample, [seed0 + i for i in range(workers)])
+    wall = time.perf_counter() - t0
+    per_granule = float(np.mean([p["interp_full_s"] + p["amf_s"] + p["avg_s"] + p["oi_s"]
+                                 for p in parts]))
+    value = workers * P_OMI / per_granule
+    return {"value": value, "unit": "px/s", "cores": workers, "kind": "port",
+            "sample": ("%d OMI HCHO granule(s) (98,640 px, global 361x576 grid), one per core, through "
+                       "oracle/ (numpy/scipy restatement of the reference): gridding timed with 1 and "
+                       "3 of the 47 levels (5 and 9 of 97 fields) and extrapolated linearly in the "
+                       "field count, + amf_recal + per-granule share of averaging and OI; "
+                       "%.1f s of CPU wall time, %.1f s per full granule per core"
+                       % (workers, wall, per_granule))}, wall
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workers = os.cpu_count() or 1
+    vals = []
+    t_all = time.perf_counter()
+    for step in range(args.warmup + args.steps):
+        if step < args.warmup and step > 0:
+            continue  # one warm-up pass is enough to page the libraries in
+        base, wall = cpu_baseline(workers, seed0=100 + 17 * step)
+        if step >= args.warmup:
+            vals.append(base["value"])
+        if time.perf_counter() - t_all > 420 and vals:
+            break
+    value = float(np.mean(vals))
+    base["value"] = value
+    line = {"impl": "reference", "metric": "L2 pixels/sec through interp+AMF+grid+OI",
+            "value": value, "unit": "px/s", "n_gpus": args.gpus, "steps": len(vals),
+            "warmup": args.warmup, "ms_per_step": 1e3 * workers * P_OMI / value,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "OMI HCHO one-month OI with AMF recalculation (configs[1]); "
+                                   "bounded sample: one granule per host core per step"},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": "px/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------- B200 arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    import torch
+    from oisatgmi_b200 import _dev, _lib, plan as _plan
+    from oisatgmi_b200.pipeline import MonthPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        pg = dist.group.WORLD
+    t_setup = time.perf_counter()
+    model = make_model()
+    day = make_day(1000 * rank, args.orbits)
+
+    def new_pipe():
+        return MonthPipeline(model, GRID_SIZE, FLAG_THRESH, sensor="OMI", gas="HCHO",
+                             error_ctm=50.0, process_group=pg)
+
+    pipe = new_pipe()
+    hosts = [MonthPipeline.host_arrays(g, pin=True) for g in day]
+    lons = [np.asarray(g.longitude_center) for g in day]
+    lats = [np.asarray(g.latitude_center) for g in day]
+    t0 = time.perf_counter()
+    plans = _plan.granule_plans(lons, lats, pipe.gplan, GRID_SIZE * 2.0)
+    plan_build_s = time.perf_counter() - t0
+    import copy
+    for d in range(args.days):
+        for i, g in enumerate(day):
+            gg = copy.copy(g)
+            gg.time = g.time + datetime.timedelta(days=d)
+            pipe.add_granule(gg, plan=plans[i], host=hosts[i])
+    pipe.upload_ctm()
+    pipe.build_tables()
+    pipe.allocate()
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
+    n_px = pipe.n_pixels()
+    host_t, _ = pipe.build_tables()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        pipe.run()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = _lib.launch_count()
+    marks_all = []
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        marks = []
+        res = pipe.run(marks)
+        marks_all.append(marks)
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = _lib.launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        import torch.distributed as dist
+        tmax = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_total = float(tmax.item())
+        npx = torch.tensor([float(n_px)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(npx)
+        n_px_all = int(npx.item())
+    else:
+        n_px_all = n_px
+    clocks = sampler.stop(t_wall0, t_wall1)
+    ms_step = ms_total / args.steps
+    value = n_px_all / (ms_step * 1e-3)
+
+    # per-phase device times (CUDA events on the launching stream)
+    phase = {}
+    for marks in marks_all:
+        for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+            phase.setdefault(n1, []).append(e0.elapsed_time(e1))
+    phase_ms = {k: float(np.mean(v)) for k, v in phase.items()}
+
+    # roofline of the dominant kernel (oisat_fused_amf): its own algorithmic bytes
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    g0 = pipe.granules[0]
+    rec_bytes = 2 * (2 * N_LEV + 2)            # float16 rows of one pixel (SW, p, vcd, sigma)
+    px_bytes = rec_bytes + 8 + 1               # + amf (f64) + quality byte
+    pair_bytes = 3 * 72 * 4 + 5 * 8            # model column (3 x 72 f32) + 5 staged f64
+    n_pairs = host_t["n_pairs"]
+    fused_bytes = n_px * px_bytes + n_pairs * pair_bytes
+    fused_ms = phase_ms.get("fused", float("nan"))
+    achieved = fused_bytes / (fused_ms * 1e-3) / 1e9
+    # whole-pipeline view with SURVEY.md section 8d's per-pixel figure (427 B/px for OMI HCHO)
+    pipe_bytes_px = 216 + (n_pairs / n_px) * (864 + 160) + 207936 * 14 * 8 / n_px
+    roofline = {"bound": "hbm", "kernel": "fused_amf_kernel", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else
+                               "fallback 6650 GB/s (of fallback)",
+                "traffic": None,
+                "algorithmic_bytes_per_launch": fused_bytes,
+                "kernel_ms": fused_ms,
+                "pipeline": {"bytes_per_px": pipe_bytes_px,
+                             "achieved_GBps": pipe_bytes_px * value / 1e9,
+                             "frac_of_measured": pipe_bytes_px * value / 1e9 / peak,
+                             "frac_of_nominal_8TBps": pipe_bytes_px * value / 1e9 / 8000.0},
+                "phase_ms": phase_ms}
+
+    # ------------------------------------------------------------------ e2e
+    e2e = None
+    if not args.no_e2e:
+        e2e_times, h2d, d2h = [], 0, 0
+        for it in range(args.e2e_steps + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            p2 = new_pipe()
+            dev = _dev.device()
+            lonlat_dev = [(h["lon"].to(dev, non_blocking=True), h["lat"].to(dev, non_blocking=True))
+                          for h in hosts]
+            day_plans = _plan.granule_plans(lons, lats, p2.gplan, GRID_SIZE * 2.0,
+                                            lonlat_dev=lonlat_dev)
+            for i, g in enumerate(day):
+                p2.add_granule(g, plan=day_plans[i], host=hosts[i])   # H2D from pinned memory
+            out = p2.results_to_host(p2.run())                        # D2H of the gridded results
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if it > 0:
+                e2e_times.append(dt)
+            h2d = p2.input_bytes() + p2.plan_bytes()
+            d2h = sum(v.nbytes for v in out.values() if hasattr(v, "nbytes"))
+            day_px = p2.n_pixels()
+            del p2
+        e2e_s = float(np.mean(e2e_times))
+        e2e_val = day_px / e2e_s
+        if world > 1:
+            import torch.distributed as dist
+            tv = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+            e2e_val = day_px * world / float(tv.item())
+        e2e = {"value": e2e_val, "unit": "px/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h),
+               "batch": "one day = %d granules from pinned host memory; includes geometry-plan "
+                        "construction (K0 on GPU, Qhull + point location on %d host cores), H2D, all "
+                        "kernels, D2H of 9 gridded outputs" % (len(day), os.cpu_count() or 1),
+               "s_per_step": e2e_s, "steps": len(e2e_times)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, _ = cpu_baseline(1)
+
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": "L2 pixels/sec through interp+AMF+grid+OI", "value": value, "unit": "px/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "OMI HCHO one-month OI with AMF recalculation from scattering weights "
+                               "(BASELINE configs[1]): %d granules x 98,640 px x 47 levels per GPU, "
+                               "GMI 361x576x72 grid, 8 model slots" % len(pipe.granules),
+                   "granules_per_gpu": len(pipe.granules), "pixels_per_gpu": n_px,
+                   "pairs_per_gpu": int(n_pairs), "l2": "inputs_larger_than_L2 (%.1f GB resident)"
+                   % (pipe.input_bytes() / 1e9), "geometry_plan": "cached in HBM for `value`, rebuilt "
+                   "inside `e2e`", "plan_build_s_for_%d_geometries" % len(day): plan_build_s,
+                   "host_cores": os.cpu_count(), "setup_s": setup_s,
+                   "knee_index": int(res["knee_index"])},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -207,6 +207,35 @@ int oisat_pack_granule(const void* sw, const void* p_mid, int32_t n_sat_lev,
                        const void* vcd, const void* sigma, const void* trop /* may be NULL */,
                        int64_t n_px, void* records, void* stream);
 
+/* a whole batch of granules in ONE launch, quality mask included: a pixel with
+ * NOT(qflag > flag_thresh) becomes an all-NaN record and a NaN in amf_masked, which
+ * is exactly what multiplying every field by the 1/NaN mask does
+ * (interpolator.py:126-128,163).  `items` is a DEVICE array; block0 is the running
+ * sum of oisat_pack_blocks(n_px) over the preceding items. */
+typedef struct oisat_pack_item {
+  const void* sw;      /* [L][n_px] float16 */
+  const void* p_mid;   /* [L][n_px] float16 */
+  const void* vcd;     /* [n_px] float16 */
+  const void* sigma;   /* [n_px] float16 */
+  const void* trop;    /* [n_px] float16 or NULL */
+  const void* qflag;   /* [n_px] of qflag_dtype */
+  const void* amf;     /* [n_px] of amf_dtype */
+  int64_t n_px;
+  int64_t px0;         /* first record / good byte of this granule */
+  int64_t block0;      /* first thread block of this granule */
+} oisat_pack_item;
+int64_t oisat_pack_blocks(int64_t n_px);
+int oisat_pack_batch(const oisat_pack_item* items, int32_t n_items, int64_t total_blocks,
+                     int32_t n_sat_lev, int32_t has_trop, int32_t qflag_dtype,
+                     double flag_thresh, int32_t amf_dtype, void* records, double* amf_masked,
+                     void* stream);
+
+/* derived model fields, once per month instead of once per granule
+ * (amf_recal.py:151-152): logp = float32 log(p_mid) (:108), pcol = float32 partial
+ * column (:51-56).  n = n_slots*n_lev*n_cell elements, 16-byte aligned pointers. */
+int oisat_ctm_prepare(const float* pmid, const float* prof, const float* dp, int64_t n,
+                      float* logp, float* pcol, void* stream);
+
 /* fused gather-interpolation + AMF recalculation over a batch of granules.
  * One "pair" = (granule, model cell) that the geometry plan marks as reachable.
  * Pairs are grouped in tiles of <=32 consecutive cells of one model row.
@@ -232,19 +261,19 @@ typedef struct oisat_fused_args {
   /* per-granule tables, [n_granules] */
   int32_t n_granules;
   const int64_t* gran_record0;   /* first record (pixel) of the granule in `records`  */
-  const int64_t* gran_px0;       /* first pixel of the granule in good/amf            */
+  const int64_t* gran_px0;       /* first pixel of the granule in amf_masked          */
   const int32_t* gran_slot;      /* matched model time slot                           */
   /* pixel data */
-  const void* records;           /* packed float16 records                            */
-  const uint8_t* good;           /* [total px]                                        */
-  const void* amf;               /* [total px] */
-  int32_t amf_dtype;
+  int64_t n_records;             /* pixels in `records` (n_records * chunks < 2^32)   */
+  const void* records;           /* packed float16 records (oisat_pack_batch)         */
+  const double* amf_masked;      /* [total px] NaN-masked AMF (oisat_pack_batch)      */
   int32_t n_sat_lev;
   int32_t has_trop;
-  /* model fields, float32 [n_slots][n_ctm_lev][n_cell] */
+  /* model fields, float32 [n_slots][n_ctm_lev][n_cell]; logp/pcol from
+   * oisat_ctm_prepare, p_mid only read when has_trop (tropopause mask, :111-114) */
   const float* ctm_pmid;
-  const float* ctm_prof;
-  const float* ctm_dp;
+  const float* ctm_logp;
+  const float* ctm_pcol;
   int32_t n_ctm_lev;
   int64_t n_cell;
   /* output: staged[5][n_pairs] */

@@ -36,11 +36,17 @@ class FusedArgs(C.Structure):
         ("n_pairs", i64), ("nwin", i32), ("vert", vp), ("w", vp), ("box_weight", f64),
         ("box_weight_err", f64),
         ("n_granules", i32), ("gran_record0", vp), ("gran_px0", vp), ("gran_slot", vp),
-        ("records", vp), ("good", vp), ("amf", vp), ("amf_dtype", i32), ("n_sat_lev", i32),
+        ("n_records", i64), ("records", vp), ("amf_masked", vp), ("n_sat_lev", i32),
         ("has_trop", i32),
-        ("ctm_pmid", vp), ("ctm_prof", vp), ("ctm_dp", vp), ("n_ctm_lev", i32), ("n_cell", i64),
+        ("ctm_pmid", vp), ("ctm_logp", vp), ("ctm_pcol", vp), ("n_ctm_lev", i32), ("n_cell", i64),
         ("staged", vp),
     ]
+
+
+class PackItem(C.Structure):
+    """struct oisat_pack_item"""
+    _fields_ = [("sw", vp), ("p_mid", vp), ("vcd", vp), ("sigma", vp), ("trop", vp), ("qflag", vp),
+                ("amf", vp), ("n_px", i64), ("px0", i64), ("block0", i64)]
 
 
 # name -> (restype, argtypes); mirrors include/oisat.h one to one
@@ -68,6 +74,9 @@ PROTOTYPES = {
     "oisat_oi_apply": (C.c_int, [vp, vp, vp, vp, i64, f64, vp, vp, vp, vp, vp]),
     "oisat_pack_record_halfs": (i64, [i32, i32]),
     "oisat_pack_granule": (C.c_int, [vp, vp, i32, vp, vp, vp, i64, vp, vp]),
+    "oisat_pack_blocks": (i64, [i64]),
+    "oisat_pack_batch": (C.c_int, [vp, i32, i64, i32, i32, i32, f64, i32, vp, vp, vp]),
+    "oisat_ctm_prepare": (C.c_int, [vp, vp, vp, i64, vp, vp, vp]),
     "oisat_fused_amf": (C.c_int, [C.POINTER(FusedArgs), vp]),
     "oisat_accum_pairs": (C.c_int, [vp, i64, vp, vp, vp, i64, vp]),
 }

@@ -1,11 +1,18 @@
 // Fused month pipeline for float16 `satellite_amf` products (OMI NO2 / HCHO,
 // TROPOMI NO2 -- the BASELINE configurations):
 //
-//   oisat_pack_granule  reader layout ([level][pixel] float16, level-major) ->
+//   oisat_ctm_prepare   once per model slot: float32 log-pressure and partial
+//                       column (amf_recal.py:51-56,108) so the per-pair work
+//                       reads two derived fields instead of recomputing them
+//                       for every granule like the reference does (:151-152).
+//   oisat_pack_granule / oisat_pack_batch
+//                       reader layout ([level][pixel] float16, level-major) ->
 //                       one pixel-major record per pixel, so that gathering a
 //                       stencil vertex is ONE coalesced 128-bit load per lane
 //                       instead of ~2L scattered 2-byte loads (which would be
-//                       bound by L1 wavefronts, not HBM: DESIGN.md section 4).
+//                       bound by L1 wavefronts, not HBM: DESIGN.md section 4);
+//                       the batch form also folds the quality mask
+//                       (interpolator.py:126-128) and runs a whole month in one launch.
 //   oisat_fused_amf     per (granule, model cell) pair: gather-interpolate all
 //                       2L+2(+1) gridded quantities in float64 (interpolator.py:
 //                       162-209 through the geometry plan), read the model column
@@ -17,227 +24,402 @@
 // Record layout: R = 8*nchunk halfs, nchunk = ceil(nrow/8), nrow = 2L+2(+1);
 // rows = [SW_0..SW_{L-1}, p_0..p_{L-1}, vcd, sigma^2 (squared in float16,
 // interpolator.py:186), tropopause?].  Row r sits in chunk r % nchunk at element
-// r / nchunk: lane q of a warp loads chunk q (16 bytes) and owns rows
+// r / nchunk: lane q of a group loads chunk q (16 bytes) and owns rows
 // q, q+nchunk, ..., so the later shared-memory transpose is conflict-free.
 #include "vertical.cuh"
 
 namespace oisat {
 
-constexpr int kFusedWarps = 4;
 constexpr int kTileCells = 32;
+constexpr int kFusedThreads = 256;
 
 __host__ __device__ inline int record_rows(int L, int has_trop) { return 2 * L + 2 + (has_trop ? 1 : 0); }
 __host__ __device__ inline int record_chunks(int L, int has_trop) { return (record_rows(L, has_trop) + 7) / 8; }
 
-// ------------------------------------------------------------------ pack ----
-constexpr int kPackPixels = 64;
-
+// ----------------------------------------------------------------- prepare ----
 __global__ void __launch_bounds__(256)
-pack_kernel(const __half* __restrict__ sw, const __half* __restrict__ pmid, int L,
-            const __half* __restrict__ vcd, const __half* __restrict__ sigma,
-            const __half* __restrict__ trop, int64_t n_px, __half* __restrict__ records) {
-  extern __shared__ __half tile[];  // [kPackPixels][R + 2]
-  const int has_trop = trop != nullptr;
+ctm_prepare_kernel(const float* __restrict__ pmid, const float* __restrict__ prof,
+                   const float* __restrict__ dp, int64_t n, float* __restrict__ logp,
+                   float* __restrict__ pcol) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 pm = *reinterpret_cast<const float4*>(pmid + i);
+    const float4 pr = *reinterpret_cast<const float4*>(prof + i);
+    const float4 d = *reinterpret_cast<const float4*>(dp + i);
+    float4 lp, pc;
+    lp.x = log_f32(pm.x); lp.y = log_f32(pm.y); lp.z = log_f32(pm.z); lp.w = log_f32(pm.w);
+    pc.x = partial_column_f32(d.x, pr.x); pc.y = partial_column_f32(d.y, pr.y);
+    pc.z = partial_column_f32(d.z, pr.z); pc.w = partial_column_f32(d.w, pr.w);
+    *reinterpret_cast<float4*>(logp + i) = lp;
+    *reinterpret_cast<float4*>(pcol + i) = pc;
+  } else {
+    for (int64_t j = i; j < n; ++j) {
+      logp[j] = log_f32(pmid[j]);
+      pcol[j] = partial_column_f32(dp[j], prof[j]);
+    }
+  }
+}
+
+// -------------------------------------------------------------------- pack ----
+constexpr int kPackPixels = 128;
+
+struct PackSrc {
+  const __half* sw;
+  const __half* pmid;
+  const __half* vcd;
+  const __half* sigma;
+  const __half* trop;
+  int64_t n_px;
+};
+
+__device__ __forceinline__ int record_slot(int row, int nchunk) {
+  return 8 * (row % nchunk) + row / nchunk;
+}
+
+// One block transposes kPackPixels pixels x nrow rows through shared memory.
+// Load phase: a thread moves two neighbouring pixels of one source row per
+// 32-bit load (rows are contiguous along pixels in the reader layout), so a warp
+// reads 128 contiguous bytes; the odd word pitch of the tile makes the
+// transposing stores conflict-free.  Store phase: 16 lanes per record, one
+// 16-byte chunk each, i.e. fully coalesced 128-bit stores.
+__device__ __forceinline__ void pack_block(const PackSrc& s, int L, int has_trop, int64_t p0,
+                                           __half* __restrict__ records, __half* tile,
+                                           const unsigned char* bad) {
   const int nrow = record_rows(L, has_trop);
   const int nchunk = record_chunks(L, has_trop);
   const int R = 8 * nchunk, pitch = R + 2;
-  const int64_t p0 = (int64_t)blockIdx.x * kPackPixels;
-  const int px = threadIdx.x & (kPackPixels - 1);
-  const int64_t p = p0 + px;
-  for (int r = threadIdx.x / kPackPixels; r < R; r += blockDim.x / kPackPixels) {
-    // r enumerates record slots; slot -> source row
-    const int q = r >> 3, e = r & 7;
-    const int row = q + nchunk * e;
-    __half v = __float2half_rn(0.0f);
-    if (p < n_px && row < nrow) {
-      if (row < L) v = sw[(int64_t)row * n_px + p];
-      else if (row < 2 * L) v = pmid[(int64_t)(row - L) * n_px + p];
-      else if (row == 2 * L) v = vcd[p];
-      else if (row == 2 * L + 1) {
-        const float s = __half2float(sigma[p]);
-        v = __float2half_rn(__fmul_rn(s, s));  // numpy float16 square
-      } else v = trop[p];
+  const int64_t left = s.n_px - p0;
+  const int n_here = left < kPackPixels ? (int)left : kPackPixels;
+  const bool pairs_ok = ((s.n_px & 1) == 0) && (n_here == kPackPixels);
+  const __half zero = __float2half_rn(0.0f);
+  __shared__ unsigned char slot_tab[2 * kMaxSatLev + 16];  // row -> slot, no divisions in the loop
+  for (int row = threadIdx.x; row < nrow; row += blockDim.x)
+    slot_tab[row] = (unsigned char)record_slot(row, nchunk);
+  __syncthreads();
+  // padding slots of the record (rows >= nrow)
+  for (int i = threadIdx.x; i < kPackPixels * (R - nrow); i += blockDim.x) {
+    const int px = i / (R - nrow), row = nrow + i % (R - nrow);
+    tile[px * pitch + record_slot(row, nchunk)] = zero;
+  }
+  if (pairs_ok) {
+    const int pp = threadIdx.x & (kPackPixels / 2 - 1);   // pixel pair
+    const int rl = threadIdx.x / (kPackPixels / 2);       // row lane
+    const int rstep = blockDim.x / (kPackPixels / 2);
+    __half* t0 = tile + (2 * pp) * pitch;
+    __half* t1 = t0 + pitch;
+    const int64_t col = p0 + 2 * pp;
+#pragma unroll 4
+    for (int row = rl; row < L; row += rstep) {
+      const __half2 a = *reinterpret_cast<const __half2*>(s.sw + (int64_t)row * s.n_px + col);
+      const __half2 b = *reinterpret_cast<const __half2*>(s.pmid + (int64_t)row * s.n_px + col);
+      const int sa = slot_tab[row], sb = slot_tab[L + row];
+      t0[sa] = __low2half(a); t1[sa] = __high2half(a);
+      t0[sb] = __low2half(b); t1[sb] = __high2half(b);
     }
-    tile[px * pitch + r] = v;
+    if (rl == 0) {
+      const __half2 v = *reinterpret_cast<const __half2*>(s.vcd + col);
+      const int sv = record_slot(2 * L, nchunk);
+      t0[sv] = __low2half(v); t1[sv] = __high2half(v);
+    } else if (rl == 1) {
+      const float2 g = __half22float2(*reinterpret_cast<const __half2*>(s.sigma + col));
+      const int ss = record_slot(2 * L + 1, nchunk);
+      t0[ss] = __float2half_rn(__fmul_rn(g.x, g.x));   // numpy float16 square
+      t1[ss] = __float2half_rn(__fmul_rn(g.y, g.y));
+    } else if (rl == 2 && has_trop) {
+      const __half2 v = *reinterpret_cast<const __half2*>(s.trop + col);
+      const int st = record_slot(2 * L + 2, nchunk);
+      t0[st] = __low2half(v); t1[st] = __high2half(v);
+    }
+  } else {  // ragged tail / odd pixel count: one value per thread step
+    for (int i = threadIdx.x; i < n_here * nrow; i += blockDim.x) {
+      const int row = i / n_here, px = i - row * n_here;
+      const int64_t p = p0 + px;
+      __half v;
+      if (row < L) v = s.sw[(int64_t)row * s.n_px + p];
+      else if (row < 2 * L) v = s.pmid[(int64_t)(row - L) * s.n_px + p];
+      else if (row == 2 * L) v = s.vcd[p];
+      else if (row == 2 * L + 1) {
+        const float g = __half2float(s.sigma[p]);
+        v = __float2half_rn(__fmul_rn(g, g));
+      } else v = s.trop[p];
+      tile[px * pitch + record_slot(row, nchunk)] = v;
+    }
   }
   __syncthreads();
-  // contiguous write-out, 4 bytes per thread step (pitch keeps rows 4-byte aligned)
-  const int words_per_rec = R / 2;
-  const int64_t n_here = (n_px - p0) < kPackPixels ? (n_px - p0) : kPackPixels;
-  uint32_t* dst = reinterpret_cast<uint32_t*>(records + p0 * R);
+  uint4* dst = reinterpret_cast<uint4*>(records + p0 * R);
   const uint32_t* src = reinterpret_cast<const uint32_t*>(tile);
-  for (int64_t i = threadIdx.x; i < n_here * words_per_rec; i += blockDim.x) {
-    const int rec = (int)(i / words_per_rec), wd = (int)(i % words_per_rec);
-    dst[i] = src[rec * (pitch / 2) + wd];
+  const int q = threadIdx.x & 15;
+  if (q < nchunk) {
+    const uint32_t nan2 = 0x7e007e00u;  // two float16 quiet NaNs
+    for (int rec = threadIdx.x >> 4; rec < n_here; rec += blockDim.x >> 4) {
+      const uint32_t* w = src + rec * (pitch / 2) + 4 * q;
+      // a masked pixel is a NaN vertex for EVERY field (interpolator.py:126-128,163)
+      dst[rec * nchunk + q] = (bad != nullptr && bad[rec]) ? make_uint4(nan2, nan2, nan2, nan2)
+                                                           : make_uint4(w[0], w[1], w[2], w[3]);
+    }
   }
 }
 
-// ----------------------------------------------------------------- fused ----
+__global__ void __launch_bounds__(256)
+pack_kernel(PackSrc s, int L, int has_trop, __half* __restrict__ records) {
+  extern __shared__ __half tile[];
+  pack_block(s, L, has_trop, (int64_t)blockIdx.x * kPackPixels, records, tile, nullptr);
+}
+
+__global__ void __launch_bounds__(256)
+pack_batch_kernel(const oisat_pack_item* __restrict__ items, int n_items, int L, int has_trop,
+                  int qflag_dtype, double thresh, int amf_dtype, __half* __restrict__ records,
+                  double* __restrict__ amf_masked) {
+  extern __shared__ __half tile[];
+  __shared__ unsigned char bad[kPackPixels];
+  // granule of this block: last item with block0 <= blockIdx.x
+  int lo = 0, hi = n_items - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[mid].block0 <= (int64_t)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const oisat_pack_item it = items[lo];
+  PackSrc s{(const __half*)it.sw, (const __half*)it.p_mid, (const __half*)it.vcd,
+            (const __half*)it.sigma, (const __half*)it.trop, it.n_px};
+  const int64_t p0 = ((int64_t)blockIdx.x - it.block0) * kPackPixels;
+  if (threadIdx.x < kPackPixels) {
+    const int64_t p = p0 + threadIdx.x;
+    bool is_bad = true;
+    if (p < it.n_px) {
+      is_bad = !(load_as_double(it.qflag, qflag_dtype, p) > thresh);
+      amf_masked[it.px0 + p] = is_bad ? qnan() : load_as_double(it.amf, amf_dtype, p);
+    }
+    bad[threadIdx.x] = is_bad ? 1 : 0;
+  }
+  // (pack_block starts with a __syncthreads that also publishes `bad`)
+  pack_block(s, L, has_trop, p0, records + it.px0 * (8 * record_chunks(L, has_trop)), tile, bad);
+}
+
+// ------------------------------------------------------------------- fused ----
 struct FusedParams {
   oisat_fused_args a;
-  int nrow, nchunk, R;
-  double box, box_err;
+  int nrow, nchunk, nfield;
+  int scratch_doubles;  // per group
 };
 
 __device__ __forceinline__ void half8_to_double(const uint4& u, double* z) {
-  const __half2* h = reinterpret_cast<const __half2*>(&u);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float2 f = __half22float2(h[i]);
-    z[2 * i] = (double)f.x;
-    z[2 * i + 1] = (double)f.y;
+    // float16 -> float64 is exact; one conversion per value, no float32 stop-over
+    asm("{ .reg .b16 lo, hi;\n\t"
+        "  mov.b32 {lo, hi}, %2;\n\t"
+        "  cvt.f64.f16 %0, lo;\n\t"
+        "  cvt.f64.f16 %1, hi; }"
+        : "=d"(z[2 * i]), "=d"(z[2 * i + 1]) : "r"(w[i]));
   }
 }
 
-__global__ void __launch_bounds__(kFusedWarps * 32)
+// LANES threads per (granule, cell) pair: 16 when a record has <= 15 chunks
+// (every BASELINE product), 32 otherwise.  Both halves of a warp run the same
+// instruction stream on different pairs; an idle half re-does its neighbour's
+// pair and discards the result, so the warp never diverges.
+template <int LANES>
+__global__ void __launch_bounds__(kFusedThreads, 4)
 fused_amf_kernel(const __grid_constant__ FusedParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int kGroups = kFusedThreads / LANES;
   const oisat_fused_args& A = P.a;
   const int n_ctm = A.n_ctm_lev;
   const int cpitch = n_ctm + 1;
-  float* ctm_s = reinterpret_cast<float*>(smem_raw);                    // [3][32][cpitch]
-  WarpScratch* scratch = reinterpret_cast<WarpScratch*>(
-      smem_raw + ((3 * kTileCells * cpitch * sizeof(float) + 15) / 16) * 16);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ctm_s = reinterpret_cast<float*>(smem_raw);  // [nfield][32][cpitch]
+  double* scratch_base = reinterpret_cast<double*>(
+      smem_raw + (((size_t)P.nfield * kTileCells * cpitch * sizeof(float) + 15) / 16) * 16);
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (LANES - 1);
+  const int grp = threadIdx.x / LANES;
   const int64_t tile = blockIdx.x;
   const int g = A.tile_granule[tile];
   const int cell0 = A.tile_cell0[tile];
   const int64_t pair0 = A.tile_pair0[tile];
   const uint32_t mask = A.tile_mask[tile];
+  const bool has_trop = A.has_trop != 0;
 
-  // ---- stage the model tile: 32 consecutive cells x n_ctm levels x 3 fields.
-  // Global reads are coalesced along cells; the transposed, padded shared layout
-  // [cell][level] makes the later per-cell column reads conflict-free.
-  {
-    const int64_t slot_off = (int64_t)A.gran_slot[g] * n_ctm * A.n_cell;
-    const int c = lane;
-    const bool in_row = (int64_t)cell0 + c < A.n_cell;
-    for (int k = warp; k < n_ctm; k += kFusedWarps) {
-      const int64_t src = slot_off + (int64_t)k * A.n_cell + cell0 + c;
-      float pm = 0.f, pr = 0.f, dp = 0.f;
-      if (in_row) { pm = A.ctm_pmid[src]; pr = A.ctm_prof[src]; dp = A.ctm_dp[src]; }
-      ctm_s[(0 * kTileCells + c) * cpitch + k] = pm;
-      ctm_s[(1 * kTileCells + c) * cpitch + k] = pr;
-      ctm_s[(2 * kTileCells + c) * cpitch + k] = dp;
-    }
-  }
-  __syncthreads();
-
-  WarpScratch& s = scratch[warp];
-  double* rows = s.xs;  // xs and ys are adjacent: 2*128 doubles >= nrow
   const int L = A.n_sat_lev;
   const int S = 3 * A.nwin;
   const int64_t rec0 = A.gran_record0[g];
   const int64_t px0 = A.gran_px0[g];
   const uint4* records = reinterpret_cast<const uint4*>(A.records);
+  const int n_in_tile = __popc(mask);
+  constexpr int kSweep = (LANES == 16) ? 15 : 30;  // whole window nodes per sweep
 
-  // set bits of the tile mask are dealt round-robin to the warps
-  int ord = 0;
-  for (uint32_t m = mask; m; m &= m - 1, ++ord) {
-    if ((ord % kFusedWarps) != warp) continue;
-    const int l = __ffs(m) - 1;  // cell offset inside the tile
+  // Lane k of a group fetches stencil entry k of its pair: the chunk index of
+  // the vertex record (host checks it fits 32 bits), the weight, and the AMF term
+  // (AMF is not float16, hence not in the record; the pack step has NaN-masked it).
+  auto load_entries = [&](int64_t pair, int base, int nk, uint32_t& cix, double& wt, double& za) {
+    cix = 0;
+    wt = 0.0;
+    za = 0.0;
+    if (gl < nk) {
+      const int32_t v = A.vert[pair * S + base + gl];
+      wt = A.w[pair * S + base + gl];
+      cix = (uint32_t)((rec0 + v) * P.nchunk);
+      za = wt * A.amf_masked[px0 + v];
+    }
+  };
+  // first round's entries are requested before the model tile is staged, so the
+  // two dependent global-load chains overlap
+  uint32_t pre_cix;
+  double pre_wt, pre_za;
+  load_entries(pair0 + (grp < n_in_tile ? grp : n_in_tile - 1), 0, S < kSweep ? S : kSweep, pre_cix,
+               pre_wt, pre_za);
+
+  // ---- stage the model tile: 32 consecutive cells x n_ctm levels x nfield
+  // derived fields.  Global reads are coalesced along cells; the transposed,
+  // padded shared layout [cell][level] makes the per-cell column reads
+  // conflict-free.
+  {
+    const int64_t slot_off = (int64_t)A.gran_slot[g] * n_ctm * A.n_cell;
+    const int c = lane;
+    const bool in_grid = (int64_t)cell0 + c < A.n_cell;
+    for (int k = threadIdx.x >> 5; k < n_ctm; k += kFusedThreads / 32) {
+      const int64_t src = slot_off + (int64_t)k * A.n_cell + cell0 + c;
+      float lp = 0.f, pc = 0.f, pm = 0.f;
+      if (in_grid) {
+        lp = __ldg(A.ctm_logp + src);
+        pc = __ldg(A.ctm_pcol + src);
+        if (has_trop) pm = __ldg(A.ctm_pmid + src);
+      }
+      ctm_s[(0 * kTileCells + c) * cpitch + k] = lp;
+      ctm_s[(1 * kTileCells + c) * cpitch + k] = pc;
+      if (has_trop) ctm_s[(2 * kTileCells + c) * cpitch + k] = pm;
+    }
+  }
+  __syncthreads();
+
+  const GroupScratch s = carve_scratch(scratch_base + (size_t)grp * P.scratch_doubles, L, n_ctm,
+                                       P.nrow);
+  double* rows = s.xs;  // [xs|ys] is contiguous and holds >= nrow doubles
+
+  const int rounds = (n_in_tile + kGroups - 1) / kGroups;
+  for (int rd = 0; rd < rounds; ++rd) {
+    int ord = rd * kGroups + grp;
+    const bool mine = ord < n_in_tile;
+    if (!__any_sync(0xffffffffu, mine)) continue;  // no block-wide barrier below: warps may skip
+    if (!mine) ord = n_in_tile - 1;  // shadow work of an odd half warp, results discarded
+    const int l = (int)__fns(mask, 0, ord + 1);  // cell offset of the ord-th set bit
     const int64_t pair = pair0 + ord;
+
     double acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.0;
     double acc_amf = 0.0;
-    bool alive = true;
-    for (int base = 0; base < S; base += 30) {  // 30 = 10 window nodes per sweep
-      const int nk = (S - base) < 30 ? (S - base) : 30;
-      int32_t v = 0;
-      double wt = 0.0;
-      if (lane < nk) {
-        v = A.vert[pair * S + base + lane];
-        wt = A.w[pair * S + base + lane];
-        alive = alive && (A.good[px0 + v] != 0);
-      }
-      double fine[8], fine_amf = 0.0;
-      for (int k = 0; k < nk; ++k) {
-        const int32_t vk = __shfl_sync(0xffffffffu, v, k);
-        const double wk = __shfl_sync(0xffffffffu, wt, k);
-        const int j = k % 3;
-        if (lane < P.nchunk) {
-          const uint4 u = __ldg(&records[(rec0 + vk) * P.nchunk + lane]);
-          double z[8];
-          half8_to_double(u, z);
+    for (int base = 0; base < S; base += kSweep) {
+      const int nk = (S - base) < kSweep ? (S - base) : kSweep;
+      uint32_t cix;
+      double wt, za;
+      if (rd == 0 && base == 0) { cix = pre_cix; wt = pre_wt; za = pre_za; }
+      else load_entries(pair, base, nk, cix, wt, za);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const double prod = __dmul_rn(wk, z[e]);
-            fine[e] = j == 0 ? __dadd_rn(0.0, prod) : __dadd_rn(fine[e], prod);
-          }
-        } else if (lane == P.nchunk) {
-          const double z = load_as_double(A.amf, A.amf_dtype, px0 + vk);
-          const double prod = __dmul_rn(wk, z);
-          fine_amf = j == 0 ? __dadd_rn(0.0, prod) : __dadd_rn(fine_amf, prod);
+      for (int o = LANES / 2; o > 0; o >>= 1) za += __shfl_xor_sync(0xffffffffu, za, o, LANES);
+      acc_amf += za;
+      for (int node = 0; node < nk; node += 3) {
+        uint4 u[3];
+        double wk[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {  // issue the three vertex loads together
+          const uint32_t ck = __shfl_sync(0xffffffffu, cix, node + j, LANES);
+          wk[j] = __shfl_sync(0xffffffffu, wt, node + j, LANES);
+          if (gl < P.nchunk) u[j] = __ldg(&records[ck + gl]);
         }
-        if (j == 2) {
-          if (lane < P.nchunk) {
+        if (gl < P.nchunk) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int row = lane + P.nchunk * e;
-              const double bw = row == 2 * L + 1 ? P.box_err : P.box;
-              acc[e] = __dadd_rn(acc[e], __dmul_rn(fine[e], bw));
-            }
-          } else if (lane == P.nchunk) {
-            acc_amf = __dadd_rn(acc_amf, __dmul_rn(fine_amf, P.box));
+          for (int j = 0; j < 3; ++j) {
+            double z[8];
+            half8_to_double(u[j], z);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = fma(wk[j], z[e], acc[e]);
           }
         }
       }
     }
-    alive = __all_sync(0xffffffffu, alive);
-    if (!alive) {  // a masked vertex poisons every field of the cell (interpolator.py:126-128)
-      if (lane < 5) A.staged[(int64_t)lane * A.n_pairs + pair] = qnan();
-      continue;
-    }
-    if (lane < P.nchunk) {
+    // box mean: sum over the window first, scale once (interpolator.py:40-46,66-76)
+    if (gl < P.nchunk) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const int row = lane + P.nchunk * e;
-        if (row < P.nrow) rows[row] = acc[e];
+        const int row = gl + P.nchunk * e;
+        if (row < P.nrow) rows[row] = acc[e] * (row == 2 * L + 1 ? A.box_weight_err : A.box_weight);
       }
     }
-    const double old_amf = __shfl_sync(0xffffffffu, acc_amf, P.nchunk);
+    const double old_amf = acc_amf * A.box_weight;
     __syncwarp();
     const double vcd = rows[2 * L];
     const double sigma = sqrt(rows[2 * L + 1]);  // interpolator.py:188
-    const bool has_trop = A.has_trop != 0;
     const double trop = has_trop ? rows[2 * L + 2] : 0.0;
-    for (int i = lane; i < L; i += 32) {
-      s.xr[i] = log(rows[L + i]);
-      s.yr[i] = rows[i];
+    // amf_recal.py:99-100 skips cells without a retrieval.  Masked pixels arrive as
+    // NaN records, so such cells are common (cloud fields are coherent): when both
+    // halves of the warp are idle or dead the vertical operator is skipped, and a
+    // dead half next to a live one runs it on a dummy monotone table (results
+    // discarded) so that it stays on the sort's fast path.
+    const bool dead = !(vcd == vcd);
+    if (__all_sync(0xffffffffu, dead || !mine)) {
+      if (mine && gl == 0) {
+        A.staged[0 * A.n_pairs + pair] = qnan();
+        A.staged[1 * A.n_pairs + pair] = sigma;
+        A.staged[2 * A.n_pairs + pair] = qnan();
+        A.staged[3 * A.n_pairs + pair] = qnan();
+        A.staged[4 * A.n_pairs + pair] = old_amf;
+      }
+      __syncwarp();
+      continue;
+    }
+    for (int i = gl; i < L; i += LANES) {
+      s.xr[i] = dead ? (double)i : log(rows[L + i]);
+      s.yr[i] = dead ? 0.0 : rows[i];
     }
     __syncwarp();
-    double new_amf = qnan(), col = qnan(), vnew = qnan();
-    if (vcd == vcd) {  // amf_recal.py:99-100
-      const float* cp = ctm_s + (0 * kTileCells + l) * cpitch;
-      const float* cx = ctm_s + (1 * kTileCells + l) * cpitch;
-      const float* cd = ctm_s + (2 * kTileCells + l) * cpitch;
-      double colsum;
-      new_amf = warp_amf_cell<true>(
-          s, L, n_ctm, has_trop, trop, [&](int k) { return (double)cp[k]; },
-          [&](int k) { return (double)partial_column_f32(cd[k], cx[k]); }, &colsum, lane);
-      vnew = (old_amf * vcd) / new_amf;                       // amf_recal.py:179
+    const float* clp = ctm_s + (0 * kTileCells + l) * cpitch;
+    const float* cpc = ctm_s + (1 * kTileCells + l) * cpitch;
+    const float* cpm = ctm_s + (2 * kTileCells + l) * cpitch;
+    double colsum;
+    double new_amf = group_amf_cell<LANES, true, true>(
+        s, L, n_ctm, has_trop, trop, [&](int k) { return (double)cpm[k]; },
+        [&](int k) { return (double)clp[k]; }, [&](int k) { return (double)cpc[k]; }, &colsum,
+        lane);
+    double vnew = qnan(), col = qnan();
+    if (vcd == vcd) {                                         // amf_recal.py:99-100
+      vnew = (old_amf * vcd) / new_amf;                       // :179
       col = (vnew != vnew || isinf(vnew)) ? qnan() : colsum;  // :180-181
+    } else {
+      new_amf = qnan();                                       // :176
     }
-    __syncwarp();
-    if (lane == 0) {
+    if (mine && gl == 0) {
       A.staged[0 * A.n_pairs + pair] = vnew;
       A.staged[1 * A.n_pairs + pair] = sigma;
       A.staged[2 * A.n_pairs + pair] = col;
       A.staged[3 * A.n_pairs + pair] = new_amf;
       A.staged[4 * A.n_pairs + pair] = old_amf;
     }
+    __syncwarp();
   }
 }
 
-static size_t fused_smem_bytes(int n_ctm) {
-  const size_t ctm = ((size_t)3 * kTileCells * (n_ctm + 1) * sizeof(float) + 15) / 16 * 16;
-  return ctm + kFusedWarps * sizeof(WarpScratch);
+static size_t fused_smem_bytes(const FusedParams& P, int lanes) {
+  const size_t ctm = (((size_t)P.nfield * kTileCells * (P.a.n_ctm_lev + 1) * sizeof(float)) + 15) /
+                     16 * 16;
+  return ctm + (size_t)(kFusedThreads / lanes) * P.scratch_doubles * sizeof(double);
 }
 
 }  // namespace oisat
 
 using namespace oisat;
+
+extern "C" int oisat_ctm_prepare(const float* pmid, const float* prof, const float* dp, int64_t n,
+                                 float* logp, float* pcol, void* stream) {
+  if (n <= 0) return OISAT_OK;
+  OISAT_CHECK_ARG(pmid && prof && dp && logp && pcol, "null pointer");
+  OISAT_CHECK_ARG(((uintptr_t)pmid | (uintptr_t)prof | (uintptr_t)dp | (uintptr_t)logp |
+                   (uintptr_t)pcol) % 16 == 0, "pointers must be 16-byte aligned");
+  ctm_prepare_kernel<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, (cudaStream_t)stream>>>(
+      pmid, prof, dp, n, logp, pcol);
+  OISAT_CHECK_LAUNCH();
+  return OISAT_OK;
+}
 
 extern "C" int64_t oisat_pack_record_halfs(int32_t n_sat_lev, int32_t has_trop) {
   return 8 * (int64_t)record_chunks(n_sat_lev, has_trop);
@@ -251,9 +433,32 @@ extern "C" int oisat_pack_granule(const void* sw, const void* p_mid, int32_t n_s
   if (n_px <= 0) return OISAT_OK;
   const int R = 8 * record_chunks(n_sat_lev, trop != nullptr);
   const size_t smem = (size_t)kPackPixels * (R + 2) * sizeof(__half);
+  PackSrc s{(const __half*)sw, (const __half*)p_mid, (const __half*)vcd, (const __half*)sigma,
+            (const __half*)trop, n_px};
   pack_kernel<<<(unsigned)ceil_div(n_px, kPackPixels), 256, smem, (cudaStream_t)stream>>>(
-      (const __half*)sw, (const __half*)p_mid, n_sat_lev, (const __half*)vcd,
-      (const __half*)sigma, (const __half*)trop, n_px, (__half*)records);
+      s, n_sat_lev, trop != nullptr, (__half*)records);
+  OISAT_CHECK_LAUNCH();
+  return OISAT_OK;
+}
+
+extern "C" int64_t oisat_pack_blocks(int64_t n_px) { return ceil_div(n_px, kPackPixels); }
+
+extern "C" int oisat_pack_batch(const oisat_pack_item* items, int32_t n_items,
+                                int64_t total_blocks, int32_t n_sat_lev, int32_t has_trop,
+                                int32_t qflag_dtype, double flag_thresh, int32_t amf_dtype,
+                                void* records, double* amf_masked, void* stream) {
+  if (n_items <= 0 || total_blocks <= 0) return OISAT_OK;
+  OISAT_CHECK_ARG(items && records && amf_masked, "null pointer");
+  OISAT_CHECK_ARG(amf_dtype == OISAT_F16 || amf_dtype == OISAT_F32 || amf_dtype == OISAT_F64,
+                  "bad amf dtype");
+  OISAT_CHECK_ARG(n_sat_lev >= 2 && n_sat_lev <= kMaxSatLev, "bad level count");
+  OISAT_CHECK_ARG(qflag_dtype == OISAT_F16 || qflag_dtype == OISAT_F32 || qflag_dtype == OISAT_F64,
+                  "bad quality-flag dtype");
+  const int R = 8 * record_chunks(n_sat_lev, has_trop);
+  const size_t smem = (size_t)kPackPixels * (R + 2) * sizeof(__half);
+  pack_batch_kernel<<<(unsigned)total_blocks, 256, smem, (cudaStream_t)stream>>>(
+      items, n_items, n_sat_lev, has_trop, qflag_dtype, flag_thresh, amf_dtype, (__half*)records,
+      amf_masked);
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
 }
@@ -263,29 +468,27 @@ extern "C" int oisat_fused_amf(const oisat_fused_args* h_args, void* stream) {
   const oisat_fused_args& a = *h_args;
   if (a.n_tiles == 0 || a.n_pairs == 0) return OISAT_OK;
   OISAT_CHECK_ARG(a.tile_granule && a.tile_cell0 && a.tile_pair0 && a.tile_mask && a.vert && a.w &&
-                      a.gran_record0 && a.gran_px0 && a.gran_slot && a.records && a.good &&
-                      a.amf && a.ctm_pmid && a.ctm_prof && a.ctm_dp && a.staged,
+                      a.gran_record0 && a.gran_px0 && a.gran_slot && a.records &&
+                      a.amf_masked && a.ctm_logp && a.ctm_pcol && a.staged,
                   "null pointer");
+  OISAT_CHECK_ARG(!a.has_trop || a.ctm_pmid, "tropopause masking needs the model p_mid");
   OISAT_CHECK_ARG(a.nwin >= 1 && a.n_sat_lev >= 2 && a.n_sat_lev <= kMaxSatLev, "bad stencil");
   OISAT_CHECK_ARG(a.n_ctm_lev >= 2 && a.n_ctm_lev <= kMaxCtmLev, "bad model level count");
-  OISAT_CHECK_ARG(a.amf_dtype == OISAT_F16 || a.amf_dtype == OISAT_F32 || a.amf_dtype == OISAT_F64,
-                  "bad amf dtype");
   FusedParams P;
   P.a = a;
   P.nrow = record_rows(a.n_sat_lev, a.has_trop);
   P.nchunk = record_chunks(a.n_sat_lev, a.has_trop);
-  P.R = 8 * P.nchunk;
+  P.nfield = a.has_trop ? 3 : 2;
+  P.scratch_doubles = scratch_doubles(a.n_sat_lev, a.n_ctm_lev, P.nrow);
   OISAT_CHECK_ARG(P.nchunk < 32, "record too wide");
-  P.box = a.box_weight;
-  P.box_err = a.box_weight_err;
-  const size_t smem = fused_smem_bytes(a.n_ctm_lev);
-  static size_t configured = 0;
-  if (smem > configured) {
-    OISAT_CHECK_CUDA(cudaFuncSetAttribute(fused_amf_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  fused_amf_kernel<<<(unsigned)a.n_tiles, kFusedWarps * 32, smem, (cudaStream_t)stream>>>(P);
+  OISAT_CHECK_ARG(a.n_records > 0 && a.n_records * P.nchunk < ((int64_t)1 << 32),
+                  "record block too large for 32-bit chunk indices: split the batch");
+  const int lanes = P.nchunk < 16 ? 16 : 32;
+  const size_t smem = fused_smem_bytes(P, lanes);
+  auto kern = lanes == 16 ? fused_amf_kernel<16> : fused_amf_kernel<32>;
+  OISAT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+  kern<<<(unsigned)a.n_tiles, kFusedThreads, smem, (cudaStream_t)stream>>>(P);
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
 }

@@ -11,6 +11,16 @@
 namespace oisat {
 
 constexpr int kWarpsPerBlock = 4;
+constexpr int kArr = 128;  // >= kMaxSatLev, kMaxCtmLev
+
+struct WarpArrays {
+  double xr[kArr], yr[kArr], xs[kArr], ys[kArr], va[kArr], vb[kArr];
+  __device__ __forceinline__ GroupScratch view() {
+    GroupScratch s;
+    s.xr = xr; s.yr = yr; s.xs = xs; s.ys = ys; s.va = va; s.vb = vb;
+    return s;
+  }
+};
 
 struct CtmView {
   const void* pmid;
@@ -30,7 +40,7 @@ vertical_amf_kernel(int64_t n_items, const int32_t* __restrict__ sat_index,
                     const double* __restrict__ p_sat, const double* __restrict__ sw, int n_sat,
                     int64_t sat_stride, CtmView ctm, int n_ctm, double* __restrict__ new_amf,
                     double* __restrict__ ctm_vcd, double* __restrict__ vcd_out) {
-  __shared__ WarpScratch scratch[kWarpsPerBlock];
+  __shared__ WarpArrays scratch[kWarpsPerBlock];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t item = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
   if (item >= n_items) return;
@@ -41,7 +51,7 @@ vertical_amf_kernel(int64_t n_items, const int32_t* __restrict__ sat_index,
     if (lane == 0) { new_amf[si] = qnan(); ctm_vcd[si] = qnan(); vcd_out[si] = qnan(); }
     return;
   }
-  WarpScratch& s = scratch[warp];
+  const GroupScratch s = scratch[warp].view();
   for (int l = lane; l < n_sat; l += 32) {
     s.xr[l] = log(p_sat[(int64_t)l * sat_stride + si]);
     s.yr[l] = sw[(int64_t)l * sat_stride + si];
@@ -52,18 +62,19 @@ vertical_amf_kernel(int64_t n_items, const int32_t* __restrict__ sat_index,
   double col;
   double namf;
   if (CTM_F32) {
-    namf = warp_amf_cell<true>(
-        s, n_sat, n_ctm, has_trop, tp,
-        [&](int k) { return (double)ld_f32(ctm.pmid, (int64_t)k * ctm.stride + ci); },
+    auto pm = [&](int k) { return (double)ld_f32(ctm.pmid, (int64_t)k * ctm.stride + ci); };
+    namf = group_amf_cell<32, true, false>(
+        s, n_sat, n_ctm, has_trop, tp, pm,
+        [&](int k) { return (double)log_f32(ld_f32(ctm.pmid, (int64_t)k * ctm.stride + ci)); },
         [&](int k) {
           return (double)partial_column_f32(ld_f32(ctm.dp, (int64_t)k * ctm.stride + ci),
                                             ld_f32(ctm.b, (int64_t)k * ctm.stride + ci));
         },
         &col, lane);
   } else {
-    namf = warp_amf_cell<false>(
-        s, n_sat, n_ctm, has_trop, tp,
-        [&](int k) { return ld_f64(ctm.pmid, (int64_t)k * ctm.stride + ci); },
+    auto pm = [&](int k) { return ld_f64(ctm.pmid, (int64_t)k * ctm.stride + ci); };
+    namf = group_amf_cell<32, false, false>(
+        s, n_sat, n_ctm, has_trop, tp, pm, [&](int k) { return log(pm(k)); },
         [&](int k) { return ld_f64(ctm.b, (int64_t)k * ctm.stride + ci); }, &col, lane);
   }
   if (lane == 0) {
@@ -118,11 +129,11 @@ vertical_column_kernel(int64_t n_items, const int32_t* __restrict__ sat_index,
 // (sorted in log pressure) and the satellite levels are the query points.
 // ---------------------------------------------------------------------------
 template <bool CTM_F32>
-__device__ __forceinline__ void load_ctm_table(WarpScratch& s, const CtmView& ctm, int n_ctm,
-                                               int64_t ci, int lane) {
+__device__ __forceinline__ void load_ctm_table(const GroupScratch& s, const CtmView& ctm,
+                                               int n_ctm, int64_t ci, int lane) {
   for (int k = lane; k < n_ctm; k += 32) {
     if (CTM_F32) {
-      s.xr[k] = log_as_f32(ld_f32(ctm.pmid, (int64_t)k * ctm.stride + ci));
+      s.xr[k] = (double)log_f32(ld_f32(ctm.pmid, (int64_t)k * ctm.stride + ci));
       s.yr[k] = (double)ld_f32(ctm.b, (int64_t)k * ctm.stride + ci);
     } else {
       s.xr[k] = log(ld_f64(ctm.pmid, (int64_t)k * ctm.stride + ci));
@@ -130,7 +141,7 @@ __device__ __forceinline__ void load_ctm_table(WarpScratch& s, const CtmView& ct
     }
   }
   __syncwarp();
-  warp_sort_levels(s.xr, s.yr, n_ctm, s.xs, s.ys, lane);
+  group_sort_levels<32>(s.xr, s.yr, n_ctm, s.xs, s.ys, lane);
 }
 
 template <bool CTM_F32>
@@ -142,7 +153,7 @@ vertical_mopitt_kernel(int64_t n_items, const int32_t* __restrict__ sat_index,
                        const double* __restrict__ ap_prof, int n_sat, int64_t sat_stride,
                        CtmView ctm, int n_ctm, double* __restrict__ ctm_vcd,
                        double* __restrict__ ctm_xcol) {
-  __shared__ WarpScratch scratch[kWarpsPerBlock];
+  __shared__ WarpArrays scratch[kWarpsPerBlock];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t item = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
   if (item >= n_items) return;
@@ -153,7 +164,7 @@ vertical_mopitt_kernel(int64_t n_items, const int32_t* __restrict__ sat_index,
     if (lane == 0) { ctm_vcd[si] = qnan(); ctm_xcol[si] = qnan(); }
     return;
   }
-  WarpScratch& s = scratch[warp];
+  const GroupScratch s = scratch[warp].view();
   load_ctm_table<CTM_F32>(s, ctm, n_ctm, ci, lane);
   // interpolate the model profile to the satellite levels and weight with AK[1:]
   for (int l = lane; l < n_sat; l += 32) {
@@ -161,7 +172,7 @@ vertical_mopitt_kernel(int64_t n_items, const int32_t* __restrict__ sat_index,
     double xi;
     if (CTM_F32) {
       // float32 tables: scipy stays on interp1d._call_linear, then NaN outside the range
-      xi = interp1d_linear(s.xs, s.ys, n_ctm, q);
+      xi = interp1d_linear<false>(s.xs, s.ys, n_ctm, q);
       if (q < s.xs[0] || q > s.xs[n_ctm - 1]) xi = qnan();
     } else {
       xi = np_interp_nanfill(s.xs, s.ys, n_ctm, q);
@@ -182,9 +193,9 @@ vertical_mopitt_kernel(int64_t n_items, const int32_t* __restrict__ sat_index,
     }
   }
   __syncwarp();
-  const double part = warp_np_sum<double>(s.va, n_sat, lane);
-  const double air = CTM_F32 ? (double)warp_np_sum<float>(airf, n_ctm, lane)
-                             : warp_np_sum<double>(s.vb, n_ctm, lane);
+  const double part = group_np_sum<double, 32>(s.va, n_sat, lane);
+  const double air = CTM_F32 ? (double)group_np_sum<float, 32>(airf, n_ctm, lane)
+                             : group_np_sum<double, 32>(s.vb, n_ctm, lane);
   if (lane == 0) {
     // surface term uses the bottom model layer as stored (unsorted index 0)
     double x0;
@@ -204,7 +215,7 @@ vertical_gosat_kernel(int64_t n_items, const int32_t* __restrict__ sat_index,
                       const double* __restrict__ p_sat, const double* __restrict__ ak,
                       const double* __restrict__ ap_prof, const double* __restrict__ pw, int n_sat,
                       int64_t sat_stride, CtmView ctm, int n_ctm, double* __restrict__ ctm_xcol) {
-  __shared__ WarpScratch scratch[kWarpsPerBlock];
+  __shared__ WarpArrays scratch[kWarpsPerBlock];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t item = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
   if (item >= n_items) return;
@@ -215,18 +226,18 @@ vertical_gosat_kernel(int64_t n_items, const int32_t* __restrict__ sat_index,
     if (lane == 0) ctm_xcol[si] = qnan();
     return;
   }
-  WarpScratch& s = scratch[warp];
+  const GroupScratch s = scratch[warp].view();
   load_ctm_table<CTM_F32>(s, ctm, n_ctm, ci, lane);
   for (int l = lane; l < n_sat; l += 32) {
     const int64_t e = (int64_t)l * sat_stride + si;
-    const double xi = interp1d_linear(s.xs, s.ys, n_ctm, log(p_sat[e]));
+    const double xi = interp1d_linear<false>(s.xs, s.ys, n_ctm, log(p_sat[e]));
     const double ap = ap_prof[e];
     double t = ap + (xi - ap) * ak[e];
     t = t * pw[e];
     s.va[l] = (t <= 0.0 || t != t) ? 0.0 : t;  // t<=0 -> NaN -> dropped by nansum
   }
   __syncwarp();
-  const double tot = warp_np_sum<double>(s.va, n_sat, lane);
+  const double tot = group_np_sum<double, 32>(s.va, n_sat, lane);
   if (lane == 0) ctm_xcol[si] = tot;
 }
 

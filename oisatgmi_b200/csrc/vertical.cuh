@@ -1,7 +1,10 @@
-// Warp-level building blocks of the per-cell vertical operators (K3).  One warp
-// works on one model cell; per-warp scratch lives in shared memory.  The same
-// routines serve the stand-alone kernels (k3_vertical.cu) and the fused month
-// pipeline (fused_amf.cu), which is what keeps the two paths results-identical.
+// Building blocks of the per-cell vertical operators (K3).  A GROUP of LANES
+// threads (a full warp, or a half warp in the fused month kernel) works on one
+// model cell; group scratch lives in shared memory.  The same routines serve the
+// stand-alone kernels (k3_vertical.cu) and the fused pipeline (fused_amf.cu).
+// All 32 lanes of a warp always execute these routines together (the two halves
+// on different cells), so full-mask shuffles/votes are used and per-group
+// results are extracted with the group's lane mask.
 //
 // Everything that numpy/scipy evaluate in a fixed order is evaluated in that
 // order here (no FMA contraction in this tree, see common.cuh):
@@ -19,7 +22,7 @@
 namespace oisat {
 
 constexpr int kMaxSatLev = 96;   // TEMPO has 72 (reader.py:502-512)
-constexpr int kMaxCtmLev = 128;  // numpy's pairwise block: one leaf
+constexpr int kMaxCtmLev = 127;  // one leaf of numpy's pairwise sum, 7-step search
 
 constexpr float kG0f = 9.80665f;
 constexpr float kMairF = (float)28.97e-3;
@@ -52,15 +55,33 @@ __device__ __forceinline__ float air_column_f32(float dp) {
   return v;
 }
 
+// float32 natural log as numpy evaluates np.log on a float32 array (the result
+// is float32).  CUDA's logf is within 1 ulp; numpy's SIMD kernel within ~4 ulp;
+// the two agree to float32 rounding noise, which is the reference's own noise
+// floor for this term (SURVEY.md A.8).
+__device__ __forceinline__ float log_f32(float p) { return logf(p); }
+
 __device__ __forceinline__ bool nan_less(double a, double b) {
   // numpy's sort/searchsorted order: NaN is larger than everything
   return a < b || (b != b && a == a);
 }
 
-// Pairwise sum (numpy order) of vals[0..n), n <= 128, executed by a full warp.
-// NaNs must already be replaced (nansum) by the caller.  Result on all lanes.
-template <typename T>
-__device__ __forceinline__ T warp_np_sum(const T* vals, int n, int lane) {
+template <int LANES>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+  return LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << (lane & ~(LANES - 1)));
+}
+
+template <int LANES>
+__device__ __forceinline__ bool group_all(bool pred, int lane) {
+  const unsigned m = group_mask<LANES>(lane);
+  return (__ballot_sync(0xffffffffu, pred) & m) == m;
+}
+
+// Pairwise sum (numpy order) of vals[0..n), n <= 128, by the first 8 lanes of the
+// group.  NaNs must already be replaced (nansum).  Result on all lanes of the group.
+template <typename T, int LANES>
+__device__ __forceinline__ T group_np_sum(const T* vals, int n, int lane) {
+  const int gl = lane & (LANES - 1);
   T res;
   if (n < 8) {
     res = (T)0;
@@ -69,14 +90,14 @@ __device__ __forceinline__ T warp_np_sum(const T* vals, int n, int lane) {
   }
   const int body = n - (n % 8);
   T r = (T)0;
-  if (lane < 8) {
-    r = vals[lane];
-    for (int i = 8 + lane; i < body; i += 8) r = r + vals[i];
+  if (gl < 8) {
+    r = vals[gl];
+    for (int i = 8 + gl; i < body; i += 8) r = r + vals[i];
   }
   r = r + __shfl_xor_sync(0xffffffffu, r, 1);
   r = r + __shfl_xor_sync(0xffffffffu, r, 2);
   r = r + __shfl_xor_sync(0xffffffffu, r, 4);
-  res = __shfl_sync(0xffffffffu, r, 0);
+  res = __shfl_sync(0xffffffffu, r, 0, LANES);
   for (int i = body; i < n; ++i) res = res + vals[i];
   return res;
 }
@@ -84,22 +105,24 @@ __device__ __forceinline__ T warp_np_sum(const T* vals, int n, int lane) {
 // Stable ascending argsort of (x, y) pairs held in shared memory, NaN last
 // (np.argsort(kind='mergesort')), written to xs/ys.  Fast paths for the two
 // monotone cases every real profile falls into.
-__device__ __forceinline__ void warp_sort_levels(const double* xr, const double* yr, int n,
-                                                 double* xs, double* ys, int lane) {
+template <int LANES>
+__device__ __forceinline__ void group_sort_levels(const double* xr, const double* yr, int n,
+                                                  double* xs, double* ys, int lane) {
+  const int gl = lane & (LANES - 1);
   bool inc = true, dec = true;
-  for (int i = lane; i + 1 < n; i += 32) {
+  for (int i = gl; i + 1 < n; i += LANES) {
     const double a = xr[i], b = xr[i + 1];
     inc = inc && (a <= b);  // equal keys keep their order under a stable sort
     dec = dec && (a > b);
   }
-  inc = __all_sync(0xffffffffu, inc);
-  dec = __all_sync(0xffffffffu, dec);
+  inc = group_all<LANES>(inc, lane);
+  dec = group_all<LANES>(dec, lane);
   if (inc) {
-    for (int i = lane; i < n; i += 32) { xs[i] = xr[i]; ys[i] = yr[i]; }
+    for (int i = gl; i < n; i += LANES) { xs[i] = xr[i]; ys[i] = yr[i]; }
   } else if (dec) {
-    for (int i = lane; i < n; i += 32) { xs[n - 1 - i] = xr[i]; ys[n - 1 - i] = yr[i]; }
+    for (int i = gl; i < n; i += LANES) { xs[n - 1 - i] = xr[i]; ys[n - 1 - i] = yr[i]; }
   } else {
-    for (int i = lane; i < n; i += 32) {
+    for (int i = gl; i < n; i += LANES) {
       const double xi = xr[i];
       int rank = 0;
       for (int j = 0; j < n; ++j) {
@@ -114,17 +137,26 @@ __device__ __forceinline__ void warp_sort_levels(const double* xr, const double*
   __syncwarp();
 }
 
-// np.searchsorted(xs, v, side='left')
+// np.searchsorted(xs, v, side='left') for n <= 127: fixed trip count, no
+// data-dependent branches (the two halves of a warp search different tables)
+// A NaN table entry compares false, i.e. "larger", like numpy's NaN-last order; a
+// NaN query gives position 0 where numpy gives n, but every caller turns a NaN
+// query into a NaN result whatever the bracket, so the outputs are identical.
 __device__ __forceinline__ int searchsorted_left(const double* xs, int n, double v) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (nan_less(xs[mid], v)) lo = mid + 1; else hi = mid;
+  int pos = 0;
+  for (int step = 1 << (31 - __clz(n)); step >= 1; step >>= 1) {  // uniform trip count
+    const int t = pos + step;
+    const int probe = (t <= n ? t : n) - 1;
+    const bool take = (t <= n) && (xs[probe] < v);
+    pos = take ? t : pos;
   }
-  return lo;
+  return pos;
 }
 
-// interp1d._call_linear (linear extrapolation falls out of the index clipping)
+// interp1d._call_linear (linear extrapolation falls out of the index clipping).
+// FAST: one reciprocal instead of two divisions (differs from scipy in the last
+// bit; used by the fused kernel only).
+template <bool FAST>
 __device__ __forceinline__ double interp1d_linear(const double* xs, const double* ys, int n,
                                                   double v) {
   int idx = searchsorted_left(xs, n, v);
@@ -133,6 +165,10 @@ __device__ __forceinline__ double interp1d_linear(const double* xs, const double
   const double x_lo = xs[idx - 1], x_hi = xs[idx];
   const double y_lo = ys[idx - 1], y_hi = ys[idx];
   const double den = x_hi - x_lo;
+  if (FAST) {
+    const double r = 1.0 / den;
+    return ((v - x_lo) * r) * y_hi + ((x_hi - v) * r) * y_lo;
+  }
   return ((v - x_lo) / den) * y_hi + ((x_hi - v) / den) * y_lo;
 }
 
@@ -160,57 +196,72 @@ __device__ __forceinline__ double np_interp_nanfill(const double* xp, const doub
   return r;
 }
 
-// float32 natural log as numpy evaluates np.log on a float32 array (the result
-// is float32).  CUDA's logf is within 1 ulp; numpy's SIMD kernel within ~4 ulp;
-// the two agree to float32 rounding noise, which is the reference's own noise
-// floor for this term (SURVEY.md A.8).
-__device__ __forceinline__ double log_as_f32(float p) { return (double)logf(p); }
-
-struct WarpScratch {
-  double xr[kMaxSatLev > kMaxCtmLev ? kMaxSatLev : kMaxCtmLev];
-  double yr[kMaxSatLev > kMaxCtmLev ? kMaxSatLev : kMaxCtmLev];
-  double xs[kMaxSatLev > kMaxCtmLev ? kMaxSatLev : kMaxCtmLev];
-  double ys[kMaxSatLev > kMaxCtmLev ? kMaxSatLev : kMaxCtmLev];
-  double va[kMaxCtmLev];
-  double vb[kMaxCtmLev];
+// Group scratch.  In the stand-alone kernels the six arrays are distinct; the
+// fused kernel aliases them to save shared memory: [xs|ys] doubles as the staging
+// area of the gridded rows, and va/vb live in [xr|yr], which is dead once the
+// table is sorted.
+struct GroupScratch {
+  double* xr;
+  double* yr;
+  double* xs;
+  double* ys;
+  double* va;
+  double* vb;
 };
+
+__host__ __device__ inline int scratch_sorted_len(int n_sat, int n_rows) {
+  const int half_rows = (n_rows + 1) / 2;
+  return n_sat > half_rows ? n_sat : half_rows;
+}
+__host__ __device__ inline int scratch_raw_len(int n_sat, int n_ctm) {
+  return n_sat > n_ctm ? n_sat : n_ctm;
+}
+__host__ __device__ inline int scratch_doubles(int n_sat, int n_ctm, int n_rows) {
+  return 2 * scratch_sorted_len(n_sat, n_rows) + 2 * scratch_raw_len(n_sat, n_ctm);
+}
+__device__ __forceinline__ GroupScratch carve_scratch(double* base, int n_sat, int n_ctm,
+                                                      int n_rows) {
+  GroupScratch s;
+  const int a = scratch_sorted_len(n_sat, n_rows), b = scratch_raw_len(n_sat, n_ctm);
+  s.xs = base;
+  s.ys = base + a;
+  s.xr = base + 2 * a;
+  s.yr = base + 2 * a + b;
+  s.va = s.xr;
+  s.vb = s.yr;
+  return s;
+}
 
 // ---------------------------------------------------------------------------
 // AMF recalculation for one cell (amf_recal.py:93-119).  The caller has put
-// log(p_sat) / scattering weights into s.xr / s.yr (n_sat entries).  Model
-// column accessors return level k of this cell.  CTM_F32: native float32 model
-// fields (partial column, log and column sum in float32).
-// Returns new_amf; *col receives the model column (nansum of partial columns).
+// log(p_sat) / scattering weights into s.xr / s.yr (n_sat entries).  Accessors
+// return, for model level k of this cell: pm(k) p_mid, lp(k) log p_mid and pc(k)
+// the partial column -- float32 values widened exactly when CTM_F32 (native
+// model fields: the column sum is then a float32 sum like numpy's), float64
+// otherwise.  Returns new_amf; *col receives nansum(partial column).
 // ---------------------------------------------------------------------------
-template <bool CTM_F32, typename GetPmid, typename GetPc>
-__device__ __forceinline__ double warp_amf_cell(WarpScratch& s, int n_sat, int n_ctm,
-                                                bool has_trop, double trop, GetPmid pmid_at,
-                                                GetPc pc_at, double* col, int lane) {
-  warp_sort_levels(s.xr, s.yr, n_sat, s.xs, s.ys, lane);
-  float* pcf = reinterpret_cast<float*>(s.vb);
-  for (int k = lane; k < n_ctm; k += 32) {
-    double pm, lp, pc;
-    if (CTM_F32) {
-      const float pmf = (float)pmid_at(k);
-      pm = (double)pmf;
-      lp = log_as_f32(pmf);
-      pc = pc_at(k);  // float32 value widened exactly
-    } else {
-      pm = pmid_at(k);
-      lp = log(pm);
-      pc = pc_at(k);
-    }
-    double sw = interp1d_linear(s.xs, s.ys, n_sat, lp);
+template <int LANES, bool CTM_F32, bool FAST, typename GetPm, typename GetLp, typename GetPc>
+__device__ __forceinline__ double group_amf_cell(const GroupScratch& s, int n_sat, int n_ctm,
+                                                 bool has_trop, double trop, GetPm pm_at,
+                                                 GetLp lp_at, GetPc pc_at, double* col, int lane) {
+  const int gl = lane & (LANES - 1);
+  group_sort_levels<LANES>(s.xr, s.yr, n_sat, s.xs, s.ys, lane);
+  double* va = s.va;
+  double* vb = s.vb;
+  float* pcf = reinterpret_cast<float*>(vb);
+  for (int k = gl; k < n_ctm; k += LANES) {
+    double pc = pc_at(k);
+    double sw = interp1d_linear<FAST>(s.xs, s.ys, n_sat, lp_at(k));
     if (isinf(sw)) sw = 0.0;
-    if (has_trop && pm < trop) { sw = qnan(); pc = qnan(); }
+    if (has_trop && pm_at(k) < trop) { sw = qnan(); pc = qnan(); }
     const double prod = sw * pc;
-    s.va[k] = (prod != prod) ? 0.0 : prod;  // nansum: NaN -> 0
-    if (CTM_F32) pcf[k] = (pc != pc) ? 0.0f : (float)pc; else s.vb[k] = (pc != pc) ? 0.0 : pc;
+    va[k] = (prod != prod) ? 0.0 : prod;  // nansum: NaN -> 0
+    if (CTM_F32) pcf[k] = (pc != pc) ? 0.0f : (float)pc; else vb[k] = (pc != pc) ? 0.0 : pc;
   }
   __syncwarp();
-  const double scd = warp_np_sum<double>(s.va, n_ctm, lane);
-  const double vcd_m = CTM_F32 ? (double)warp_np_sum<float>(pcf, n_ctm, lane)
-                               : warp_np_sum<double>(s.vb, n_ctm, lane);
+  const double scd = group_np_sum<double, LANES>(va, n_ctm, lane);
+  const double vcd_m = CTM_F32 ? (double)group_np_sum<float, LANES>(pcf, n_ctm, lane)
+                               : group_np_sum<double, LANES>(vb, n_ctm, lane);
   __syncwarp();
   *col = vcd_m;
   return vcd_m != 0.0 ? scd / vcd_m : qnan();

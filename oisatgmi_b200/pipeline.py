@@ -49,6 +49,7 @@ class MonthPipeline:
         self._stamps, self._fracs = _v.ctm_clock(ctm_data)
         self._ctm_dev = None
         self._tables = None
+        self._buf = None
         self.timings = {}
 
     # ------------------------------------------------------------------ inputs
@@ -79,37 +80,73 @@ class MonthPipeline:
         per = np.asarray(self.ctm_data[0].pressure_mid).shape[0]
         return day * per + hour
 
-    def add_granule(self, sat, pin=False):
-        """Upload one reader record (before gridding) and build its geometry plan.
-        Returns False when the granule is skipped like the reference would
-        (Qhull failure or nothing on the grid, interpolator.py:152-155,165-167)."""
+    FIELDS = ("lon", "lat", "vcd", "sigma", "amf", "qflag", "pmid", "sw", "trop")
+
+    @staticmethod
+    def host_arrays(sat, pin=False):
+        """Reader record -> flat host tensors in the reader's own dtypes (pinned on
+        request, so that uploads are asynchronous DMA copies)."""
+        t = _dev.torch()
         for name in ("vcd", "uncertainty", "pressure_mid", "scattering_weights"):
             if np.asarray(getattr(sat, name)).dtype != np.float16:
                 raise _lib.OisatError("fused path expects float16 %s (reader dtypes)" % name)
-        g = _Granule()
-        lat = np.asarray(sat.latitude_center)
-        lon = np.asarray(sat.longitude_center)
-        g.n_px = lat.size
-        g.nlev = np.shape(sat.pressure_mid)[0]
-        g.has_trop = np.size(sat.tropopause) != 1
-        up = lambda a: _dev.to_device(np.ascontiguousarray(a).reshape(-1), pin=pin)  # noqa: E731
-        g.dev = {
-            "lon": up(_plan.coord_array(lon)), "lat": up(_plan.coord_array(lat)),
-            "vcd": up(sat.vcd), "sigma": up(sat.uncertainty),
-            "amf": up(_dev.native_float(np.asarray(sat.amf))),
-            "qflag": up(_dev.native_float(np.asarray(sat.quality_flag).squeeze())),
-            "pmid": up(sat.pressure_mid), "sw": up(sat.scattering_weights),
-            "trop": up(sat.tropopause) if g.has_trop else None,
+        has_trop = np.size(sat.tropopause) != 1
+        src = {
+            "lon": _plan.coord_array(sat.longitude_center),
+            "lat": _plan.coord_array(sat.latitude_center),
+            "vcd": sat.vcd, "sigma": sat.uncertainty,
+            "amf": _dev.native_float(np.asarray(sat.amf)),
+            "qflag": _dev.native_float(np.asarray(sat.quality_flag).squeeze()),
+            "pmid": sat.pressure_mid, "sw": sat.scattering_weights,
+            "trop": sat.tropopause if has_trop else None,
         }
-        g.plan = _plan.granule_plan(lon, lat, self.gplan, radius=self.grid_size * 2.0,
-                                    lonlat_dev=(g.dev["lon"], g.dev["lat"]), cache=False)
+        out = {}
+        for k, a in src.items():
+            if a is None:
+                out[k] = None
+                continue
+            h = t.from_numpy(np.ascontiguousarray(a).reshape(-1))
+            out[k] = h.pin_memory() if pin else h
+        return out
+
+    def add_granule(self, sat, plan=None, host=None, pin=False):
+        """Upload one reader record (before gridding) and attach its geometry plan
+        (built here unless given).  Returns False when the granule is skipped like
+        the reference would (Qhull failure or nothing on the grid,
+        interpolator.py:152-155,165-167)."""
+        g = _Granule()
+        g.host = host if host is not None else self.host_arrays(sat, pin=pin)
+        g.n_px = int(np.size(sat.latitude_center))
+        g.nlev = np.shape(sat.pressure_mid)[0]
+        g.has_trop = g.host["trop"] is not None
+        dev = _dev.device()
+        g.dev = {k: (None if h is None else h.to(dev, non_blocking=True))
+                 for k, h in g.host.items()}
+        if plan is None:
+            plan = _plan.granule_plan(np.asarray(sat.longitude_center),
+                                      np.asarray(sat.latitude_center), self.gplan,
+                                      radius=self.grid_size * 2.0,
+                                      lonlat_dev=(g.dev["lon"], g.dev["lat"]), cache=False)
+        g.plan = plan
         g.slot = self._slot_of(sat.time)
         g.time = sat.time
         if g.plan is None or g.plan.n_cells == 0:
             return False
         self.granules.append(g)
         self._tables = None
+        self._buf = None
         return True
+
+    def refresh_inputs(self):
+        """Host -> device copy of every granule's reader arrays (the per-step
+        upload of the end-to-end measurement).  Returns the bytes copied."""
+        n = 0
+        for g in self.granules:
+            for k, h in g.host.items():
+                if h is not None:
+                    g.dev[k].copy_(h, non_blocking=True)
+                    n += h.numel() * h.element_size()
+        return n
 
     def input_bytes(self):
         """Bytes of reader-typed pixel data resident on the device."""
@@ -172,31 +209,49 @@ class MonthPipeline:
         g0 = self.granules[0]
         R = int(L.oisat_pack_record_halfs(g0.nlev, int(g0.has_trop)))
         t = _dev.torch()
+        pm, pr, dp = self.upload_ctm()
+        # device table of the batch pack launch
+        items = (_lib.PackItem * len(self.granules))()
+        block0 = 0
+        for i, (g, p0) in enumerate(zip(self.granules, host["px0"])):
+            d = g.dev
+            items[i].sw, items[i].p_mid = d["sw"].data_ptr(), d["pmid"].data_ptr()
+            items[i].vcd, items[i].sigma = d["vcd"].data_ptr(), d["sigma"].data_ptr()
+            items[i].trop = _dev.ptr(d["trop"])
+            items[i].qflag = d["qflag"].data_ptr()
+            items[i].amf = d["amf"].data_ptr()
+            items[i].n_px, items[i].px0, items[i].block0 = g.n_px, int(p0), block0
+            block0 += int(L.oisat_pack_blocks(g.n_px))
+        raw = np.frombuffer(bytes(items), dtype=np.uint8).copy()
         self._buf = dict(
             records=_dev.empty((host["total_px"], R), "float16"),
-            good=_dev.empty((host["total_px"],), "uint8"),
-            amf=t.cat([g.dev["amf"] for g in self.granules]),
+            amf_masked=_dev.empty((host["total_px"],)),
             staged=_dev.empty((5, host["n_pairs"])),
             acc=_dev.zeros((10, self.n_cell)),
+            ctm_logp=t.empty_like(pm), ctm_pcol=t.empty_like(pm),
+            pack_items=_dev.to_device(raw), pack_blocks=block0,
         )
         return self._buf
 
-    def run_pack(self):
-        """Quality mask + pixel-major packing of every granule."""
+    def run_prepare(self):
+        """Derived model fields (float32 log pressure, partial column)."""
         L = _lib.lib()
-        host, _ = self.build_tables()
+        pm, pr, dp = self.upload_ctm()
         buf = self._buf
-        s = _dev.stream()
-        R = buf["records"].shape[1]
-        for g, p0 in zip(self.granules, host["px0"]):
-            d = g.dev
-            _lib.check(L.oisat_quality_mask(d["qflag"].data_ptr(), _dev.dtype_code(d["qflag"]),
-                                            g.n_px, self.flag_thresh,
-                                            buf["good"].data_ptr() + int(p0), s))
-            _lib.check(L.oisat_pack_granule(d["sw"].data_ptr(), d["pmid"].data_ptr(), g.nlev,
-                                            d["vcd"].data_ptr(), d["sigma"].data_ptr(),
-                                            _dev.ptr(d["trop"]), g.n_px,
-                                            buf["records"].data_ptr() + int(p0) * R * 2, s))
+        _lib.check(L.oisat_ctm_prepare(pm.data_ptr(), pr.data_ptr(), dp.data_ptr(), pm.numel(),
+                                       buf["ctm_logp"].data_ptr(), buf["ctm_pcol"].data_ptr(),
+                                       _dev.stream()))
+
+    def run_pack(self):
+        """Quality mask + pixel-major packing of every granule, one launch."""
+        L = _lib.lib()
+        buf = self._buf
+        g0 = self.granules[0]
+        _lib.check(L.oisat_pack_batch(buf["pack_items"].data_ptr(), len(self.granules),
+                                      buf["pack_blocks"], g0.nlev, int(g0.has_trop),
+                                      _dev.dtype_code(g0.dev["qflag"]), self.flag_thresh,
+                                      _dev.dtype_code(g0.dev["amf"]), buf["records"].data_ptr(),
+                                      buf["amf_masked"].data_ptr(), _dev.stream()))
 
     def fused_args(self):
         host, dev = self.build_tables()
@@ -220,13 +275,13 @@ class MonthPipeline:
         a.gran_record0 = dev["gran_px0"].data_ptr()
         a.gran_px0 = dev["gran_px0"].data_ptr()
         a.gran_slot = dev["gran_slot"].data_ptr()
+        a.n_records = host["total_px"]
         a.records = buf["records"].data_ptr()
-        a.good = buf["good"].data_ptr()
-        a.amf = buf["amf"].data_ptr()
-        a.amf_dtype = _dev.dtype_code(buf["amf"])
+        a.amf_masked = buf["amf_masked"].data_ptr()
         a.n_sat_lev = g0.nlev
         a.has_trop = int(g0.has_trop)
-        a.ctm_pmid, a.ctm_prof, a.ctm_dp = pm.data_ptr(), pr.data_ptr(), dp.data_ptr()
+        a.ctm_pmid = pm.data_ptr()
+        a.ctm_logp, a.ctm_pcol = buf["ctm_logp"].data_ptr(), buf["ctm_pcol"].data_ptr()
         a.n_ctm_lev = pm.shape[1]
         a.n_cell = self.n_cell
         a.staged = buf["staged"].data_ptr()
@@ -272,14 +327,30 @@ class MonthPipeline:
                     increment_OI=inc, error_OI=err, knee_index=pick, ak_means=ak_means,
                     factor=float(factors[pick]))
 
-    def run(self):
-        """pack -> fused -> accumulate -> OI on the current stream."""
+    def run(self, marks=None):
+        """pack -> fused -> accumulate -> OI on the current stream.  `marks`
+        (a list) receives (phase, cuda event) pairs recorded on that stream."""
         if getattr(self, "_buf", None) is None:
             self.allocate()
+
+        def mark(name):
+            if marks is not None:
+                e = _dev.torch().cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
+        mark("start")
+        self.run_prepare()
+        mark("prepare")
         self.run_pack()
+        mark("pack")
         self.run_fused()
+        mark("fused")
         self.run_accumulate()
-        return self.run_oi()
+        mark("accumulate")
+        res = self.run_oi()
+        mark("oi")
+        return res
 
     def results_to_host(self, res):
         shape = self.gplan.out_shape

@@ -302,3 +302,49 @@ def clear_caches():
     _grid_plans.clear()
     _granule_plans.clear()
     _nn_tables.clear()
+
+
+# ---------------------------------------------------------------------------
+# many granules at once: K0 on the GPU for all of them, then the host part
+# (Qhull + walk) on every core.  Worker processes are forked AFTER the K0 masks
+# are on the host and never touch CUDA.
+# ---------------------------------------------------------------------------
+_pool_job = None
+
+
+def _pool_worker(i):
+    lons, lats, keeps, gplan, radius = _pool_job
+    p = granule_plan(lons[i], lats[i], gplan, radius, keep=keeps[i], cache=False)
+    if p is None:
+        return None
+    return p.cells, p.vert, p.w
+
+
+def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonlat_dev=None):
+    """Plans for a batch of granules (list of lon/lat arrays)."""
+    import multiprocessing as mp
+    import os
+    global _pool_job
+    n = len(lons)
+    keeps_dev = []
+    for i in range(n):
+        if lonlat_dev is not None:
+            lo, la = lonlat_dev[i]
+        else:
+            lo, la = _dev.to_device(coord_array(lons[i])), _dev.to_device(coord_array(lats[i]))
+        keeps_dev.append(distance_mask(lo, la, gplan, radius))
+    keeps = [_dev.to_host(k).astype(bool) for k in keeps_dev]
+    workers = min(n, workers or os.cpu_count() or 1)
+    _pool_job = (lons, lats, keeps, gplan, radius)
+    try:
+        if workers <= 1:
+            raw = [_pool_worker(i) for i in range(n)]
+        else:
+            with mp.get_context("fork").Pool(workers) as pool:
+                raw = pool.map(_pool_worker, range(n), chunksize=1)
+    finally:
+        _pool_job = None
+    out = []
+    for r, k in zip(raw, keeps):
+        out.append(None if r is None else GranulePlan(gplan, r[0], r[1], r[2], k))
+    return out
