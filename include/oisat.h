@@ -76,6 +76,35 @@ int oisat_distmask(const void* px_lon, const void* px_lat, int32_t coord_dtype, 
                    const double* xs, int64_t W, const double* ys, int64_t H,
                    double radius, uint8_t* keep, void* stream);
 
+/* ---- K1: geometry plan (triangulation on the host, the rest on the device) -----
+ * HOST function: Delaunay triangulation of n points, h_tri receives 3 vertex
+ * indices per triangle (capacity in triangles; 2n is always enough).  Returns the
+ * triangle count, or a negative OISAT_E_* (OISAT_E_UNSUPPORTED: no triangle
+ * exists -- scipy.spatial.Delaunay raises for such input and the reference
+ * skips the granule, interpolator.py:152-155).  *n_ties counts exactly collinear /
+ * co-circular configurations met while deciding: if it is non-zero the
+ * triangulation is not unique and callers that need Qhull's choice must use it. */
+int64_t oisat_h_delaunay(const double* h_x, const double* h_y, int64_t n, int32_t* h_tri,
+                         int64_t tri_capacity, int64_t* n_ties);
+
+/* node_tri[f] (caller pre-fills with INT32_MAX) <- lowest index of a triangle that
+ * contains mesh node f by scipy's rule (barycentric coordinates within
+ * [-eps, 1+eps], eps = 100*DBL_EPSILON); only nodes with keep[f] != 0 are tested. */
+int oisat_locate(const int32_t* tri, int64_t n_tri, const void* px, const void* py,
+                 int32_t coord_dtype, const double* xs, int64_t W, const double* ys, int64_t H,
+                 const uint8_t* keep, int32_t* node_tri, void* stream);
+
+/* cell_ok[c] = nn_ok[c] and every node window[c*nwin + k] is located */
+int oisat_plan_cells(const int32_t* window, int32_t nwin, const uint8_t* nn_ok, int64_t n_cell,
+                     const int32_t* node_tri, uint8_t* cell_ok, void* stream);
+
+/* stencil of the kept cells: vertices and barycentric weights of every window node,
+ * pair-major ([cell][3*nwin], fused kernel) or stencil-major ([3*nwin][cell], K2) */
+int oisat_plan_fill(const int32_t* cells, int64_t n_cells, const int32_t* window, int32_t nwin,
+                    const int32_t* node_tri, const int32_t* tri, const void* px, const void* py,
+                    int32_t coord_dtype, const double* xs, int64_t W, const double* ys,
+                    int32_t pair_major, int32_t* vert, double* w, void* stream);
+
 /* good[p] = (quality_flag[p] > thresh)  (interpolator.py:126-128) */
 int oisat_quality_mask(const void* qflag, int32_t dtype, int64_t n_px, double thresh,
                        uint8_t* good, void* stream);

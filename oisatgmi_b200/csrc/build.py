@@ -16,12 +16,12 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["api.cu", "k0_geometry.cu", "k2_interp.cu", "k3_vertical.cu", "k4_accum.cu",
-           "k5_oi.cu", "fused_amf.cu"]
+SOURCES = ["api.cu", "k0_geometry.cu", "k1_locate.cu", "k2_interp.cu", "k3_vertical.cu",
+           "k4_accum.cu", "k5_oi.cu", "fused_amf.cu", "delaunay.cpp"]
 HEADERS = ["common.cuh", "vertical.cuh", os.path.join("..", "..", "include", "oisat.h")]
 LIB = os.path.join(HERE, "liboisat.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--fmad=false", "-Xcompiler", "-fPIC",
+              "--fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
               "--expt-relaxed-constexpr", "--extended-lambda"]
 
 
@@ -52,7 +52,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(HERE, src.replace(".cu", ".o"))
+        obj = os.path.join(HERE, os.path.splitext(src)[0] + ".o")
+        assert obj.endswith(".o") and obj != os.path.join(HERE, src)
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", os.path.join(HERE, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

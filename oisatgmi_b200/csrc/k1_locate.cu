@@ -1,0 +1,239 @@
+// K1: geometry plan on the GPU (plan builder v1).
+//
+//   oisat_locate      which Delaunay triangle contains each node of the working
+//                     mesh -- what LinearNDInterpolator's directed walk answers
+//                     point by point on the host (interpolator.py:13-15; 13 s per
+//                     TROPOMI granule).  Here every TRIANGLE rasterises its own
+//                     bounding box and claims the nodes it contains, with scipy's
+//                     acceptance rule (all barycentric coordinates within
+//                     [-eps, 1+eps], eps = 100*DBL_EPSILON, qhull._find_simplex).
+//                     A node on a shared edge is claimed by the lowest triangle
+//                     index; both candidates interpolate to the same value there.
+//   oisat_plan_cells  per model cell: is every node of its box window located
+//                     (inside the hull and within reach of a pixel)?
+//   oisat_plan_fill   vertices and barycentric weights of every window node of
+//                     every kept cell: the stencil K2 / the fused kernel consume.
+#include <climits>
+
+#include "common.cuh"
+
+namespace oisat {
+
+constexpr double kLocateEps = 100.0 * 2.220446049250313e-16;  // scipy: eps = 100 * DBL_EPSILON
+constexpr int kSmallBox = 64;  // nodes a single thread rasterises on its own
+
+template <typename T>
+struct Coords {
+  const T* x;
+  const T* y;
+  __device__ __forceinline__ double px(int32_t i) const { return (double)x[i]; }
+  __device__ __forceinline__ double py(int32_t i) const { return (double)y[i]; }
+};
+
+struct TriGeom {
+  double x2, y2;          // reference vertex (scipy: r = last vertex)
+  double t00, t01, t10, t11;  // inverse of [[x0-x2, x1-x2], [y0-y2, y1-y2]]
+  bool ok;
+};
+
+__device__ __forceinline__ TriGeom tri_geom(double x0, double y0, double x1, double y1, double x2,
+                                            double y2) {
+  TriGeom g;
+  const double a = x0 - x2, b = x1 - x2, c = y0 - y2, d = y1 - y2;
+  const double det = a * d - b * c;
+  const double r = 1.0 / det;
+  g.x2 = x2; g.y2 = y2;
+  g.t00 = d * r; g.t01 = -b * r;
+  g.t10 = -c * r; g.t11 = a * r;
+  g.ok = det != 0.0 && det == det;
+  return g;
+}
+
+// barycentric coordinates as scipy evaluates them (qhull._barycentric_coordinates)
+__device__ __forceinline__ void bary(const TriGeom& g, double qx, double qy, double* c) {
+  const double d0 = qx - g.x2, d1 = qy - g.y2;
+  c[0] = __dadd_rn(__dmul_rn(g.t00, d0), __dmul_rn(g.t01, d1));
+  c[1] = __dadd_rn(__dmul_rn(g.t10, d0), __dmul_rn(g.t11, d1));
+  c[2] = __dsub_rn(__dsub_rn(1.0, c[0]), c[1]);
+}
+
+__device__ __forceinline__ bool inside(const double* c) {
+  return c[0] >= -kLocateEps && c[0] <= 1.0 + kLocateEps && c[1] >= -kLocateEps &&
+         c[1] <= 1.0 + kLocateEps && c[2] >= -kLocateEps && c[2] <= 1.0 + kLocateEps;
+}
+
+struct Box {
+  int i0, i1, j0, j1;
+  __device__ __forceinline__ int64_t count() const {
+    return (i1 < i0 || j1 < j0) ? 0 : (int64_t)(i1 - i0 + 1) * (j1 - j0 + 1);
+  }
+};
+
+__device__ __forceinline__ Box node_box(double xmin, double xmax, double ymin, double ymax,
+                                        const double* xs, int64_t W, const double* ys, int64_t H) {
+  const double x0 = xs[0], y0 = ys[0];
+  const double sx = W > 1 ? (xs[W - 1] - x0) / (double)(W - 1) : 1.0;
+  const double sy = H > 1 ? (ys[H - 1] - y0) / (double)(H - 1) : 1.0;
+  Box b;
+  // one node of slack on each side; the inside test is what decides
+  const double fi0 = floor((xmin - x0) / sx) - 1.0, fi1 = ceil((xmax - x0) / sx) + 1.0;
+  const double fj0 = floor((ymin - y0) / sy) - 1.0, fj1 = ceil((ymax - y0) / sy) + 1.0;
+  b.i0 = fi0 < 0.0 ? 0 : (fi0 > (double)(W - 1) ? (int)W : (int)fi0);
+  b.i1 = fi1 > (double)(W - 1) ? (int)W - 1 : (fi1 < 0.0 ? -1 : (int)fi1);
+  b.j0 = fj0 < 0.0 ? 0 : (fj0 > (double)(H - 1) ? (int)H : (int)fj0);
+  b.j1 = fj1 > (double)(H - 1) ? (int)H - 1 : (fj1 < 0.0 ? -1 : (int)fj1);
+  return b;
+}
+
+__device__ __forceinline__ void claim(const TriGeom& g, int32_t t, int i, int j,
+                                      const double* xs, const double* ys, int64_t W,
+                                      const uint8_t* keep, int32_t* node_tri) {
+  const int64_t f = (int64_t)j * W + i;
+  if (!keep[f]) return;
+  double c[3];
+  bary(g, xs[i], ys[j], c);
+  if (inside(c)) atomicMin(&node_tri[f], t);
+}
+
+// thread = triangle.  Small boxes are rasterised by the thread itself; larger ones
+// (hull pockets, date-line crossers) by the whole warp, lane-strided.
+template <typename T>
+__global__ void __launch_bounds__(256)
+locate_kernel(const int32_t* __restrict__ tri, int64_t n_tri, Coords<T> P,
+              const double* __restrict__ xs, int64_t W, const double* __restrict__ ys, int64_t H,
+              const uint8_t* __restrict__ keep, int32_t* __restrict__ node_tri) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  TriGeom g;
+  g.ok = false;
+  Box b{0, -1, 0, -1};
+  if (t < n_tri) {
+    const int32_t v0 = tri[3 * t], v1 = tri[3 * t + 1], v2 = tri[3 * t + 2];
+    const double x0 = P.px(v0), y0 = P.py(v0), x1 = P.px(v1), y1 = P.py(v1), x2 = P.px(v2),
+                 y2 = P.py(v2);
+    g = tri_geom(x0, y0, x1, y1, x2, y2);
+    if (g.ok)
+      b = node_box(fmin(x0, fmin(x1, x2)), fmax(x0, fmax(x1, x2)), fmin(y0, fmin(y1, y2)),
+                   fmax(y0, fmax(y1, y2)), xs, W, ys, H);
+  }
+  const int64_t cnt = g.ok ? b.count() : 0;
+  if (cnt > 0 && cnt <= kSmallBox) {
+    for (int j = b.j0; j <= b.j1; ++j)
+      for (int i = b.i0; i <= b.i1; ++i) claim(g, (int32_t)t, i, j, xs, ys, W, keep, node_tri);
+  }
+  unsigned big = __ballot_sync(0xffffffffu, cnt > kSmallBox);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    TriGeom h;
+    h.x2 = __shfl_sync(0xffffffffu, g.x2, src); h.y2 = __shfl_sync(0xffffffffu, g.y2, src);
+    h.t00 = __shfl_sync(0xffffffffu, g.t00, src); h.t01 = __shfl_sync(0xffffffffu, g.t01, src);
+    h.t10 = __shfl_sync(0xffffffffu, g.t10, src); h.t11 = __shfl_sync(0xffffffffu, g.t11, src);
+    const int i0 = __shfl_sync(0xffffffffu, b.i0, src), i1 = __shfl_sync(0xffffffffu, b.i1, src);
+    const int j0 = __shfl_sync(0xffffffffu, b.j0, src), j1 = __shfl_sync(0xffffffffu, b.j1, src);
+    const int32_t tt = (int32_t)__shfl_sync(0xffffffffu, (long long)t, src);
+    const int bw = i1 - i0 + 1;
+    const int64_t total = (int64_t)bw * (j1 - j0 + 1);
+    for (int64_t k = lane; k < total; k += 32)
+      claim(h, tt, i0 + (int)(k % bw), j0 + (int)(k / bw), xs, ys, W, keep, node_tri);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+plan_cells_kernel(const int32_t* __restrict__ window, int nwin, const uint8_t* __restrict__ nn_ok,
+                  int64_t n_cell, const int32_t* __restrict__ node_tri,
+                  uint8_t* __restrict__ cell_ok) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cell) return;
+  bool ok = nn_ok == nullptr || nn_ok[c] != 0;
+  for (int k = 0; ok && k < nwin; ++k) ok = node_tri[window[c * nwin + k]] != INT_MAX;
+  cell_ok[c] = ok ? 1 : 0;
+}
+
+// thread = (kept cell, window node)
+template <typename T>
+__global__ void __launch_bounds__(256)
+plan_fill_kernel(const int32_t* __restrict__ cells, int64_t n_cells,
+                 const int32_t* __restrict__ window, int nwin,
+                 const int32_t* __restrict__ node_tri, const int32_t* __restrict__ tri,
+                 Coords<T> P, const double* __restrict__ xs, int64_t W,
+                 const double* __restrict__ ys, int pair_major, int32_t* __restrict__ vert,
+                 double* __restrict__ w) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_cells * nwin) return;
+  const int64_t p = idx / nwin;
+  const int k = (int)(idx - p * nwin);
+  const int32_t f = window[(int64_t)cells[p] * nwin + k];
+  const int32_t t = node_tri[f];
+  const int32_t v[3] = {tri[3 * (int64_t)t], tri[3 * (int64_t)t + 1], tri[3 * (int64_t)t + 2]};
+  const TriGeom g = tri_geom(P.px(v[0]), P.py(v[0]), P.px(v[1]), P.py(v[1]), P.px(v[2]),
+                             P.py(v[2]));
+  double c[3];
+  bary(g, xs[f % W], ys[f / W], c);
+  const int S = 3 * nwin;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int64_t o = pair_major ? p * S + 3 * k + j : (int64_t)(3 * k + j) * n_cells + p;
+    vert[o] = v[j];
+    w[o] = c[j];
+  }
+}
+
+}  // namespace oisat
+
+using namespace oisat;
+
+extern "C" int oisat_locate(const int32_t* tri, int64_t n_tri, const void* px, const void* py,
+                            int32_t coord_dtype, const double* xs, int64_t W, const double* ys,
+                            int64_t H, const uint8_t* keep, int32_t* node_tri, void* stream) {
+  if (n_tri <= 0) return OISAT_OK;
+  OISAT_CHECK_ARG(tri && px && py && xs && ys && keep && node_tri, "null pointer");
+  OISAT_CHECK_ARG(coord_dtype == OISAT_F32 || coord_dtype == OISAT_F64, "coords must be f32/f64");
+  OISAT_CHECK_ARG(W >= 1 && H >= 1 && W * H < (int64_t)INT_MAX, "bad mesh extent");
+  const unsigned blocks = (unsigned)ceil_div(n_tri, 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (coord_dtype == OISAT_F32)
+    locate_kernel<float><<<blocks, 256, 0, s>>>(tri, n_tri,
+                                               Coords<float>{(const float*)px, (const float*)py},
+                                               xs, W, ys, H, keep, node_tri);
+  else
+    locate_kernel<double><<<blocks, 256, 0, s>>>(
+        tri, n_tri, Coords<double>{(const double*)px, (const double*)py}, xs, W, ys, H, keep,
+        node_tri);
+  OISAT_CHECK_LAUNCH();
+  return OISAT_OK;
+}
+
+extern "C" int oisat_plan_cells(const int32_t* window, int32_t nwin, const uint8_t* nn_ok,
+                                int64_t n_cell, const int32_t* node_tri, uint8_t* cell_ok,
+                                void* stream) {
+  if (n_cell <= 0) return OISAT_OK;
+  OISAT_CHECK_ARG(window && node_tri && cell_ok && nwin >= 1, "null pointer");
+  plan_cells_kernel<<<(unsigned)ceil_div(n_cell, 256), 256, 0, (cudaStream_t)stream>>>(
+      window, nwin, nn_ok, n_cell, node_tri, cell_ok);
+  OISAT_CHECK_LAUNCH();
+  return OISAT_OK;
+}
+
+extern "C" int oisat_plan_fill(const int32_t* cells, int64_t n_cells, const int32_t* window,
+                               int32_t nwin, const int32_t* node_tri, const int32_t* tri,
+                               const void* px, const void* py, int32_t coord_dtype,
+                               const double* xs, int64_t W, const double* ys, int32_t pair_major,
+                               int32_t* vert, double* w, void* stream) {
+  if (n_cells <= 0) return OISAT_OK;
+  OISAT_CHECK_ARG(cells && window && node_tri && tri && px && py && xs && ys && vert && w,
+                  "null pointer");
+  OISAT_CHECK_ARG(coord_dtype == OISAT_F32 || coord_dtype == OISAT_F64, "coords must be f32/f64");
+  const unsigned blocks = (unsigned)ceil_div(n_cells * nwin, 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (coord_dtype == OISAT_F32)
+    plan_fill_kernel<float><<<blocks, 256, 0, s>>>(
+        cells, n_cells, window, nwin, node_tri, tri,
+        Coords<float>{(const float*)px, (const float*)py}, xs, W, ys, pair_major, vert, w);
+  else
+    plan_fill_kernel<double><<<blocks, 256, 0, s>>>(
+        cells, n_cells, window, nwin, node_tri, tri,
+        Coords<double>{(const double*)px, (const double*)py}, xs, W, ys, pair_major, vert, w);
+  OISAT_CHECK_LAUNCH();
+  return OISAT_OK;
+}

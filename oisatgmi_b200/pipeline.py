@@ -171,8 +171,11 @@ class MonthPipeline:
         S = 3 * self.gplan.nwin
         cells = np.concatenate([g.plan.cells for g in G]).astype(np.int64)
         gran = np.concatenate([np.full(g.plan.n_cells, i, np.int32) for i, g in enumerate(G)])
-        vert = np.concatenate([g.plan.vert.T for g in G]).astype(np.int32)   # (n_pairs, S)
-        w = np.concatenate([g.plan.w.T for g in G])
+        # stencil entries stay on the device (pair-major); only `cells` is host data
+        t = _dev.torch()
+        pairs = [g.plan.dev_pairs() for g in G]
+        vert = t.cat([p[0] for p in pairs]) if len(pairs) > 1 else pairs[0][0]   # (n_pairs, S)
+        w = t.cat([p[1] for p in pairs]) if len(pairs) > 1 else pairs[0][1]
         n_pairs = cells.size
         # tiles: runs of pairs of one granule inside one 32-aligned cell segment
         tid = gran.astype(np.int64) * ((self.n_cell + 31) // 32 + 1) + cells // 32
@@ -190,8 +193,7 @@ class MonthPipeline:
         host = dict(n_pairs=n_pairs, n_tiles=len(starts), S=S, px0=px0,
                     total_px=int(sum(g.n_px for g in G)))
         d = _dev.to_device
-        dev = dict(vert=d(np.ascontiguousarray(vert)), w=d(np.ascontiguousarray(w)),
-                   tile_pair0=d(tile_pair0), tile_gran=d(tile_gran), tile_cell0=d(tile_cell0),
+        dev = dict(vert=vert, w=w, tile_pair0=d(tile_pair0), tile_gran=d(tile_gran), tile_cell0=d(tile_cell0),
                    tile_mask=d(tile_mask.view(np.int32)), seg_start=d(seg_start),
                    seg_pair=d(order), gran_px0=d(px0),
                    gran_slot=d(np.array([g.slot for g in G], np.int32)))

@@ -166,6 +166,13 @@ class GridPlan:
             self._dev_axes = (_dev.to_device(self.lon_axis), _dev.to_device(self.lat_axis))
         return self._dev_axes
 
+    def dev_tables(self):
+        """(window (n_cell, nwin) int32, nn_ok (n_cell) uint8) on the device."""
+        if getattr(self, "_dev_tables", None) is None:
+            self._dev_tables = (_dev.to_device(self.window.astype(np.int32)),
+                                _dev.to_device(self.nn_ok.astype(np.uint8)))
+        return self._dev_tables
+
 
 def grid_plan(coords, grid_size, mesh=None) -> GridPlan:
     key = (float(grid_size), _digest(coords["Latitude"], coords["Longitude"]),
@@ -187,28 +194,60 @@ def distance_mask(lon_dev, lat_dev, gplan: GridPlan, radius: float) -> np.ndarra
 
 
 class GranulePlan:
-    """Per-granule stencil: `cells` (flat output index), `vert`/`w` of shape
-    (3*nwin, n_cells)."""
+    """Per-granule stencil: `cells` (flat output index of every kept cell, host
+    int64) plus, for each kept cell, the 3*nwin (vertex, weight) entries.  The
+    entries live either on the host (built by scipy, v0: `vert`/`w`,
+    stencil-major (3*nwin, n_cells)) or on the device (built by K1, v1: pair-major
+    (n_cells, 3*nwin)); the accessors convert lazily."""
 
-    def __init__(self, gplan, cells, vert, w, keep=None):
+    def __init__(self, gplan, cells, vert=None, w=None, keep=None, dev_pairs=None, builder="v0"):
         self.gplan = gplan
-        self.keep = keep  # bool over mesh nodes: K0 predicate
+        self.keep = keep  # bool over mesh nodes (K0 predicate); host array or None
         self.cells = cells
-        self.vert = vert
-        self.w = w
         self.n_cells = int(cells.size)
         self.nwin = gplan.nwin
-        self._dev = None
+        self.builder = builder
+        self._host = None if vert is None else (vert, w)
+        self._pairs = dev_pairs      # (vert (n, S) int32, w (n, S) float64) device tensors
+        self._stencil = None         # (cells int32, vert (S, n), w (S, n)) device tensors
+
+    @property
+    def vert(self):
+        return self._host_arrays()[0]
+
+    @property
+    def w(self):
+        return self._host_arrays()[1]
+
+    def _host_arrays(self):
+        if self._host is None:
+            v, w = self._pairs
+            self._host = (np.ascontiguousarray(_dev.to_host(v).T),
+                          np.ascontiguousarray(_dev.to_host(w).T))
+        return self._host
+
+    def dev_pairs(self):
+        """Pair-major device tensors for the fused kernel."""
+        if self._pairs is None:
+            v, w = self._host
+            self._pairs = (_dev.to_device(np.ascontiguousarray(v.T)),
+                           _dev.to_device(np.ascontiguousarray(w.T)))
+        return self._pairs
 
     def dev(self):
-        if self._dev is None:
-            self._dev = (_dev.to_device(self.cells.astype(np.int32)),
-                         _dev.to_device(self.vert), _dev.to_device(self.w))
-        return self._dev
+        """(cells, vert, w) stencil-major device tensors for K2."""
+        if self._stencil is None:
+            cells = _dev.to_device(self.cells.astype(np.int32))
+            if self._host is not None:
+                self._stencil = (cells, _dev.to_device(self._host[0]), _dev.to_device(self._host[1]))
+            else:
+                v, w = self._pairs
+                self._stencil = (cells, v.t().contiguous(), w.t().contiguous())
+        return self._stencil
 
 
 def coord_array(a):
-    """Pixel coordinates for K0: float32/float64 as delivered, anything else
+    """Pixel coordinates for K0/K1: float32/float64 as delivered, anything else
     (e.g. the filler's float16 mesh) widened exactly to float64."""
     a = np.asarray(a)
     if a.dtype not in (np.float32, np.float64):
@@ -221,6 +260,24 @@ def triangulate(lon, lat):
     pts[:, 0] = np.asarray(lon).flatten()
     pts[:, 1] = np.asarray(lat).flatten()
     return Delaunay(pts)  # Qhull; raises on degenerate input (caller returns None)
+
+
+def native_delaunay(lon, lat):
+    """oisat_h_delaunay (csrc/delaunay.cpp): (triangles (n_tri, 3) int32, n_ties),
+    or (None, 0) when no triangle exists.  The call releases the GIL."""
+    import ctypes as C
+    L = _lib.lib()
+    x = np.ascontiguousarray(np.asarray(lon, dtype=np.float64).ravel())
+    y = np.ascontiguousarray(np.asarray(lat, dtype=np.float64).ravel())
+    n = x.size
+    if n < 3:
+        return None, 0
+    tri = np.empty((2 * n, 3), dtype=np.int32)
+    ties = C.c_int64(0)
+    nt = L.oisat_h_delaunay(x.ctypes.data, y.ctypes.data, n, tri.ctypes.data, 2 * n, C.byref(ties))
+    if nt <= 0:
+        return None, 0
+    return tri[:nt], int(ties.value)
 
 
 def locate(tri, qx, qy):
@@ -242,30 +299,17 @@ def locate(tri, qx, qy):
     return s, verts, wts
 
 
-def granule_plan(lon, lat, gplan: GridPlan, radius: float, lonlat_dev=None, cache=True,
-                 keep=None):
-    """Build (or fetch) the stencil of one granule.  Returns None when Qhull
-    cannot triangulate the pixel centres (interpolator.py:152-155).  `keep`
-    (host bool array over the mesh nodes) replaces the K0 launch; it exists so
-    that the host-side composition can be unit-tested without a GPU."""
-    lon = np.asarray(lon)
-    lat = np.asarray(lat)
-    key = (_digest(lon, lat), gplan.key, float(radius))
-    if cache and key in _granule_plans:
-        _granule_plans.move_to_end(key)
-        return _granule_plans[key]
-    keep_dev = None
-    if keep is None:
-        if lonlat_dev is None:
-            lonlat_dev = (_dev.to_device(coord_array(lon)), _dev.to_device(coord_array(lat)))
-        keep_dev = distance_mask(lonlat_dev[0], lonlat_dev[1], gplan, radius)  # async
+def _plan_mode():
+    import os
+    return os.environ.get("OISAT_PLAN", "auto")
+
+
+def _plan_v0(lon, lat, gplan, keep):
+    """Host plan: Qhull + scipy's directed walk (exact for every input class)."""
     try:
-        tri = triangulate(lon, lat)  # Qhull runs while K0 is in flight
+        tri = triangulate(lon, lat)
     except Exception:
         return None
-    if keep_dev is not None:
-        keep = _dev.to_host(keep_dev)
-    keep = np.asarray(keep).astype(bool).ravel()
     n_nodes = gplan.H * gplan.W
     if n_nodes <= FULL_WALK_MAX_NODES:
         cand = np.arange(n_nodes)
@@ -290,8 +334,78 @@ def granule_plan(lon, lat, gplan: GridPlan, radius: float, lonlat_dev=None, cach
     S = 3 * gplan.nwin
     vert = np.ascontiguousarray(verts[sel].reshape(len(cells), S).T)   # (3*nwin, n)
     w = np.ascontiguousarray(wts[sel].reshape(len(cells), S).T)
-    plan = GranulePlan(gplan, cells, vert.astype(np.int32), w, keep)
-    if cache:
+    return GranulePlan(gplan, cells, vert.astype(np.int32), w, keep, builder="v0")
+
+
+def _plan_v1_device(tri_host, lonlat_dev, gplan, keep_dev):
+    """Device part of the v1 plan: point location (K1), per-cell validity, and the
+    stencil fill.  Only the per-cell flags (n_cell bytes) visit the host."""
+    L = _lib.lib()
+    t = _dev.torch()
+    lo, la = lonlat_dev
+    xs, ys = gplan.dev_axes()
+    window, nn_ok = gplan.dev_tables()
+    tri = _dev.to_device(tri_host)
+    node_tri = _dev.full((gplan.H * gplan.W,), 2 ** 31 - 1, "int32")
+    code = _dev.dtype_code(lo)
+    s = _dev.stream()
+    _lib.check(L.oisat_locate(tri.data_ptr(), tri.shape[0], lo.data_ptr(), la.data_ptr(), code,
+                              xs.data_ptr(), gplan.W, ys.data_ptr(), gplan.H, keep_dev.data_ptr(),
+                              node_tri.data_ptr(), s))
+    n_cell = int(np.prod(gplan.out_shape))
+    ok = _dev.empty((n_cell,), "uint8")
+    _lib.check(L.oisat_plan_cells(window.data_ptr(), gplan.nwin, nn_ok.data_ptr(), n_cell,
+                                  node_tri.data_ptr(), ok.data_ptr(), s))
+    cells = np.flatnonzero(_dev.to_host(ok))
+    n = cells.size
+    S = 3 * gplan.nwin
+    vert = _dev.empty((n, S), "int32")
+    w = _dev.empty((n, S))
+    if n:
+        cells_d = _dev.to_device(cells.astype(np.int32))
+        _lib.check(L.oisat_plan_fill(cells_d.data_ptr(), n, window.data_ptr(), gplan.nwin,
+                                     node_tri.data_ptr(), tri.data_ptr(), lo.data_ptr(),
+                                     la.data_ptr(), code, xs.data_ptr(), gplan.W, ys.data_ptr(), 1,
+                                     vert.data_ptr(), w.data_ptr(), s))
+    return GranulePlan(gplan, cells, keep=None, dev_pairs=(vert, w), builder="v1")
+
+
+def granule_plan(lon, lat, gplan: GridPlan, radius: float, lonlat_dev=None, cache=True,
+                 keep=None):
+    """Build (or fetch) the stencil of one granule.  Returns None when the pixel
+    centres cannot be triangulated (interpolator.py:152-155).
+
+    Builder v1 (default for model-grid targets): native Delaunay on the host,
+    point location and stencil assembly on the GPU.  It is used when the native
+    triangulation met no exact tie (collinear / co-circular input), i.e. when the
+    Delaunay triangulation is unique and therefore the one Qhull returns; lattice
+    inputs (MOPITT L3, GOSAT second pass) tie everywhere and go through builder v0
+    (Qhull + scipy's own walk), cached by geometry.  OISAT_PLAN=v0 forces v0.
+    `keep` (host bool array over the mesh nodes) replaces the K0 launch and forces
+    v0; it exists so that the host-side composition can be unit-tested without a GPU."""
+    lon = np.asarray(lon)
+    lat = np.asarray(lat)
+    key = (_digest(lon, lat), gplan.key, float(radius))
+    if cache and key in _granule_plans:
+        _granule_plans.move_to_end(key)
+        return _granule_plans[key]
+    plan = None
+    if keep is not None:
+        plan = _plan_v0(lon, lat, gplan, np.asarray(keep).astype(bool).ravel())
+    else:
+        if lonlat_dev is None:
+            lonlat_dev = (_dev.to_device(coord_array(lon)), _dev.to_device(coord_array(lat)))
+        keep_dev = distance_mask(lonlat_dev[0], lonlat_dev[1], gplan, radius)  # async
+        use_v1 = gplan.upscale and _plan_mode() != "v0"
+        if use_v1:
+            tri, ties = native_delaunay(lon, lat)   # runs while K0 is in flight
+            if tri is None:
+                return None
+            if ties == 0 or _plan_mode() == "v1":
+                plan = _plan_v1_device(tri, lonlat_dev, gplan, keep_dev)
+        if plan is None:
+            plan = _plan_v0(lon, lat, gplan, _dev.to_host(keep_dev).astype(bool))
+    if plan is not None and cache:
         _granule_plans[key] = plan
         while len(_granule_plans) > _granule_plans.cap:
             _granule_plans.popitem(last=False)
@@ -304,47 +418,29 @@ def clear_caches():
     _nn_tables.clear()
 
 
-# ---------------------------------------------------------------------------
-# many granules at once: K0 on the GPU for all of them, then the host part
-# (Qhull + walk) on every core.  Worker processes are forked AFTER the K0 masks
-# are on the host and never touch CUDA.
-# ---------------------------------------------------------------------------
-_pool_job = None
-
-
-def _pool_worker(i):
-    lons, lats, keeps, gplan, radius = _pool_job
-    p = granule_plan(lons[i], lats[i], gplan, radius, keep=keeps[i], cache=False)
-    if p is None:
-        return None
-    return p.cells, p.vert, p.w
-
-
 def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonlat_dev=None):
-    """Plans for a batch of granules (list of lon/lat arrays)."""
-    import multiprocessing as mp
+    """Plans for a batch of granules (lists of lon/lat arrays): K0 for all of them,
+    the native triangulations on a thread pool (the C call releases the GIL), then
+    the device part granule by granule."""
     import os
-    global _pool_job
+    from concurrent.futures import ThreadPoolExecutor
     n = len(lons)
-    keeps_dev = []
-    for i in range(n):
-        if lonlat_dev is not None:
-            lo, la = lonlat_dev[i]
-        else:
-            lo, la = _dev.to_device(coord_array(lons[i])), _dev.to_device(coord_array(lats[i]))
-        keeps_dev.append(distance_mask(lo, la, gplan, radius))
-    keeps = [_dev.to_host(k).astype(bool) for k in keeps_dev]
-    workers = min(n, workers or os.cpu_count() or 1)
-    _pool_job = (lons, lats, keeps, gplan, radius)
-    try:
-        if workers <= 1:
-            raw = [_pool_worker(i) for i in range(n)]
-        else:
-            with mp.get_context("fork").Pool(workers) as pool:
-                raw = pool.map(_pool_worker, range(n), chunksize=1)
-    finally:
-        _pool_job = None
+    if lonlat_dev is None:
+        lonlat_dev = [(_dev.to_device(coord_array(lons[i])), _dev.to_device(coord_array(lats[i])))
+                      for i in range(n)]
+    keeps = [distance_mask(lo, la, gplan, radius) for lo, la in lonlat_dev]
+    if not gplan.upscale or _plan_mode() == "v0":
+        return [granule_plan(lons[i], lats[i], gplan, radius, lonlat_dev=lonlat_dev[i], cache=False)
+                for i in range(n)]
+    workers = max(1, min(n, workers or os.cpu_count() or 1))
+    with ThreadPoolExecutor(workers) as ex:
+        tris = list(ex.map(lambda i: native_delaunay(lons[i], lats[i]), range(n)))
     out = []
-    for r, k in zip(raw, keeps):
-        out.append(None if r is None else GranulePlan(gplan, r[0], r[1], r[2], k))
+    for i, (tri, ties) in enumerate(tris):
+        if tri is None:
+            out.append(None)
+        elif ties == 0 or _plan_mode() == "v1":
+            out.append(_plan_v1_device(tri, lonlat_dev[i], gplan, keeps[i]))
+        else:
+            out.append(_plan_v0(lons[i], lats[i], gplan, _dev.to_host(keeps[i]).astype(bool)))
     return out

@@ -166,3 +166,32 @@ def test_empty_and_all_masked_granules():
     assert interpolator.interpolator(1, 0.25, g, c["coords"], flag_thresh=0.0) is None
     with pytest.raises(Exception):
         interpolator.interpolator(5, 0.25, c["granules"][0], c["coords"])
+
+
+@pytest.mark.parametrize("name", ["omi_no2", "tropomi_no2"])
+def test_gpu_plan_builder_equals_host_plan(name, monkeypatch):
+    """Builder v1 (native Delaunay + K1 point location on the GPU) against builder
+    v0 (Qhull + scipy's walk, what the reference itself runs): same kept cells, same
+    triangle per window node, weights to rounding."""
+    from oisatgmi_b200 import plan
+    c = cases.amf_case(name)
+    gpl = plan.grid_plan(c["coords"], c["grid_size"])
+    for g in c["granules"]:
+        monkeypatch.setenv("OISAT_PLAN", "v0")
+        p0 = plan.granule_plan(g.longitude_center, g.latitude_center, gpl, 2 * c["grid_size"],
+                               cache=False)
+        monkeypatch.setenv("OISAT_PLAN", "auto")
+        p1 = plan.granule_plan(g.longitude_center, g.latitude_center, gpl, 2 * c["grid_size"],
+                               cache=False)
+        assert p0.builder == "v0" and p1.builder == "v1"
+        assert np.array_equal(p0.cells, p1.cells)                       # bit-exact masks
+        S, n = p0.vert.shape
+        # same triangle per node (vertex order inside a triangle is free)
+        v0 = np.sort(p0.vert.reshape(S // 3, 3, n), axis=1)
+        v1 = np.sort(p1.vert.reshape(S // 3, 3, n), axis=1)
+        assert np.array_equal(v0, v1)
+        o0 = np.argsort(p0.vert.reshape(S // 3, 3, n), axis=1)
+        o1 = np.argsort(p1.vert.reshape(S // 3, 3, n), axis=1)
+        w0 = np.take_along_axis(p0.w.reshape(S // 3, 3, n), o0, axis=1)
+        w1 = np.take_along_axis(p1.w.reshape(S // 3, 3, n), o1, axis=1)
+        assert np.max(np.abs(w0 - w1)) < 1e-12

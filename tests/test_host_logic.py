@@ -142,3 +142,89 @@ def test_time_matching_follows_reference_rules():
     k, day, hour = v.closest_slot(ctm, stamps, fracs, dt.datetime(2005, 6, 1, 23, 0))
     assert (day, hour) == (0, 7)
     assert v.closest_day(ctm, stamps, dt.datetime(2005, 6, 20))[1] == 7  # day stamp vs slot stamps
+
+
+# --------------------------------------------------------- native triangulation
+def _tri_set(t):
+    return set(map(tuple, np.sort(np.asarray(t), axis=1)))
+
+
+def test_native_delaunay_equals_qhull_on_general_position_inputs():
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(12)
+    cases_xy = []
+    for n in (3, 4, 7, 50, 3000):
+        cases_xy.append((rng.uniform(-50, 50, n), rng.uniform(-20, 20, n)))
+    # swath pieces: the real use (float32 coordinates, date-line wrap included)
+    for geo in (synth.regional_geo(cases.REGION), dict(node_lon_deg=172.0, u0_deg=10, u1_deg=25)):
+        lat, lon = synth.swath_geolocation(180, 60, rng=rng, **geo)
+        cases_xy.append((lon.ravel().astype(np.float64), lat.ravel().astype(np.float64)))
+    for x, y in cases_xy:
+        tri, ties = plan.native_delaunay(x, y)
+        ref = Delaunay(np.column_stack((x, y)))
+        assert ties == 0
+        assert _tri_set(tri) == _tri_set(ref.simplices), len(x)
+    # a tight cluster (1e-3) next to a wide one (5): circumcircle margins fall below
+    # Qhull's tolerance, which is relative to the global coordinate range -- Qhull
+    # then returns a non-Delaunay diagonal.  The native builder must flag the input
+    # (so the product takes Qhull's answer, like the reference) ...
+    x = np.concatenate([rng.normal(0, 1e-3, 300), rng.normal(40, 5, 300)])
+    y = np.concatenate([rng.normal(0, 1e-3, 300), rng.normal(-10, 5, 300)])
+    tri, ties = plan.native_delaunay(x, y)
+    assert ties > 0
+
+
+def test_native_delaunay_reports_ties_and_degenerate_input():
+    lon, lat = np.meshgrid(np.arange(10.0), np.arange(8.0))
+    tri, ties = plan.native_delaunay(lon.ravel(), lat.ravel())      # co-circular quads everywhere
+    assert tri is not None and len(tri) == 2 * 9 * 7 and ties > 0    # valid, but not unique
+    tri, ties = plan.native_delaunay(np.arange(12.0), np.full(12, 3.0))   # collinear
+    assert tri is None
+    tri, ties = plan.native_delaunay(np.array([0.0, 1.0]), np.array([0.0, 1.0]))
+    assert tri is None
+    # exact duplicates are not vertices (Qhull lists them as coplanar points)
+    x = np.array([0.0, 1.0, 0.0, 1.0, 0.3, 0.3])
+    y = np.array([0.0, 0.0, 1.0, 1.1, 0.4, 0.4])
+    tri, _ = plan.native_delaunay(x, y)
+    assert len({int(v) for v in tri.ravel()} & {4, 5}) == 1
+
+
+def test_native_delaunay_exact_predicates_on_nearly_degenerate_input():
+    """Lattice perturbed by ~1 ulp: the floating-point filter cannot decide, the
+    exact stage must, and the result must still be THE Delaunay triangulation
+    (checked with exact rational arithmetic on every interior edge)."""
+    from fractions import Fraction
+    rng = np.random.default_rng(4)
+    gx, gy = np.meshgrid(np.arange(12.0), np.arange(9.0))
+    x = (gx.ravel() + rng.integers(-2, 3, gx.size) * 2.0 ** -50)
+    y = (gy.ravel() + rng.integers(-2, 3, gy.size) * 2.0 ** -50)
+    tri, ties = plan.native_delaunay(x, y)
+    assert tri is not None
+    F = lambda v: Fraction(float(v))  # noqa: E731
+
+    def incircle(a, b, c, d):
+        rows = []
+        for p in (a, b, c):
+            dx, dy = F(x[p]) - F(x[d]), F(y[p]) - F(y[d])
+            rows.append((dx, dy, dx * dx + dy * dy))
+        (a0, a1, a2), (b0, b1, b2), (c0, c1, c2) = rows
+        return a0 * (b1 * c2 - b2 * c1) - a1 * (b0 * c2 - b2 * c0) + a2 * (b0 * c1 - b1 * c0)
+
+    def orient(a, b, c):
+        return (F(x[a]) - F(x[c])) * (F(y[b]) - F(y[c])) - (F(y[a]) - F(y[c])) * (F(x[b]) - F(x[c]))
+
+    edges = {}
+    for t in tri:
+        for k in range(3):
+            e = tuple(sorted((int(t[k]), int(t[(k + 1) % 3]))))
+            edges.setdefault(e, []).append(int(t[(k + 2) % 3]))
+    violations = 0
+    for (a, b), opp in edges.items():
+        if len(opp) != 2:
+            continue
+        c, d = opp
+        if orient(a, b, c) < 0:
+            a, b = b, a
+        if incircle(a, b, c, d) > 0:
+            violations += 1
+    assert violations == 0
