@@ -89,10 +89,11 @@ int64_t oisat_h_delaunay(const double* h_x, const double* h_y, int64_t n, int32_
 
 /* node_tri[f] (caller pre-fills with INT32_MAX) <- lowest index of a triangle that
  * contains mesh node f by scipy's rule (barycentric coordinates within
- * [-eps, 1+eps], eps = 100*DBL_EPSILON); only nodes with keep[f] != 0 are tested. */
+ * [-eps, 1+eps], eps = 100*DBL_EPSILON); only nodes with keep[f] != 0 are tested.
+ * `work`: n_tri + 1 int32 of scratch. */
 int oisat_locate(const int32_t* tri, int64_t n_tri, const void* px, const void* py,
                  int32_t coord_dtype, const double* xs, int64_t W, const double* ys, int64_t H,
-                 const uint8_t* keep, int32_t* node_tri, void* stream);
+                 const uint8_t* keep, int32_t* node_tri, int32_t* work, void* stream);
 
 /* cell_ok[c] = nn_ok[c] and every node window[c*nwin + k] is located */
 int oisat_plan_cells(const int32_t* window, int32_t nwin, const uint8_t* nn_ok, int64_t n_cell,

@@ -95,48 +95,57 @@ __device__ __forceinline__ void claim(const TriGeom& g, int32_t t, int i, int j,
   if (inside(c)) atomicMin(&node_tri[f], t);
 }
 
-// thread = triangle.  Small boxes are rasterised by the thread itself; larger ones
-// (hull pockets, date-line crossers) by the whole warp, lane-strided.
+// Pass 1, thread = triangle.  A triangle whose bounding box holds few mesh nodes
+// rasterises it; the others (hull pockets, date-line crossers: boxes of up to the
+// whole mesh) are only appended to a list.
 template <typename T>
 __global__ void __launch_bounds__(256)
 locate_kernel(const int32_t* __restrict__ tri, int64_t n_tri, Coords<T> P,
               const double* __restrict__ xs, int64_t W, const double* __restrict__ ys, int64_t H,
-              const uint8_t* __restrict__ keep, int32_t* __restrict__ node_tri) {
+              const uint8_t* __restrict__ keep, int32_t* __restrict__ node_tri,
+              int32_t* __restrict__ big_count, int32_t* __restrict__ big_list) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  TriGeom g;
-  g.ok = false;
-  Box b{0, -1, 0, -1};
-  if (t < n_tri) {
-    const int32_t v0 = tri[3 * t], v1 = tri[3 * t + 1], v2 = tri[3 * t + 2];
-    const double x0 = P.px(v0), y0 = P.py(v0), x1 = P.px(v1), y1 = P.py(v1), x2 = P.px(v2),
-                 y2 = P.py(v2);
-    g = tri_geom(x0, y0, x1, y1, x2, y2);
-    if (g.ok)
-      b = node_box(fmin(x0, fmin(x1, x2)), fmax(x0, fmax(x1, x2)), fmin(y0, fmin(y1, y2)),
-                   fmax(y0, fmax(y1, y2)), xs, W, ys, H);
+  if (t >= n_tri) return;
+  const int32_t v0 = tri[3 * t], v1 = tri[3 * t + 1], v2 = tri[3 * t + 2];
+  const double x0 = P.px(v0), y0 = P.py(v0), x1 = P.px(v1), y1 = P.py(v1), x2 = P.px(v2),
+               y2 = P.py(v2);
+  const TriGeom g = tri_geom(x0, y0, x1, y1, x2, y2);
+  if (!g.ok) return;
+  const Box b = node_box(fmin(x0, fmin(x1, x2)), fmax(x0, fmax(x1, x2)), fmin(y0, fmin(y1, y2)),
+                         fmax(y0, fmax(y1, y2)), xs, W, ys, H);
+  const int64_t cnt = b.count();
+  if (cnt == 0) return;
+  if (cnt > kSmallBox) {
+    big_list[atomicAdd(big_count, 1)] = (int32_t)t;
+    return;
   }
-  const int64_t cnt = g.ok ? b.count() : 0;
-  if (cnt > 0 && cnt <= kSmallBox) {
-    for (int j = b.j0; j <= b.j1; ++j)
-      for (int i = b.i0; i <= b.i1; ++i) claim(g, (int32_t)t, i, j, xs, ys, W, keep, node_tri);
+  for (int j = b.j0; j <= b.j1; ++j)
+    for (int i = b.i0; i <= b.i1; ++i) claim(g, (int32_t)t, i, j, xs, ys, W, keep, node_tri);
+}
+
+// Pass 2, thread = mesh node.  The few kept nodes that no small triangle claimed
+// (they sit in a hull pocket, or outside the hull) are tested against the short
+// list of large triangles; node-centric, so the large boxes are never rasterised.
+template <typename T>
+__global__ void __launch_bounds__(256)
+locate_big_kernel(const int32_t* __restrict__ tri, Coords<T> P, const double* __restrict__ xs,
+                  int64_t W, const double* __restrict__ ys, int64_t H,
+                  const uint8_t* __restrict__ keep, int32_t* __restrict__ node_tri,
+                  const int32_t* __restrict__ big_count, const int32_t* __restrict__ big_list) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= W * H || !keep[f] || node_tri[f] != INT_MAX) return;
+  const int n_big = *big_count;
+  const double qx = xs[f % W], qy = ys[f / W];
+  int32_t best = INT_MAX;
+  for (int k = 0; k < n_big; ++k) {
+    const int32_t t = big_list[k];
+    const int32_t v0 = tri[3 * (int64_t)t], v1 = tri[3 * (int64_t)t + 1], v2 = tri[3 * (int64_t)t + 2];
+    const TriGeom g = tri_geom(P.px(v0), P.py(v0), P.px(v1), P.py(v1), P.px(v2), P.py(v2));
+    double c[3];
+    bary(g, qx, qy, c);
+    if (inside(c) && t < best) best = t;
   }
-  unsigned big = __ballot_sync(0xffffffffu, cnt > kSmallBox);
-  while (big) {
-    const int src = __ffs(big) - 1;
-    big &= big - 1;
-    TriGeom h;
-    h.x2 = __shfl_sync(0xffffffffu, g.x2, src); h.y2 = __shfl_sync(0xffffffffu, g.y2, src);
-    h.t00 = __shfl_sync(0xffffffffu, g.t00, src); h.t01 = __shfl_sync(0xffffffffu, g.t01, src);
-    h.t10 = __shfl_sync(0xffffffffu, g.t10, src); h.t11 = __shfl_sync(0xffffffffu, g.t11, src);
-    const int i0 = __shfl_sync(0xffffffffu, b.i0, src), i1 = __shfl_sync(0xffffffffu, b.i1, src);
-    const int j0 = __shfl_sync(0xffffffffu, b.j0, src), j1 = __shfl_sync(0xffffffffu, b.j1, src);
-    const int32_t tt = (int32_t)__shfl_sync(0xffffffffu, (long long)t, src);
-    const int bw = i1 - i0 + 1;
-    const int64_t total = (int64_t)bw * (j1 - j0 + 1);
-    for (int64_t k = lane; k < total; k += 32)
-      claim(h, tt, i0 + (int)(k % bw), j0 + (int)(k / bw), xs, ys, W, keep, node_tri);
-  }
+  if (best != INT_MAX) node_tri[f] = best;
 }
 
 __global__ void __launch_bounds__(256)
@@ -185,21 +194,34 @@ using namespace oisat;
 
 extern "C" int oisat_locate(const int32_t* tri, int64_t n_tri, const void* px, const void* py,
                             int32_t coord_dtype, const double* xs, int64_t W, const double* ys,
-                            int64_t H, const uint8_t* keep, int32_t* node_tri, void* stream) {
+                            int64_t H, const uint8_t* keep, int32_t* node_tri, int32_t* work,
+                            void* stream) {
   if (n_tri <= 0) return OISAT_OK;
-  OISAT_CHECK_ARG(tri && px && py && xs && ys && keep && node_tri, "null pointer");
+  OISAT_CHECK_ARG(tri && px && py && xs && ys && keep && node_tri && work, "null pointer");
   OISAT_CHECK_ARG(coord_dtype == OISAT_F32 || coord_dtype == OISAT_F64, "coords must be f32/f64");
-  OISAT_CHECK_ARG(W >= 1 && H >= 1 && W * H < (int64_t)INT_MAX, "bad mesh extent");
+  OISAT_CHECK_ARG(W >= 1 && H >= 1 && W * H < (int64_t)INT_MAX && n_tri < (int64_t)INT_MAX,
+                  "bad extent");
   const unsigned blocks = (unsigned)ceil_div(n_tri, 256);
+  const unsigned nblocks = (unsigned)ceil_div(W * H, 256);
   cudaStream_t s = (cudaStream_t)stream;
-  if (coord_dtype == OISAT_F32)
-    locate_kernel<float><<<blocks, 256, 0, s>>>(tri, n_tri,
-                                               Coords<float>{(const float*)px, (const float*)py},
-                                               xs, W, ys, H, keep, node_tri);
-  else
-    locate_kernel<double><<<blocks, 256, 0, s>>>(
-        tri, n_tri, Coords<double>{(const double*)px, (const double*)py}, xs, W, ys, H, keep,
-        node_tri);
+  int32_t* big_count = work;       // work = [count][list of n_tri]
+  int32_t* big_list = work + 1;
+  OISAT_CHECK_CUDA(cudaMemsetAsync(big_count, 0, sizeof(int32_t), s));
+  if (coord_dtype == OISAT_F32) {
+    const Coords<float> P{(const float*)px, (const float*)py};
+    locate_kernel<float><<<blocks, 256, 0, s>>>(tri, n_tri, P, xs, W, ys, H, keep, node_tri,
+                                               big_count, big_list);
+    OISAT_CHECK_LAUNCH();
+    locate_big_kernel<float><<<nblocks, 256, 0, s>>>(tri, P, xs, W, ys, H, keep, node_tri,
+                                                    big_count, big_list);
+  } else {
+    const Coords<double> P{(const double*)px, (const double*)py};
+    locate_kernel<double><<<blocks, 256, 0, s>>>(tri, n_tri, P, xs, W, ys, H, keep, node_tri,
+                                                big_count, big_list);
+    OISAT_CHECK_LAUNCH();
+    locate_big_kernel<double><<<nblocks, 256, 0, s>>>(tri, P, xs, W, ys, H, keep, node_tri,
+                                                     big_count, big_list);
+  }
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
 }

@@ -303,8 +303,8 @@ class MonthPipeline:
                                        dev["seg_start"].data_ptr(), dev["seg_pair"].data_ptr(),
                                        buf["staged"].data_ptr(), host["n_pairs"], _dev.stream()))
         if self.pg is not None:
-            import torch.distributed as dist
-            dist.all_reduce(buf["acc"], op=dist.ReduceOp.SUM, group=self.pg)
+            from .sharding import merge_accumulators
+            merge_accumulators(buf["acc"], self.pg)   # the path's only collective (NCCL)
 
     def run_oi(self):
         """Means, bias correction, OI sweep, knee, apply.  Returns device tensors."""

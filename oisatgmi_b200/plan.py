@@ -349,9 +349,10 @@ def _plan_v1_device(tri_host, lonlat_dev, gplan, keep_dev):
     node_tri = _dev.full((gplan.H * gplan.W,), 2 ** 31 - 1, "int32")
     code = _dev.dtype_code(lo)
     s = _dev.stream()
+    work = _dev.empty((tri.shape[0] + 1,), "int32")
     _lib.check(L.oisat_locate(tri.data_ptr(), tri.shape[0], lo.data_ptr(), la.data_ptr(), code,
                               xs.data_ptr(), gplan.W, ys.data_ptr(), gplan.H, keep_dev.data_ptr(),
-                              node_tri.data_ptr(), s))
+                              node_tri.data_ptr(), work.data_ptr(), s))
     n_cell = int(np.prod(gplan.out_shape))
     ok = _dev.empty((n_cell,), "uint8")
     _lib.check(L.oisat_plan_cells(window.data_ptr(), gplan.nwin, nn_ok.data_ptr(), n_cell,
