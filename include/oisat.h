@@ -308,9 +308,22 @@ typedef struct oisat_fused_args {
   int64_t n_cell;
   /* output: staged[5][n_pairs] */
   double* staged;
+  /* per-pair tables (split form only): granule and model cell of every pair */
+  const int32_t* pair_granule;
+  const int32_t* pair_cell;
 } oisat_fused_args;
 
 int oisat_fused_amf(const oisat_fused_args* h_args, void* stream);
+
+/* Split form, same results in two launches (preferred when a record has fewer
+ * than 16 chunks, i.e. for every BASELINE product): a half-warp gather that writes
+ * the gridded column of each pair to `rows` ([ceil(n_pairs/32)][rows_per_pair][32]
+ * float64, so that ...) and a ONE-THREAD-PER-PAIR vertical operator whose loads are
+ * all coalesced across the 32 pairs of a row-buffer tile and whose interp1d
+ * bracket search is a merge of the two pressure-sorted level lists.  The tile
+ * table of the args is not used; pair_granule / pair_cell are. */
+int64_t oisat_rows_per_pair(int32_t n_sat_lev, int32_t has_trop);
+int oisat_fused_amf_split(const oisat_fused_args* h_args, double* rows, void* stream);
 
 /* ordered segmented reduction of the staged pair values into the accumulators:
  * for model cell c the pairs seg_pair[seg_start[c] .. seg_start[c+1]) are listed

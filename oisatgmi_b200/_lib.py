@@ -39,7 +39,7 @@ class FusedArgs(C.Structure):
         ("n_records", i64), ("records", vp), ("amf_masked", vp), ("n_sat_lev", i32),
         ("has_trop", i32),
         ("ctm_pmid", vp), ("ctm_logp", vp), ("ctm_pcol", vp), ("n_ctm_lev", i32), ("n_cell", i64),
-        ("staged", vp),
+        ("staged", vp), ("pair_granule", vp), ("pair_cell", vp),
     ]
 
 
@@ -83,6 +83,8 @@ PROTOTYPES = {
     "oisat_pack_batch": (C.c_int, [vp, i32, i64, i32, i32, i32, f64, i32, vp, vp, vp]),
     "oisat_ctm_prepare": (C.c_int, [vp, vp, vp, i64, vp, vp, vp]),
     "oisat_fused_amf": (C.c_int, [C.POINTER(FusedArgs), vp]),
+    "oisat_rows_per_pair": (i64, [i32, i32]),
+    "oisat_fused_amf_split": (C.c_int, [C.POINTER(FusedArgs), vp, vp]),
     "oisat_accum_pairs": (C.c_int, [vp, i64, vp, vp, vp, i64, vp]),
 }
 

@@ -195,7 +195,8 @@ class MonthPipeline:
         d = _dev.to_device
         dev = dict(vert=vert, w=w, tile_pair0=d(tile_pair0), tile_gran=d(tile_gran), tile_cell0=d(tile_cell0),
                    tile_mask=d(tile_mask.view(np.int32)), seg_start=d(seg_start),
-                   seg_pair=d(order), gran_px0=d(px0),
+                   seg_pair=d(order), gran_px0=d(px0), pair_gran=d(gran),
+                   pair_cell=d(cells.astype(np.int32)),
                    gran_slot=d(np.array([g.slot for g in G], np.int32)))
         self._tables = (host, dev)
         return self._tables
@@ -231,6 +232,9 @@ class MonthPipeline:
             staged=_dev.empty((5, host["n_pairs"])),
             acc=_dev.zeros((10, self.n_cell)),
             ctm_logp=t.empty_like(pm), ctm_pcol=t.empty_like(pm),
+            rows=(_dev.empty(((host["n_pairs"] + 15) // 16,
+                              int(L.oisat_rows_per_pair(g0.nlev, int(g0.has_trop))), 16))
+                  if self.split else None),
             pack_items=_dev.to_device(raw), pack_blocks=block0,
         )
         return self._buf
@@ -287,12 +291,28 @@ class MonthPipeline:
         a.n_ctm_lev = pm.shape[1]
         a.n_cell = self.n_cell
         a.staged = buf["staged"].data_ptr()
+        a.pair_granule = dev["pair_gran"].data_ptr()
+        a.pair_cell = dev["pair_cell"].data_ptr()
         return a
+
+    @property
+    def split(self):
+        """Two-launch form (half-warp gather + thread-per-pair vertical operator):
+        needs records of fewer than 16 chunks; OISAT_FUSED=single forces the
+        one-kernel form."""
+        import os
+        g0 = self.granules[0]
+        halfs = int(_lib.lib().oisat_pack_record_halfs(g0.nlev, int(g0.has_trop)))
+        return halfs // 8 < 16 and os.environ.get("OISAT_FUSED", "split") != "single"
 
     def run_fused(self):
         L = _lib.lib()
         a = self.fused_args()
-        _lib.check(L.oisat_fused_amf(C.byref(a), _dev.stream()))
+        if self.split:
+            _lib.check(L.oisat_fused_amf_split(C.byref(a), self._buf["rows"].data_ptr(),
+                                               _dev.stream()))
+        else:
+            _lib.check(L.oisat_fused_amf(C.byref(a), _dev.stream()))
 
     def run_accumulate(self):
         L = _lib.lib()
