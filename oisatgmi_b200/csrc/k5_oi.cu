@@ -8,6 +8,7 @@
 // partial sums, combined by the same recursive halving), so the 99 means -- and
 // therefore the discrete knee decision taken on the host -- are bit-identical
 // to np.nanmean(AK.flatten()).
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(256)
 oi_sweep_leaf_kernel(const double* __restrict__ Sa, const double* __restrict__ So,
                      const int64_t* __restrict__ leaf_start, int64_t n_leaf,
                      const __grid_constant__ Factors fac, double* __restrict__ leaf_sum,
-                     double* __restrict__ leaf_cnt) {
+                     int64_t sum_stride, double* __restrict__ leaf_cnt) {
   const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;  // leaf id
   const int j = threadIdx.x & 7;
   const bool active = g < n_leaf;
@@ -76,33 +77,44 @@ oi_sweep_leaf_kernel(const double* __restrict__ Sa, const double* __restrict__ S
         acc = __dadd_rn(acc, fin ? AK : 0.0);
         cnt += fin ? 1.0 : 0.0;
       }
-      leaf_sum[(int64_t)f * n_leaf + g] = acc;
+      leaf_sum[(int64_t)f * sum_stride + g] = acc;
       leaf_cnt[(int64_t)f * n_leaf + g] = cnt;
     }
   }
 }
 
-// numpy's recursive halving over the leaves (depth <= ~40 for any int64 n)
-__device__ double combine_leaves(const double* leaf, int64_t n, int64_t* next) {
-  if (n <= kLeafMax) return leaf[(*next)++];
-  int64_t n2 = n / 2;
-  n2 -= n2 % 8;
-  const double a = combine_leaves(leaf, n2, next);
-  const double b = combine_leaves(leaf, n - n2, next);
-  return __dadd_rn(a, b);
-}
-
-__global__ void oi_sweep_combine_kernel(const double* __restrict__ leaf_sum,
-                                        const double* __restrict__ leaf_cnt, int64_t n_leaf,
-                                        int64_t n, int n_factors, double* __restrict__ sums,
-                                        double* __restrict__ counts) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= n_factors) return;
-  int64_t next = 0;
-  sums[f] = combine_leaves(leaf_sum + (int64_t)f * n_leaf, n, &next);
+// numpy's recursive halving over the leaves, level by level: the host lays the
+// (irregular) summation tree out as a schedule -- internal node i adds nodes
+// left[i] and right[i]; nodes are grouped by depth -- and one block per factor
+// walks the levels, so the ~3000 additions of a 361x576 grid take ~12 steps
+// instead of one thread's 3000 sequential adds.  Same tree => same rounding.
+__global__ void __launch_bounds__(256)
+oi_sweep_combine_kernel(double* __restrict__ val, int64_t val_stride,
+                        const double* __restrict__ leaf_cnt, int64_t n_leaf,
+                        const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                        const int32_t* __restrict__ level_start, int n_levels,
+                        double* __restrict__ sums, double* __restrict__ counts) {
+  const int f = blockIdx.x;
+  double* v = val + (int64_t)f * val_stride;
+  for (int lv = 0; lv < n_levels; ++lv) {
+    for (int i = level_start[lv] + threadIdx.x; i < level_start[lv + 1]; i += blockDim.x)
+      v[n_leaf + i] = __dadd_rn(v[left[i]], v[right[i]]);
+    __syncthreads();
+  }
+  // counts are integers: any order
+  __shared__ double part[256];
   double c = 0.0;
-  for (int64_t i = 0; i < n_leaf; ++i) c += leaf_cnt[(int64_t)f * n_leaf + i];
-  counts[f] = c;
+  for (int64_t i = threadIdx.x; i < n_leaf; i += blockDim.x) c += leaf_cnt[(int64_t)f * n_leaf + i];
+  part[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    counts[f] = part[0];
+    sums[f] = v[n_leaf > 1 ? 2 * n_leaf - 2 : 0];  // the root is the last internal node
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -144,6 +156,22 @@ static void leaf_bounds(int64_t begin, int64_t n, std::vector<int64_t>& starts) 
   leaf_bounds(begin + n2, n - n2, starts);
 }
 
+// summation tree as a levelled schedule; returns the node id of the subtree's root
+struct TreeNode { int32_t l, r, depth; };
+static int32_t build_tree(int64_t n, int32_t* next_leaf, std::vector<TreeNode>& nodes,
+                          int64_t n_leaf, int32_t* depth_out) {
+  if (n <= kLeafMax) { *depth_out = 0; return (*next_leaf)++; }
+  int64_t n2 = n / 2;
+  n2 -= n2 % 8;
+  int32_t dl, dr;
+  const int32_t l = build_tree(n2, next_leaf, nodes, n_leaf, &dl);
+  const int32_t r = build_tree(n - n2, next_leaf, nodes, n_leaf, &dr);
+  const int32_t d = 1 + (dl > dr ? dl : dr);
+  nodes.push_back({l, r, d});
+  *depth_out = d;
+  return (int32_t)(n_leaf + nodes.size() - 1);   // provisional id, remapped below
+}
+
 static int64_t leaf_count(int64_t n) {
   if (n <= kLeafMax) return 1;
   int64_t n2 = n / 2;
@@ -169,7 +197,9 @@ extern "C" int oisat_oi_prepare(const double* xa, double* y, const double* sigma
 extern "C" int64_t oisat_oi_sweep_workspace(int64_t n, int32_t n_factors) {
   if (n <= 0 || n_factors <= 0) return 0;
   const int64_t nl = leaf_count(n);
-  return (nl + 1) * (int64_t)sizeof(int64_t) + 2 * nl * n_factors * (int64_t)sizeof(double);
+  // leaf starts | schedule (left, right, level starts) | per-factor node values | leaf counts
+  return (nl + 1) * (int64_t)sizeof(int64_t) + (2 * nl + 72) * (int64_t)sizeof(int32_t) +
+         3 * nl * n_factors * (int64_t)sizeof(double) + 64;
 }
 
 extern "C" int oisat_oi_sweep(const double* Sa, const double* So, int64_t n,
@@ -183,20 +213,54 @@ extern "C" int oisat_oi_sweep(const double* Sa, const double* So, int64_t n,
   leaf_bounds(0, n, starts);
   starts.push_back(n);
   const int64_t nl = (int64_t)starts.size() - 1;
+  // schedule of the summation tree: internal nodes sorted by depth (stable), ids remapped
+  std::vector<TreeNode> nodes;
+  int32_t next_leaf = 0, root_depth = 0;
+  build_tree(n, &next_leaf, nodes, nl, &root_depth);
+  const int32_t n_int = (int32_t)nodes.size();
+  std::vector<int32_t> order(n_int), newid(n_int), left(n_int), right(n_int);
+  for (int32_t i = 0; i < n_int; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(),
+                   [&](int32_t a, int32_t b) { return nodes[a].depth < nodes[b].depth; });
+  for (int32_t k = 0; k < n_int; ++k) newid[order[k]] = k;
+  std::vector<int32_t> level_start;
+  for (int32_t k = 0; k < n_int; ++k) {
+    const TreeNode& t = nodes[order[k]];
+    if (k == 0 || t.depth != nodes[order[k - 1]].depth) level_start.push_back(k);
+    left[k] = t.l < nl ? t.l : (int32_t)(nl + newid[t.l - nl]);
+    right[k] = t.r < nl ? t.r : (int32_t)(nl + newid[t.r - nl]);
+  }
+  level_start.push_back(n_int);
+  const int n_levels = (int)level_start.size() - 1;
+  OISAT_CHECK_ARG(n_levels <= 64, "summation tree too deep");
+  // the root must be the last node of the last level: it is the only node of maximal depth
   int64_t* d_start = (int64_t*)work;
-  double* d_sum = (double*)(d_start + nl + 1);
-  double* d_cnt = d_sum + nl * n_factors;
-  // pageable source: the runtime stages it before returning, `starts` may die
+  int32_t* d_left = (int32_t*)(d_start + nl + 1);
+  int32_t* d_right = d_left + nl;
+  int32_t* d_level = d_right + nl;
+  double* d_val = (double*)(((uintptr_t)(d_level + 72) + 63) / 64 * 64);
+  double* d_cnt = d_val + 2 * nl * n_factors;
+  // pageable sources: the runtime stages them before returning, the vectors may die
   OISAT_CHECK_CUDA(cudaMemcpyAsync(d_start, starts.data(), (nl + 1) * sizeof(int64_t),
                                    cudaMemcpyHostToDevice, s));
+  if (n_int > 0) {
+    OISAT_CHECK_CUDA(cudaMemcpyAsync(d_left, left.data(), n_int * sizeof(int32_t),
+                                     cudaMemcpyHostToDevice, s));
+    OISAT_CHECK_CUDA(cudaMemcpyAsync(d_right, right.data(), n_int * sizeof(int32_t),
+                                     cudaMemcpyHostToDevice, s));
+  }
+  OISAT_CHECK_CUDA(cudaMemcpyAsync(d_level, level_start.data(),
+                                   level_start.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                   s));
   Factors fac;
   fac.n = n_factors;
   for (int i = 0; i < n_factors; ++i) fac.r[i] = h_factors[i];
   oi_sweep_leaf_kernel<<<(unsigned)ceil_div(nl * 8, 256), 256, 0, s>>>(Sa, So, d_start, nl, fac,
-                                                                      d_sum, d_cnt);
+                                                                      d_val, 2 * nl, d_cnt);
   OISAT_CHECK_LAUNCH();
-  oi_sweep_combine_kernel<<<(unsigned)ceil_div(n_factors, 32), 32, 0, s>>>(d_sum, d_cnt, nl, n,
-                                                                          n_factors, sums, counts);
+  oi_sweep_combine_kernel<<<(unsigned)n_factors, 256, 0, s>>>(d_val, 2 * nl, d_cnt, nl, d_left,
+                                                             d_right, d_level, n_levels, sums,
+                                                             counts);
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
 }
