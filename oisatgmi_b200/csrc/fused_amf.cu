@@ -61,7 +61,7 @@ ctm_prepare_kernel(const float* __restrict__ pmid, const float* __restrict__ pro
 }
 
 // -------------------------------------------------------------------- pack ----
-constexpr int kPackPixels = 128;
+constexpr int kPackPixels = 256;
 
 struct PackSrc {
   const __half* sw;
@@ -108,27 +108,47 @@ __device__ __forceinline__ void pack_block(const PackSrc& s, int L, int has_trop
     __half* t0 = tile + (2 * pp) * pitch;
     __half* t1 = t0 + pitch;
     const int64_t col = p0 + 2 * pp;
-#pragma unroll 4
-    for (int row = rl; row < L; row += rstep) {
-      const __half2 a = *reinterpret_cast<const __half2*>(s.sw + (int64_t)row * s.n_px + col);
-      const __half2 b = *reinterpret_cast<const __half2*>(s.pmid + (int64_t)row * s.n_px + col);
-      const int sa = slot_tab[row], sb = slot_tab[L + row];
-      t0[sa] = __low2half(a); t1[sa] = __high2half(a);
-      t0[sb] = __low2half(b); t1[sb] = __high2half(b);
+    // all loads of a pass are issued before the first transposing store, so a
+    // thread keeps 2*kIter independent 32-bit loads in flight (pure streaming kernel:
+    // bytes in flight per SM are what reaches HBM bandwidth)
+    constexpr int kIter = 12;
+    const __half* psw = s.sw + (int64_t)rl * s.n_px + col;
+    const __half* ppm = s.pmid + (int64_t)rl * s.n_px + col;
+    const int64_t hop = (int64_t)rstep * s.n_px;
+    for (int row0 = rl; row0 < L; row0 += kIter * rstep) {
+      __half2 va[kIter], vb[kIter];
+#pragma unroll
+      for (int i = 0; i < kIter; ++i) {
+        if (row0 + i * rstep < L) {
+          va[i] = __ldcs(reinterpret_cast<const __half2*>(psw + i * hop));
+          vb[i] = __ldcs(reinterpret_cast<const __half2*>(ppm + i * hop));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kIter; ++i) {
+        const int row = row0 + i * rstep;
+        if (row < L) {
+          const int sa = slot_tab[row], sb = slot_tab[L + row];
+          t0[sa] = __low2half(va[i]); t1[sa] = __high2half(va[i]);
+          t0[sb] = __low2half(vb[i]); t1[sb] = __high2half(vb[i]);
+        }
+      }
+      psw += kIter * hop;
+      ppm += kIter * hop;
     }
     if (rl == 0) {
       const __half2 v = *reinterpret_cast<const __half2*>(s.vcd + col);
       const int sv = record_slot(2 * L, nchunk);
       t0[sv] = __low2half(v); t1[sv] = __high2half(v);
-    } else if (rl == 1) {
       const float2 g = __half22float2(*reinterpret_cast<const __half2*>(s.sigma + col));
       const int ss = record_slot(2 * L + 1, nchunk);
       t0[ss] = __float2half_rn(__fmul_rn(g.x, g.x));   // numpy float16 square
       t1[ss] = __float2half_rn(__fmul_rn(g.y, g.y));
-    } else if (rl == 2 && has_trop) {
-      const __half2 v = *reinterpret_cast<const __half2*>(s.trop + col);
-      const int st = record_slot(2 * L + 2, nchunk);
-      t0[st] = __low2half(v); t1[st] = __high2half(v);
+      if (has_trop) {
+        const __half2 tr = *reinterpret_cast<const __half2*>(s.trop + col);
+        const int st = record_slot(2 * L + 2, nchunk);
+        t0[st] = __low2half(tr); t1[st] = __high2half(tr);
+      }
     }
   } else {  // ragged tail / odd pixel count: one value per thread step
     for (int i = threadIdx.x; i < n_here * nrow; i += blockDim.x) {
@@ -435,6 +455,8 @@ extern "C" int oisat_pack_granule(const void* sw, const void* p_mid, int32_t n_s
   const size_t smem = (size_t)kPackPixels * (R + 2) * sizeof(__half);
   PackSrc s{(const __half*)sw, (const __half*)p_mid, (const __half*)vcd, (const __half*)sigma,
             (const __half*)trop, n_px};
+  OISAT_CHECK_CUDA(cudaFuncSetAttribute(pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
   pack_kernel<<<(unsigned)ceil_div(n_px, kPackPixels), 256, smem, (cudaStream_t)stream>>>(
       s, n_sat_lev, trop != nullptr, (__half*)records);
   OISAT_CHECK_LAUNCH();
@@ -456,6 +478,8 @@ extern "C" int oisat_pack_batch(const oisat_pack_item* items, int32_t n_items,
                   "bad quality-flag dtype");
   const int R = 8 * record_chunks(n_sat_lev, has_trop);
   const size_t smem = (size_t)kPackPixels * (R + 2) * sizeof(__half);
+  OISAT_CHECK_CUDA(cudaFuncSetAttribute(pack_batch_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pack_batch_kernel<<<(unsigned)total_blocks, 256, smem, (cudaStream_t)stream>>>(
       items, n_items, n_sat_lev, has_trop, qflag_dtype, flag_thresh, amf_dtype, (__half*)records,
       amf_masked);
