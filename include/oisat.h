@@ -87,10 +87,22 @@ int oisat_distmask(const void* px_lon, const void* px_lat, int32_t coord_dtype, 
 int64_t oisat_h_delaunay(const double* h_x, const double* h_y, int64_t n, int32_t* h_tri,
                          int64_t tri_capacity, int64_t* n_ties);
 
+/* HOST function: the same triangulation for the pixel centres of a swath given as
+ * an n_rows x n_cols curvilinear lattice (row-major, the layout of the readers'
+ * 2-D latitude_center / longitude_center that interpolator.py:131-133 flattens).
+ * Points are inserted in a coarse-to-fine lattice order, each located by a short
+ * walk from the previous one (*path = 1; a radial sweep needs ~10x more edge flips
+ * on a long thin band).  Lattices with fewer than two lines or two points per line
+ * go to the general builder above (*path = 0).  Same return value, triangle set
+ * and tie report. */
+int64_t oisat_h_delaunay_swath(const double* h_x, const double* h_y, int64_t n_rows,
+                               int64_t n_cols, int32_t* h_tri, int64_t tri_capacity,
+                               int64_t* n_ties, int32_t* path);
+
 /* node_tri[f] (caller pre-fills with INT32_MAX) <- lowest index of a triangle that
  * contains mesh node f by scipy's rule (barycentric coordinates within
  * [-eps, 1+eps], eps = 100*DBL_EPSILON); only nodes with keep[f] != 0 are tested.
- * `work`: n_tri + 1 int32 of scratch. */
+ * `work`: 2 * n_tri + 2 int32 of scratch. */
 int oisat_locate(const int32_t* tri, int64_t n_tri, const void* px, const void* py,
                  int32_t coord_dtype, const double* xs, int64_t W, const double* ys, int64_t H,
                  const uint8_t* keep, int32_t* node_tri, int32_t* work, void* stream);

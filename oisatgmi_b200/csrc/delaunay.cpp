@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <limits>
 #include <numeric>
 #include <vector>
@@ -205,6 +206,36 @@ int incircle(double ax, double ay, double bx, double by, double cx, double cy, d
   return incircle_exact(ax, ay, bx, by, cx, cy, dx, dy);
 }
 
+// Edges whose fourth point lies within Qhull's floating-point tolerance of the
+// circumcircle (note (c) in Builder::run: measured, Qhull still agrees with the
+// exact answer at margins of 1e-11 of the squared coordinate range -- the smallest seen in
+// OMI/TROPOMI-shaped swaths -- and disagrees at 2e-16; 2e-14 keeps two orders of magnitude
+// of safety on the side that matters); shared by both builders.
+int64_t count_near_ties(const double* x, const double* y, int64_t n, const int32_t* tri,
+                        const int32_t* half, int64_t ntri) {
+  double maxabs = 0.0;
+  for (int64_t i = 0; i < n; ++i) maxabs = std::max(maxabs, std::max(std::fabs(x[i]), std::fabs(y[i])));
+  const double tol = 2e-14 * std::max(maxabs * maxabs, 1e-300);
+  int64_t ties = 0;
+  for (int64_t a = 0; a < 3 * ntri; ++a) {
+    const int32_t b = half[a];
+    if (b < a) continue;  // hull edge (-1) or already visited twin
+    const int32_t a0 = (int32_t)(a - a % 3), b0 = b - b % 3;
+    const int32_t p0 = tri[a0 + (a + 2) % 3], pr = tri[a], pl = tri[a0 + (a + 1) % 3],
+                  p1 = tri[b0 + (b + 2) % 3];
+    const double adx = x[p0] - x[p1], ady = y[p0] - y[p1], bdx = x[pl] - x[p1],
+                 bdy = y[pl] - y[p1], cdx = x[pr] - x[p1], cdy = y[pr] - y[p1];
+    const double det = (adx * adx + ady * ady) * (bdx * cdy - cdx * bdy) +
+                       (bdx * bdx + bdy * bdy) * (cdx * ady - adx * cdy) +
+                       (cdx * cdx + cdy * cdy) * (adx * bdy - bdx * ady);
+    const double area2 = std::fabs((x[p0] - x[pr]) * (y[pl] - y[pr]) -
+                                   (y[p0] - y[pr]) * (x[pl] - x[pr]));
+    // det / (2*area) = signed height of p1's lift above the plane of the other three
+    if (std::fabs(det) <= tol * area2) ++ties;
+  }
+  return ties;
+}
+
 // --------------------------------------------------------------- triangulation
 struct Builder {
   const double* x;
@@ -216,6 +247,7 @@ struct Builder {
   std::vector<int32_t> stack;
   int64_t ntri = 0;
   int64_t ties = 0;
+  bool near_ties = true;   // also report near-ties (note (c) in run)
   int32_t hull_start = 0;
   double cx = 0, cy = 0;
   int hash_size = 0;
@@ -462,38 +494,45 @@ struct Builder {
     // split along the other diagonal there (verified with rational arithmetic: Qhull
     // then returns a non-Delaunay pair).  Such edges are reported as ties too, so the
     // caller can take Qhull's answer instead of the exact one.
-    double maxabs = 0.0;
-    for (int64_t i = 0; i < n; ++i) maxabs = std::max(maxabs, std::max(std::fabs(x[i]), std::fabs(y[i])));
-    // measured: Qhull still agrees with the exact answer at margins of 1e-11 of the
-    // squared coordinate range (the smallest seen in OMI/TROPOMI-shaped swaths) and
-    // disagrees at 2e-16 (a 1e-3-wide cluster at coordinates ~50); 2e-14 keeps two
-    // orders of magnitude of safety on the side that matters
-    const double tol = 2e-14 * std::max(maxabs * maxabs, 1e-300);
-    for (int64_t a = 0; a < 3 * ntri; ++a) {
-      const int32_t b = half[a];
-      if (b < a) continue;  // hull edge (-1) or already visited twin
-      const int32_t a0 = (int32_t)(a - a % 3), b0 = b - b % 3;
-      const int32_t p0 = tri[a0 + (a + 2) % 3], pr = tri[a], pl = tri[a0 + (a + 1) % 3],
-                    p1 = tri[b0 + (b + 2) % 3];
-      const double adx = x[p0] - x[p1], ady = y[p0] - y[p1], bdx = x[pl] - x[p1],
-                   bdy = y[pl] - y[p1], cdx = x[pr] - x[p1], cdy = y[pr] - y[p1];
-      const double det = (adx * adx + ady * ady) * (bdx * cdy - cdx * bdy) +
-                         (bdx * bdx + bdy * bdy) * (cdx * ady - adx * cdy) +
-                         (cdx * cdx + cdy * cdy) * (adx * bdy - bdx * ady);
-      const double area2 = std::fabs((x[p0] - x[pr]) * (y[pl] - y[pr]) -
-                                     (y[p0] - y[pr]) * (x[pl] - x[pr]));
-      // det / (2*area) = signed height of p1's lift above the plane of the other three
-      if (std::fabs(det) <= tol * area2) ++ties;
-    }
+    if (near_ties) ties += count_near_ties(x, y, n, tri.data(), half.data(), ntri);
     return 0;
   }
 };
 
+#include "delaunay_swath.inl"  // GridBuilder: structured-swath builder (uses the predicates above)
+
 }  // namespace
+
+extern "C" int64_t oisat_h_delaunay_swath(const double* h_x, const double* h_y, int64_t n_rows,
+                                          int64_t n_cols, int32_t* h_tri, int64_t tri_capacity,
+                                          int64_t* n_ties, int32_t* path) {
+  if (!h_x || !h_y || !h_tri || n_rows < 1 || n_cols < 1 ||
+      n_rows * n_cols > (int64_t)0x3fffffff)
+    return OISAT_E_ARG;
+  LatticeBuilder g;
+  g.x = h_x;
+  g.y = h_y;
+  g.rows = n_rows;
+  g.cols = n_cols;
+  if (g.run() == 0) {
+    const int64_t m = g.emit(h_tri, tri_capacity);
+    if (m < 0) return OISAT_E_ARG;
+    if (n_ties)
+      *n_ties = g.ties + count_near_ties(h_x, h_y, g.n, g.tri.data(), g.half.data(), g.ntri);
+    if (path) *path = 1;
+    return m;
+  }
+  if (path) *path = 0;
+  return oisat_h_delaunay(h_x, h_y, n_rows * n_cols, h_tri, tri_capacity, n_ties);
+}
 
 extern "C" int64_t oisat_h_delaunay(const double* h_x, const double* h_y, int64_t n,
                                     int32_t* h_tri, int64_t tri_capacity, int64_t* n_ties) {
   if (!h_x || !h_y || !h_tri || n < 3 || n > (int64_t)0x3fffffff) return OISAT_E_ARG;
+  // scipy.spatial.Delaunay raises on NaN / infinite coordinates; the reference then skips
+  // the granule (interpolator.py:152-155)
+  for (int64_t i = 0; i < n; ++i)
+    if (!(std::fabs(h_x[i]) <= 1.7e308) || !(std::fabs(h_y[i]) <= 1.7e308)) return OISAT_E_UNSUPPORTED;
   Builder b;
   b.x = h_x;
   b.y = h_y;

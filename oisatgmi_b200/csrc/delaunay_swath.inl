@@ -1,0 +1,262 @@
+// Lattice-order Delaunay builder for swaths; included by delaunay.cpp inside its
+// anonymous namespace (it uses the exact predicates and count_near_ties defined there).
+//
+// A level-2 swath is a curvilinear (scan line x ground pixel) lattice and the
+// reference triangulates ALL of its pixel centres (interpolator.py:131-133; bad
+// pixels only poison the data, :126-128).  A radial sweep is a poor fit for such a
+// long thin band: measured 56 edge flips per point on OMI-shaped granules.
+//
+// This builder works for any 2-D lattice of points, whatever its shape in the
+// (lon, lat) plane: incremental Delaunay insertion in a coarse-to-fine lattice
+// order (see run()).  Consecutive points are lattice neighbours of the current
+// level, so locating each new point is a walk of a few triangles from the previous
+// one, and the flips that follow stay local (~5 per point).  Date-line crossings
+// are not special: the walk is simply long once per crossing.
+//
+// The convex hull is closed with "ghost" triangles (u, v, GHOST) so that every
+// edge has a twin and insertion outside the hull is the same 1 -> 3 split as
+// inside; the flip rule for edges that end at the ghost vertex removes reflex hull
+// corners, which fans the new point onto every hull edge it can see.  All
+// decisions use the exact predicates, so the result is the Delaunay triangulation;
+// with no ties that is the same triangle set Qhull returns.
+struct LatticeBuilder {
+  const double* x;
+  const double* y;
+  int64_t rows, cols, n;
+  int32_t G = 0;                          // ghost vertex id (= n)
+  std::vector<int32_t> tri, half, stack;  // every half-edge has a twin while ghosts exist
+  int64_t ntri = 0, flips = 0, ties = 0;
+
+  static int32_t next(int32_t e) { return e % 3 == 2 ? e - 2 : e + 1; }
+  static int32_t prev(int32_t e) { return e % 3 == 0 ? e + 2 : e - 1; }
+  int orient(int32_t a, int32_t b, int32_t c) const {
+    return orient2d(x[a], y[a], x[b], y[b], x[c], y[c]);
+  }
+  void link(int32_t a, int32_t b) { half[a] = b; half[b] = a; }
+  int32_t new_triangle(int32_t a, int32_t b, int32_t c) {
+    const int32_t s = (int32_t)(3 * ntri++);
+    tri[s] = a; tri[s + 1] = b; tri[s + 2] = c;
+    return s;
+  }
+  bool real(int32_t s) const { return tri[s] != G && tri[s + 1] != G && tri[s + 2] != G; }
+
+  // restore the Delaunay property (and hull convexity) behind the edges on `stack`;
+  // every stacked edge has the newly inserted point as the apex of its triangle
+  void relax() {
+    while (!stack.empty()) {
+      const int32_t a = stack.back();
+      stack.pop_back();
+      const int32_t b = half[a];
+      const int32_t al = next(a), ar = prev(a), bl = prev(b), br = next(b);
+      const int32_t pr = tri[a], pl = tri[al], p0 = tri[ar], p1 = tri[bl];
+      bool flip;
+      if (pr == G) flip = orient(p0, pl, p1) < 0;          // hull path p0 -> pl -> p1 turns right
+      else if (pl == G) flip = orient(p1, pr, p0) < 0;     // hull path p1 -> pr -> p0 turns right
+      else if (p0 == G || p1 == G) flip = false;           // a hull edge
+      else flip = incircle(x[pr], y[pr], x[pl], y[pl], x[p0], y[p0], x[p1], y[p1]) > 0;
+      if (!flip) continue;
+      ++flips;
+      const int32_t hbl = half[bl], har = half[ar];
+      tri[a] = p1;
+      tri[b] = p0;
+      link(a, hbl);
+      link(b, har);
+      link(ar, bl);
+      stack.push_back(a);
+      stack.push_back(br);
+    }
+  }
+
+  // split triangle s (base half-edge) at p, strictly inside it (or in a ghost)
+  int32_t split3(int32_t s, int32_t p) {
+    const int32_t b = tri[s + 1], c = tri[s + 2], a = tri[s];
+    const int32_t hb = half[s + 1], hc = half[s + 2];
+    const int32_t s2 = new_triangle(b, c, p), s3 = new_triangle(c, a, p);
+    tri[s + 2] = p;                       // (a, b, p)
+    link(s2, hb);
+    link(s3, hc);
+    link(s + 1, s2 + 2);
+    link(s2 + 1, s3 + 2);
+    link(s3 + 1, s + 2);
+    stack.push_back(s);
+    stack.push_back(s2);
+    stack.push_back(s3);
+    return real(s) ? s : (real(s2) ? s2 : s3);
+  }
+
+  // p lies on half-edge e (strictly between its end points)
+  int32_t split4(int32_t e, int32_t p) {
+    const int32_t f = half[e];
+    const int32_t en = next(e), ep = prev(e), fn = next(f), fp = prev(f);
+    const int32_t a = tri[e], b = tri[en], c = tri[ep], d = tri[fp];
+    const int32_t hen = half[en], hfn = half[fn];
+    const int32_t n1 = new_triangle(p, b, c), n2 = new_triangle(p, a, d);
+    tri[en] = p;                          // (a, p, c)
+    tri[fn] = p;                          // (b, p, d)
+    link(n1 + 1, hen);
+    link(n1 + 2, en);
+    link(n2 + 1, hfn);
+    link(n2 + 2, fn);
+    link(e, n2);
+    link(f, n1);
+    stack.push_back(ep);
+    stack.push_back(n1 + 1);
+    stack.push_back(fp);
+    stack.push_back(n2 + 1);
+    const int32_t s = e - e % 3;
+    return real(s) ? s : f - f % 3;
+  }
+
+  // 0 on success, -1 when this builder does not apply (caller falls back)
+  int run() {
+    if (rows < 2 || cols < 2) return -1;
+    n = rows * cols;
+    if (n > (int64_t)0x1fffffff) return -1;
+    for (int64_t i = 0; i < n; ++i)
+      if (!(std::fabs(x[i]) <= 1e300) || !(std::fabs(y[i]) <= 1e300)) return -1;
+    G = (int32_t)n;
+    tri.assign(3 * (2 * n + 8), -1);
+    half.assign(3 * (2 * n + 8), -1);
+    stack.reserve(256);
+    // Insertion order.  Plain row-by-row order is a trap: a new scan line lies just
+    // outside the hull, whose nearly straight previous line it sees end to end, so
+    // every point fans onto ~cols/2 hull edges that later points flip away again
+    // (measured: 24 flips per point); so is inserting the outline first (a slightly
+    // curved chain inserted end to end costs a quadratic number of flips).  Instead
+    // the lattice is inserted coarse to fine: every 2^L-th point of every 2^L-th
+    // line plus the last line / last point of each line, so that every level spans
+    // the whole footprint; L descending, boustrophedon inside a level.  That behaves
+    // like a randomised order (a few flips per point) yet keeps consecutive points
+    // close, so the location walk from the previous point stays short.
+    std::vector<int32_t> ord;
+    ord.reserve(n);
+    {
+      std::vector<uint8_t> seen(n, 0);
+      auto push = [&](int64_t i, int64_t j) {
+        const int64_t v = i * cols + j;
+        if (!seen[v]) { seen[v] = 1; ord.push_back((int32_t)v); }
+      };
+      int top = 0;
+      while ((int64_t(2) << top) < std::max(rows, cols)) ++top;
+      std::vector<int64_t> ri, cj;
+      for (int L = top; L >= 0; --L) {
+        const int64_t step = int64_t(1) << L;
+        ri.clear();
+        cj.clear();
+        for (int64_t i = 0; i < rows; i += step) ri.push_back(i);
+        if (ri.back() != rows - 1) ri.push_back(rows - 1);
+        for (int64_t j = 0; j < cols; j += step) cj.push_back(j);
+        if (cj.back() != cols - 1) cj.push_back(cols - 1);
+        bool backward = false;
+        for (int64_t i : ri) {
+          if (backward) { for (size_t c = cj.size(); c-- > 0;) push(i, cj[c]); }
+          else { for (int64_t j : cj) push(i, j); }
+          backward = !backward;
+        }
+      }
+    }
+    auto order = [&](int64_t k) { return ord[k]; };
+    int32_t p0 = order(0), p1 = order(1), p2 = -1;
+    if (x[p0] == x[p1] && y[p0] == y[p1]) return -1;
+    int64_t k2 = 2;
+    for (; k2 < n; ++k2) {
+      const int s = orient(p0, p1, order(k2));
+      if (s != 0) {
+        p2 = order(k2);
+        if (s < 0) std::swap(p0, p1);
+        break;
+      }
+    }
+    if (p2 < 0) return -1;
+    {
+      const int32_t t = new_triangle(p0, p1, p2);
+      const int32_t g1 = new_triangle(p1, p0, G), g2 = new_triangle(p2, p1, G),
+                    g3 = new_triangle(p0, p2, G);
+      link(t, g1); link(t + 1, g2); link(t + 2, g3);
+      link(g1 + 1, g3 + 2); link(g2 + 1, g1 + 2); link(g3 + 1, g2 + 2);
+    }
+    int32_t cur = 0;                      // a real triangle near the previous point
+    const int64_t max_steps = 8 * n + 64;
+    for (int64_t k = 2; k < n; ++k) {
+      if (k == k2) continue;
+      const int32_t p = order(k);
+      int32_t s = cur, from = -1;
+      int64_t steps = 0;
+      for (;;) {
+        if (++steps > max_steps) return -1;
+        // s is real here
+        int32_t cross = -1;
+        int zeros = 0, zero_edge = -1;
+        for (int e = 0; e < 3; ++e) {
+          const int32_t h = s + e;
+          if (h == from) continue;
+          const int o = orient(tri[h], tri[next(h)], p);
+          if (o < 0) { cross = h; break; }
+          if (o == 0) { ++zeros; zero_edge = h; }
+        }
+        if (cross >= 0) {
+          const int32_t t = half[cross];
+          const int32_t ts = t - t % 3;
+          if (!real(ts)) {                // left the hull through a visible edge
+            cur = split3(ts, p);
+            break;
+          }
+          from = t;
+          s = ts;
+          continue;
+        }
+        if (zeros == 0) {
+          cur = split3(s, p);
+        } else if (zeros == 1) {
+          cur = split4(zero_edge, p);
+        } else {
+          cur = s;                        // coincides with a vertex: a repeated point
+        }
+        break;
+      }
+      relax();
+    }
+    // hull: collinear triples make Qhull's answer non-unique; then drop the ghosts
+    {
+      std::vector<int32_t> hull_next(n, -1);
+      int32_t start = -1;
+      for (int64_t t = 0; t < ntri; ++t) {
+        const int32_t s = (int32_t)(3 * t);
+        if (real(s)) continue;
+        const int32_t g = tri[s] == G ? s : (tri[s + 1] == G ? s + 1 : s + 2);
+        const int32_t v = tri[next(g)], u = tri[prev(g)];   // real edge v -> u, hull edge u -> v
+        hull_next[u] = v;
+        start = u;
+      }
+      int32_t p = start;
+      int64_t nh = 0;
+      do {
+        const int32_t q = hull_next[p], r = hull_next[q];
+        if (orient(p, q, r) == 0) ++ties;
+        p = q;
+        if (++nh > n) return -1;
+      } while (p != start);
+      for (int64_t t = 0; t < ntri; ++t) {
+        const int32_t s = (int32_t)(3 * t);
+        if (real(s)) continue;
+        for (int e = 0; e < 3; ++e) {
+          if (half[s + e] >= 0) half[half[s + e]] = -1;
+          half[s + e] = -1;
+        }
+        tri[s] = tri[s + 1] = tri[s + 2] = -1;
+      }
+    }
+    return 0;
+  }
+
+  int64_t emit(int32_t* out, int64_t capacity) const {
+    int64_t m = 0;
+    for (int64_t t = 0; t < ntri; ++t) {
+      if (tri[3 * t] < 0) continue;
+      if (m >= capacity) return -1;
+      out[3 * m] = tri[3 * t]; out[3 * m + 1] = tri[3 * t + 1]; out[3 * m + 2] = tri[3 * t + 2];
+      ++m;
+    }
+    return m;
+  }
+};

@@ -20,7 +20,8 @@
 namespace oisat {
 
 constexpr double kLocateEps = 100.0 * 2.220446049250313e-16;  // scipy: eps = 100 * DBL_EPSILON
-constexpr int kSmallBox = 64;  // nodes a single thread rasterises on its own
+constexpr int kSmallBox = 64;       // nodes a single thread rasterises on its own
+constexpr int kWarpBox = 1 << 16;   // nodes a warp rasterises; larger boxes go node-centric
 
 template <typename T>
 struct Coords {
@@ -96,14 +97,16 @@ __device__ __forceinline__ void claim(const TriGeom& g, int32_t t, int i, int j,
 }
 
 // Pass 1, thread = triangle.  A triangle whose bounding box holds few mesh nodes
-// rasterises it; the others (hull pockets, date-line crossers: boxes of up to the
-// whole mesh) are only appended to a list.
+// rasterises it.  Mid-sized boxes (high-latitude pixels are many mesh nodes wide,
+// hull-pocket slivers are long) are queued for pass 2, a warp each; the few
+// boxes of up to the whole mesh (date-line crossers) are queued for pass 3.
 template <typename T>
 __global__ void __launch_bounds__(256)
 locate_kernel(const int32_t* __restrict__ tri, int64_t n_tri, Coords<T> P,
               const double* __restrict__ xs, int64_t W, const double* __restrict__ ys, int64_t H,
               const uint8_t* __restrict__ keep, int32_t* __restrict__ node_tri,
-              int32_t* __restrict__ big_count, int32_t* __restrict__ big_list) {
+              int32_t* __restrict__ counts, int32_t* __restrict__ mid_list,
+              int32_t* __restrict__ big_list) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tri) return;
   const int32_t v0 = tri[3 * t], v1 = tri[3 * t + 1], v2 = tri[3 * t + 2];
@@ -115,15 +118,44 @@ locate_kernel(const int32_t* __restrict__ tri, int64_t n_tri, Coords<T> P,
                          fmax(y0, fmax(y1, y2)), xs, W, ys, H);
   const int64_t cnt = b.count();
   if (cnt == 0) return;
+  if (cnt > kWarpBox) {
+    big_list[atomicAdd(&counts[1], 1)] = (int32_t)t;
+    return;
+  }
   if (cnt > kSmallBox) {
-    big_list[atomicAdd(big_count, 1)] = (int32_t)t;
+    mid_list[atomicAdd(&counts[0], 1)] = (int32_t)t;
     return;
   }
   for (int j = b.j0; j <= b.j1; ++j)
     for (int i = b.i0; i <= b.i1; ++i) claim(g, (int32_t)t, i, j, xs, ys, W, keep, node_tri);
 }
 
-// Pass 2, thread = mesh node.  The few kept nodes that no small triangle claimed
+// Pass 2, warp = queued mid-sized triangle (grid-stride over the queue).
+template <typename T>
+__global__ void __launch_bounds__(256)
+locate_mid_kernel(const int32_t* __restrict__ tri, Coords<T> P, const double* __restrict__ xs,
+                  int64_t W, const double* __restrict__ ys, int64_t H,
+                  const uint8_t* __restrict__ keep, int32_t* __restrict__ node_tri,
+                  const int32_t* __restrict__ counts, const int32_t* __restrict__ mid_list) {
+  const int n_mid = counts[0];
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_mid; k += warps) {
+    const int32_t t = mid_list[k];
+    const int32_t v0 = tri[3 * (int64_t)t], v1 = tri[3 * (int64_t)t + 1], v2 = tri[3 * (int64_t)t + 2];
+    const double x0 = P.px(v0), y0 = P.py(v0), x1 = P.px(v1), y1 = P.py(v1), x2 = P.px(v2),
+                 y2 = P.py(v2);
+    const TriGeom g = tri_geom(x0, y0, x1, y1, x2, y2);
+    const Box b = node_box(fmin(x0, fmin(x1, x2)), fmax(x0, fmax(x1, x2)), fmin(y0, fmin(y1, y2)),
+                           fmax(y0, fmax(y1, y2)), xs, W, ys, H);
+    const int bw = b.i1 - b.i0 + 1;
+    const int cnt = (int)b.count();
+    for (int idx = lane; idx < cnt; idx += 32)
+      claim(g, t, b.i0 + idx % bw, b.j0 + idx / bw, xs, ys, W, keep, node_tri);
+  }
+}
+
+// Pass 3, thread = mesh node.  The few kept nodes that no rasterised triangle claimed
 // (they sit in a hull pocket, or outside the hull) are tested against the short
 // list of large triangles; node-centric, so the large boxes are never rasterised.
 template <typename T>
@@ -131,10 +163,10 @@ __global__ void __launch_bounds__(256)
 locate_big_kernel(const int32_t* __restrict__ tri, Coords<T> P, const double* __restrict__ xs,
                   int64_t W, const double* __restrict__ ys, int64_t H,
                   const uint8_t* __restrict__ keep, int32_t* __restrict__ node_tri,
-                  const int32_t* __restrict__ big_count, const int32_t* __restrict__ big_list) {
+                  const int32_t* __restrict__ counts, const int32_t* __restrict__ big_list) {
   const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= W * H || !keep[f] || node_tri[f] != INT_MAX) return;
-  const int n_big = *big_count;
+  const int n_big = counts[1];
   const double qx = xs[f % W], qy = ys[f / W];
   int32_t best = INT_MAX;
   for (int k = 0; k < n_big; ++k) {
@@ -204,23 +236,31 @@ extern "C" int oisat_locate(const int32_t* tri, int64_t n_tri, const void* px, c
   const unsigned blocks = (unsigned)ceil_div(n_tri, 256);
   const unsigned nblocks = (unsigned)ceil_div(W * H, 256);
   cudaStream_t s = (cudaStream_t)stream;
-  int32_t* big_count = work;       // work = [count][list of n_tri]
-  int32_t* big_list = work + 1;
-  OISAT_CHECK_CUDA(cudaMemsetAsync(big_count, 0, sizeof(int32_t), s));
+  int32_t* counts = work;          // work = [n_mid][n_big][mid list of n_tri][big list of n_tri]
+  int32_t* mid_list = work + 2;
+  int32_t* big_list = work + 2 + n_tri;
+  const unsigned mid_blocks = 148 * 8;
+  OISAT_CHECK_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), s));
   if (coord_dtype == OISAT_F32) {
     const Coords<float> P{(const float*)px, (const float*)py};
     locate_kernel<float><<<blocks, 256, 0, s>>>(tri, n_tri, P, xs, W, ys, H, keep, node_tri,
-                                               big_count, big_list);
+                                               counts, mid_list, big_list);
+    OISAT_CHECK_LAUNCH();
+    locate_mid_kernel<float><<<mid_blocks, 256, 0, s>>>(tri, P, xs, W, ys, H, keep, node_tri,
+                                                       counts, mid_list);
     OISAT_CHECK_LAUNCH();
     locate_big_kernel<float><<<nblocks, 256, 0, s>>>(tri, P, xs, W, ys, H, keep, node_tri,
-                                                    big_count, big_list);
+                                                    counts, big_list);
   } else {
     const Coords<double> P{(const double*)px, (const double*)py};
     locate_kernel<double><<<blocks, 256, 0, s>>>(tri, n_tri, P, xs, W, ys, H, keep, node_tri,
-                                                big_count, big_list);
+                                                counts, mid_list, big_list);
+    OISAT_CHECK_LAUNCH();
+    locate_mid_kernel<double><<<mid_blocks, 256, 0, s>>>(tri, P, xs, W, ys, H, keep, node_tri,
+                                                        counts, mid_list);
     OISAT_CHECK_LAUNCH();
     locate_big_kernel<double><<<nblocks, 256, 0, s>>>(tri, P, xs, W, ys, H, keep, node_tri,
-                                                     big_count, big_list);
+                                                     counts, big_list);
   }
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;

@@ -265,19 +265,35 @@ def triangulate(lon, lat):
 def native_delaunay(lon, lat):
     """oisat_h_delaunay (csrc/delaunay.cpp): (triangles (n_tri, 3) int32, n_ties),
     or (None, 0) when no triangle exists.  The call releases the GIL."""
+    tri, ties, _ = native_delaunay_path(lon, lat)
+    return tri, ties
+
+
+def native_delaunay_path(lon, lat):
+    """As native_delaunay, plus which builder ran: 1 = structured-swath fast path
+    (2-D lon/lat whose lattice quads are all convex), 0 = general sweep-hull.
+    OISAT_DELAUNAY=general forces the latter."""
     import ctypes as C
+    import os
     L = _lib.lib()
+    shape = np.shape(lon)
     x = np.ascontiguousarray(np.asarray(lon, dtype=np.float64).ravel())
     y = np.ascontiguousarray(np.asarray(lat, dtype=np.float64).ravel())
     n = x.size
     if n < 3:
-        return None, 0
+        return None, 0, 0
     tri = np.empty((2 * n, 3), dtype=np.int32)
     ties = C.c_int64(0)
-    nt = L.oisat_h_delaunay(x.ctypes.data, y.ctypes.data, n, tri.ctypes.data, 2 * n, C.byref(ties))
+    path = C.c_int32(0)
+    if len(shape) == 2 and min(shape) >= 2 and os.environ.get("OISAT_DELAUNAY") != "general":
+        nt = L.oisat_h_delaunay_swath(x.ctypes.data, y.ctypes.data, shape[0], shape[1],
+                                      tri.ctypes.data, 2 * n, C.byref(ties), C.byref(path))
+    else:
+        nt = L.oisat_h_delaunay(x.ctypes.data, y.ctypes.data, n, tri.ctypes.data, 2 * n,
+                                C.byref(ties))
     if nt <= 0:
-        return None, 0
-    return tri[:nt], int(ties.value)
+        return None, 0, int(path.value)
+    return tri[:nt], int(ties.value), int(path.value)
 
 
 def locate(tri, qx, qy):
@@ -349,7 +365,7 @@ def _plan_v1_device(tri_host, lonlat_dev, gplan, keep_dev):
     node_tri = _dev.full((gplan.H * gplan.W,), 2 ** 31 - 1, "int32")
     code = _dev.dtype_code(lo)
     s = _dev.stream()
-    work = _dev.empty((tri.shape[0] + 1,), "int32")
+    work = _dev.empty((2 * tri.shape[0] + 2,), "int32")
     _lib.check(L.oisat_locate(tri.data_ptr(), tri.shape[0], lo.data_ptr(), la.data_ptr(), code,
                               xs.data_ptr(), gplan.W, ys.data_ptr(), gplan.H, keep_dev.data_ptr(),
                               node_tri.data_ptr(), work.data_ptr(), s))
@@ -434,14 +450,16 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
         return [granule_plan(lons[i], lats[i], gplan, radius, lonlat_dev=lonlat_dev[i], cache=False)
                 for i in range(n)]
     workers = max(1, min(n, workers or os.cpu_count() or 1))
-    with ThreadPoolExecutor(workers) as ex:
-        tris = list(ex.map(lambda i: native_delaunay(lons[i], lats[i]), range(n)))
     out = []
-    for i, (tri, ties) in enumerate(tris):
-        if tri is None:
-            out.append(None)
-        elif ties == 0 or _plan_mode() == "v1":
-            out.append(_plan_v1_device(tri, lonlat_dev[i], gplan, keeps[i]))
-        else:
-            out.append(_plan_v0(lons[i], lats[i], gplan, _dev.to_host(keeps[i]).astype(bool)))
+    with ThreadPoolExecutor(workers) as ex:
+        # map() yields in order as results arrive: the device part of granule i runs
+        # while the triangulations of the later granules are still on the pool
+        for i, (tri, ties) in enumerate(ex.map(lambda i: native_delaunay(lons[i], lats[i]),
+                                               range(n))):
+            if tri is None:
+                out.append(None)
+            elif ties == 0 or _plan_mode() == "v1":
+                out.append(_plan_v1_device(tri, lonlat_dev[i], gplan, keeps[i]))
+            else:
+                out.append(_plan_v0(lons[i], lats[i], gplan, _dev.to_host(keeps[i]).astype(bool)))
     return out

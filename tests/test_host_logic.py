@@ -228,3 +228,71 @@ def test_native_delaunay_exact_predicates_on_nearly_degenerate_input():
         if incircle(a, b, c, d) > 0:
             violations += 1
     assert violations == 0
+
+
+def _valid_triangulation(x, y, tri):
+    """All triangles non-degenerate and their areas add up to the hull's."""
+    from scipy.spatial import ConvexHull
+    a, b, c = (tri[:, k] for k in range(3))
+    area2 = (x[b] - x[a]) * (y[c] - y[a]) - (y[b] - y[a]) * (x[c] - x[a])
+    hull = ConvexHull(np.column_stack((x, y)))
+    return bool(np.all(area2 != 0)) and np.isclose(np.abs(area2).sum() / 2, hull.volume, rtol=1e-9)
+
+
+def test_lattice_delaunay_equals_general_builder():
+    """oisat_h_delaunay_swath (2-D lon/lat: coarse-to-fine lattice insertion) must give
+    the triangle set of the general builder / Qhull on every kind of swath."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(5)
+    swaths = []
+    for geo in (synth.regional_geo(cases.REGION),                       # mid-latitude piece
+                dict(node_lon_deg=172.0, u0_deg=10, u1_deg=25),         # date-line crossing
+                dict(node_lon_deg=30.0, u0_deg=60, u1_deg=120)):        # over the pole: lat turns round
+        lat, lon = synth.swath_geolocation(150, 40, rng=rng, **geo)
+        swaths.append((lon.astype(np.float64), lat.astype(np.float64)))
+    lat, lon = swaths[0][1], swaths[0][0]
+    swaths.append((lon[:, ::-1].copy(), lat[:, ::-1].copy()))           # mirrored handedness
+    swaths.append((lon.T.copy(), lat.T.copy()))                         # long axis second
+    swaths.append((lon[:2], lat[:2]))                                   # two scan lines
+    swaths.append((lon[:, :2].copy(), lat[:, :2].copy()))               # two pixels per line
+    gx, gy = np.meshgrid(np.arange(23.0), np.arange(17.0))              # jittered regular lattice
+    swaths.append((gx + rng.uniform(-0.3, 0.3, gx.shape), gy + rng.uniform(-0.3, 0.3, gy.shape)))
+    for lon, lat in swaths:
+        tri, ties, path = plan.native_delaunay_path(lon, lat)
+        assert path == 1 and ties == 0, (lon.shape, path, ties)
+        ref, ties_ref = plan.native_delaunay(lon.ravel(), lat.ravel())
+        assert ties_ref == 0
+        assert _tri_set(tri) == _tri_set(ref), lon.shape
+        assert _tri_set(tri) == _tri_set(Delaunay(np.column_stack((lon.ravel(), lat.ravel()))).simplices)
+
+
+def test_lattice_delaunay_degenerate_lattices():
+    # exactly regular lattice: points land ON edges and hull edges while inserting
+    # (2 -> 4 splits, also against ghost triangles); valid, but ties everywhere
+    gx, gy = np.meshgrid(np.arange(13.0), np.arange(9.0))
+    tri, ties, path = plan.native_delaunay_path(gx, gy)
+    assert path == 1 and ties > 0 and len(tri) == 2 * 12 * 8
+    assert _valid_triangulation(gx.ravel(), gy.ravel(), tri)
+    # rows exactly collinear, columns sheared: still on-edge insertions, no co-circular quads
+    sx = gx + 0.375 * gy + 0.015625 * gx * gx        # dyadic: exact in floating point
+    tri, ties, path = plan.native_delaunay_path(sx, gy)
+    assert path == 1 and _valid_triangulation(sx.ravel(), gy.ravel(), tri)
+    ref, _ = plan.native_delaunay(sx.ravel(), gy.ravel())
+    if ties == 0:
+        assert _tri_set(tri) == _tri_set(ref)
+    # repeated points are not vertices
+    dx, dy = gx + 0.2 * np.sin(gy), gy + 0.1 * np.cos(3 * gx)
+    dx[4, 5], dy[4, 5] = dx[4, 4], dy[4, 4]
+    tri, ties, path = plan.native_delaunay_path(dx, dy)
+    assert path == 1 and len({4 * 13 + 4, 4 * 13 + 5} & {int(v) for v in tri.ravel()}) == 1
+    assert _valid_triangulation(dx.ravel(), dy.ravel(), tri)
+    # all points on one line: no triangle at all
+    tri, ties, path = plan.native_delaunay_path(gx, 2.0 * gx + 1.0)
+    assert tri is None
+    # non-finite coordinates: scipy.spatial.Delaunay raises and the reference skips the
+    # granule (interpolator.py:152-155), so no triangulation is reported either way
+    for bad in (np.nan, np.inf):
+        nx = dx.copy()
+        nx[3, 7] = bad
+        assert plan.native_delaunay_path(nx, dy)[0] is None
+        assert plan.native_delaunay(nx.ravel(), dy.ravel())[0] is None
