@@ -186,12 +186,33 @@ pack_kernel(PackSrc s, int L, int has_trop, __half* __restrict__ records) {
   pack_block(s, L, has_trop, (int64_t)blockIdx.x * kPackPixels, records, tile, nullptr);
 }
 
+// Staged row pitch of the bulk-copy path, in halfs: 528 bytes keeps every row
+// 16-byte aligned (a bulk-copy requirement) and rotates the banks by 4 words per row.
+constexpr int kTmaPitch = kPackPixels + 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// Whole month in one launch.  One block = one tile of kPackPixels pixels of one
+// granule.  The reader layout is row-contiguous, so a tile is nrow contiguous
+// 512-byte row segments: they are fetched with bulk asynchronous copies
+// (cp.async.bulk, completion counted on an mbarrier) issued by one warp -- no
+// per-element load/store instructions and no registers tied up while ~50 KB per
+// block are in flight; with four blocks resident per SM that is what it takes to
+// keep HBM busy (the LDG/STS version above stalls at half the bandwidth: 17
+// instructions per element and no loads in flight during its store phase).  The
+// transposition then happens on the way out: a thread assembles one 16-byte record
+// chunk from eight staged rows and stores it, consecutive threads to consecutive
+// chunks.  Granules whose arrays are not 16-byte aligned (or whose pixel count is
+// not a multiple of 8) take pack_block.
 __global__ void __launch_bounds__(256)
 pack_batch_kernel(const oisat_pack_item* __restrict__ items, int n_items, int L, int has_trop,
                   int qflag_dtype, double thresh, int amf_dtype, __half* __restrict__ records,
-                  double* __restrict__ amf_masked) {
-  extern __shared__ __half tile[];
+                  double* __restrict__ amf_masked, int use_bulk) {
+  extern __shared__ __align__(128) __half tile[];
   __shared__ unsigned char bad[kPackPixels];
+  __shared__ __align__(8) unsigned long long mbar;
   // granule of this block: last item with block0 <= blockIdx.x
   int lo = 0, hi = n_items - 1;
   while (lo < hi) {
@@ -211,8 +232,80 @@ pack_batch_kernel(const oisat_pack_item* __restrict__ items, int n_items, int L,
     }
     bad[threadIdx.x] = is_bad ? 1 : 0;
   }
-  // (pack_block starts with a __syncthreads that also publishes `bad`)
-  pack_block(s, L, has_trop, p0, records + it.px0 * (8 * record_chunks(L, has_trop)), tile, bad);
+  const int nrow = record_rows(L, has_trop);
+  const int nchunk = record_chunks(L, has_trop);
+  const int R = 8 * nchunk;
+  uintptr_t align = (uintptr_t)it.sw | (uintptr_t)it.p_mid | (uintptr_t)it.vcd | (uintptr_t)it.sigma;
+  if (has_trop) align |= (uintptr_t)it.trop;
+  if (!use_bulk || (align & 15) != 0 || (it.n_px & 7) != 0) {
+    // (pack_block starts with a __syncthreads that also publishes `bad`)
+    pack_block(s, L, has_trop, p0, records + it.px0 * R, tile, bad);
+    return;
+  }
+  const int64_t left = it.n_px - p0;
+  const int n_here = left < kPackPixels ? (int)left : kPackPixels;
+  const uint32_t row_bytes = (uint32_t)n_here * (uint32_t)sizeof(__half);  // multiple of 16
+  const uint32_t bar = smem_u32(&mbar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();  // barrier initialised, `bad` published
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                   ::"r"(bar), "r"(row_bytes * (uint32_t)nrow) : "memory");
+    __syncwarp();
+    for (int row = threadIdx.x; row < nrow; row += 32) {
+      const __half* src = row < L          ? s.sw + (int64_t)row * s.n_px
+                          : row < 2 * L    ? s.pmid + (int64_t)(row - L) * s.n_px
+                          : row == 2 * L   ? s.vcd
+                          : row == 2 * L + 1 ? s.sigma
+                                             : s.trop;
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+          ::"r"(smem_u32(tile + row * kTmaPitch)), "l"(src + p0), "r"(row_bytes), "r"(bar)
+          : "memory");
+    }
+  }
+  // rows nrow..R-1 are the zero padding of the record
+  for (int i = threadIdx.x; i < (R - nrow) * kPackPixels; i += blockDim.x)
+    tile[(nrow + i / kPackPixels) * kTmaPitch + (i % kPackPixels)] = __float2half_rn(0.0f);
+  {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p;\n\t"
+                   "  mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                   "  selp.b32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(bar) : "memory");
+  }
+  if (threadIdx.x < n_here) {  // sigma -> sigma^2, squared in float16 like numpy (interpolator.py:186)
+    __half* sg = tile + (2 * L + 1) * kTmaPitch + threadIdx.x;
+    const float g = __half2float(*sg);
+    *sg = __float2half_rn(__fmul_rn(g, g));
+  }
+  __syncthreads();
+  const unsigned short* t16 = reinterpret_cast<const unsigned short*>(tile);
+  uint4* dst = reinterpret_cast<uint4*>(records + (it.px0 + p0) * R);
+  const int total = n_here * nchunk;
+  const int kstride = nchunk * kTmaPitch;  // rows q, q+nchunk, ... are the 8 elements of chunk q
+  const int dpx = (int)blockDim.x / nchunk, dq = (int)blockDim.x % nchunk;
+  int px = threadIdx.x / nchunk, q = threadIdx.x % nchunk;
+  const uint32_t nan2 = 0x7e007e00u;  // two float16 quiet NaNs
+  for (int c = threadIdx.x; c < total; c += blockDim.x) {
+    const unsigned short* e = t16 + q * kTmaPitch + px;
+    uint4 v;
+    v.x = (uint32_t)e[0] | ((uint32_t)e[kstride] << 16);
+    v.y = (uint32_t)e[2 * kstride] | ((uint32_t)e[3 * kstride] << 16);
+    v.z = (uint32_t)e[4 * kstride] | ((uint32_t)e[5 * kstride] << 16);
+    v.w = (uint32_t)e[6 * kstride] | ((uint32_t)e[7 * kstride] << 16);
+    // a masked pixel is a NaN vertex for EVERY field (interpolator.py:126-128,163)
+    if (bad[px]) v = make_uint4(nan2, nan2, nan2, nan2);
+    dst[c] = v;
+    px += dpx;
+    q += dq;
+    if (q >= nchunk) { q -= nchunk; ++px; }
+  }
 }
 
 // ------------------------------------------------------------------- fused ----
@@ -477,12 +570,16 @@ extern "C" int oisat_pack_batch(const oisat_pack_item* items, int32_t n_items,
   OISAT_CHECK_ARG(qflag_dtype == OISAT_F16 || qflag_dtype == OISAT_F32 || qflag_dtype == OISAT_F64,
                   "bad quality-flag dtype");
   const int R = 8 * record_chunks(n_sat_lev, has_trop);
-  const size_t smem = (size_t)kPackPixels * (R + 2) * sizeof(__half);
+  const size_t smem_ldg = (size_t)kPackPixels * (R + 2) * sizeof(__half);
+  const size_t smem_bulk = (size_t)R * kTmaPitch * sizeof(__half);
+  const size_t smem = smem_ldg > smem_bulk ? smem_ldg : smem_bulk;
+  const char* mode = std::getenv("OISAT_PACK");  // "ldg" forces the load/store path (A/B runs)
+  const int use_bulk = !(mode && mode[0] == 'l');
   OISAT_CHECK_CUDA(cudaFuncSetAttribute(pack_batch_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pack_batch_kernel<<<(unsigned)total_blocks, 256, smem, (cudaStream_t)stream>>>(
       items, n_items, n_sat_lev, has_trop, qflag_dtype, flag_thresh, amf_dtype, (__half*)records,
-      amf_masked);
+      amf_masked, use_bulk);
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
 }
