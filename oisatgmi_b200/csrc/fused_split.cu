@@ -20,6 +20,9 @@
 //
 // Costs 2 x 8 bytes x rows per pair of extra HBM traffic for the row buffer and
 // buys ~4x fewer instructions for the vertical operator.
+#include <cmath>
+#include <mutex>
+
 #include "vertical.cuh"
 
 namespace oisat {
@@ -127,11 +130,45 @@ gather_rows_kernel(const __grid_constant__ SplitParams P) {
 }
 
 // ---------------------------------------------------------------------------
+// natural logarithm, table-driven
+// ---------------------------------------------------------------------------
+// The merge below needs log p of every gridded satellite level (amf_recal.py:
+// 95-97): L logarithms per pair, 36% of the kernel's instructions with the CUDA
+// libm routine (~85 SASS instructions each, special cases included).  This one
+// is ~25: with x = 2^e * m and c_i the midpoint of the 1/128-wide interval of m,
+//     log x = e ln2 - log(r_i) + log1p(z),   r_i = fl(1 / c_i),  z = m r_i - 1,
+// |z| <= 2^-8, log1p by its series up to z^6 (truncation < 2e-18), -log(r_i)
+// tabulated for the ROUNDED r_i so the table absorbs its rounding.  Error
+// ~2e-16 relative, the same class as libm's and numpy's (which differ from one
+// another in the last bit as well); the parity bar for float64 fields is 1e-6.
+struct LogTable {
+  double r[128];
+  double neg_log_r[128];
+};
+__device__ LogTable g_log_table;
+
+__device__ __forceinline__ double table_log(double x, const LogTable* __restrict__ tab) {
+  if (!(x >= 2.2250738585072014e-308 && x <= 1.7976931348623157e308)) return log(x);
+  const long long bits = __double_as_longlong(x);
+  const int e = (int)(bits >> 52) - 1023;
+  const int i = (int)(bits >> 45) & 127;
+  const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+  const double z = fma(m, tab->r[i], -1.0);
+  double p = fma(z, -1.0 / 6.0, 0.2);
+  p = fma(z, p, -0.25);
+  p = fma(z, p, 1.0 / 3.0);
+  p = fma(z, p, -0.5);
+  const double l1p = fma(z * z, p, z);
+  return fma((double)e, 0.6931471805599453, tab->neg_log_r[i] + l1p);
+}
+
+// ---------------------------------------------------------------------------
 // one thread per pair
 // ---------------------------------------------------------------------------
 struct RowView {
-  const double* base;  // &rows[tile][0][pair % 16]
-  __device__ __forceinline__ double at(int row) const { return __ldg(base + row * 16); }
+  double* base;  // &staged rows[tile][0][pair % 16], in shared memory
+  __device__ __forceinline__ double at(int row) const { return base[row * 16]; }
+  __device__ __forceinline__ void set(int row, double v) const { base[row * 16] = v; }
 };
 
 // numpy pairwise sums for n <= 128 (slow path only)
@@ -165,10 +202,10 @@ __device__ __noinline__ double amf_slow_path(const RowView& r, int L, int n_ctm,
                                              const float* pm, int64_t stride, double* col) {
   double xs[kMaxSatLev], ys[kMaxSatLev];
   for (int i = 0; i < L; ++i) {
-    const double xi = log(r.at(L + i));
+    const double xi = r.at(L + i);
     int rank = 0;
     for (int j = 0; j < L; ++j) {
-      const double xj = log(r.at(L + j));
+      const double xj = r.at(L + j);
       const bool eq = (xj == xi) || (xj != xj && xi != xi);
       rank += (nan_less(xj, xi) || (eq && j < i)) ? 1 : 0;
     }
@@ -192,14 +229,56 @@ __device__ __noinline__ double amf_slow_path(const RowView& r, int L, int n_ctm,
   return vcd_m != 0.0 ? scd / vcd_m : qnan();
 }
 
+constexpr int kVerticalThreads = 64;   // four 16-pair tiles of the row buffer per block
+
+// The rows of a block's pairs are one contiguous piece of the buffer (4 tiles x
+// nrow_out x 16 doubles, ~48 KB for OMI HCHO): one bulk asynchronous copy brings
+// it into shared memory while the other resident blocks compute.  Before this,
+// every bracket shift of the walk below waited for its own global load -- and a
+// warp shifts whenever ANY of its lanes does, ~150 exposed DRAM round trips per
+// warp (ncu: 60% of the stall samples were long-scoreboard, IPC 0.3).
 template <bool HAS_TROP>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(kVerticalThreads)
 vertical_rows_kernel(const __grid_constant__ SplitParams P) {
+  extern __shared__ __align__(128) double rows_s[];  // [4][nrow_out][16]
+  __shared__ LogTable tab;
+  __shared__ __align__(8) unsigned long long mbar;
   const oisat_fused_args& A = P.a;
-  const int64_t pair = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pair >= A.n_pairs) return;
   const int L = A.n_sat_lev, n_ctm = A.n_ctm_lev;
-  RowView r{P.rows + (pair >> 4) * (int64_t)P.nrow_out * 16 + (pair & 15)};
+  const int64_t tile0 = (int64_t)blockIdx.x * (kVerticalThreads / 16);
+  const int64_t n_tiles = (A.n_pairs + 15) >> 4;
+  const int tiles_here = (int)(n_tiles - tile0 < kVerticalThreads / 16 ? n_tiles - tile0
+                                                                       : kVerticalThreads / 16);
+  const uint32_t tile_bytes = (uint32_t)P.nrow_out * 16u * (uint32_t)sizeof(double);
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 ::"r"(bar), "r"(tile_bytes * (uint32_t)tiles_here) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"((uint32_t)__cvta_generic_to_shared(rows_s)),
+          "l"(P.rows + tile0 * (int64_t)P.nrow_out * 16), "r"(tile_bytes * (uint32_t)tiles_here),
+          "r"(bar)
+        : "memory");
+  }
+  for (int i = threadIdx.x; i < 128; i += kVerticalThreads) {
+    tab.r[i] = g_log_table.r[i];
+    tab.neg_log_r[i] = g_log_table.neg_log_r[i];
+  }
+  __syncthreads();  // barrier initialised, table staged
+  const int64_t pair = (int64_t)blockIdx.x * kVerticalThreads + threadIdx.x;
+  if (pair >= A.n_pairs) return;
+  {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p;\n\t"
+                   "  mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                   "  selp.b32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(bar) : "memory");
+  }
+  RowView r{rows_s + (threadIdx.x >> 4) * (P.nrow_out * 16) + (threadIdx.x & 15)};
   const double vcd = r.at(2 * L);
   const double old_amf = A.staged[4 * A.n_pairs + pair];
   double new_amf = qnan(), vnew = qnan(), col = qnan();
@@ -217,25 +296,28 @@ vertical_rows_kernel(const __grid_constant__ SplitParams P) {
     // profile that is the storage order or its reverse.
     const bool descending = r.at(L) > r.at(2 * L - 1);
     auto row_of = [&](int j) { return descending ? L - 1 - j : j; };
-    // interp1d(xs, SW)(log p_model) as a merge: model levels run from the surface
-    // up, so the query only decreases and so does idx = searchsorted(xs, v, 'left').
-    // The bracket [c-1, c], c = clip(idx, 1, L-1), lives in registers, and the level
-    // below it (xs[c-2]) is requested one shift ahead of its use.
-    int idx = L, c = L - 1;
-    double p_lo = r.at(L + row_of(c - 1));
-    double x_hi = log(r.at(L + row_of(c))), x_lo = log(p_lo);
-    double y_hi = r.at(row_of(c)), y_lo = r.at(row_of(c - 1));
-    // queue of the next kQ levels below the bracket (sorted indices c-2, c-3, ...):
-    // the walk visits every level in order, so their loads are issued kQ shifts ahead
-    constexpr int kQ = 1;
-    double xq[kQ], yq[kQ];
-#pragma unroll
-    for (int q = 0; q < kQ; ++q) {
-      const int j = c - 2 - q;
-      xq[q] = j >= 0 ? r.at(L + row_of(j)) : 0.0;
-      yq[q] = j >= 0 ? r.at(row_of(j)) : 0.0;
+    // Phase A, the same instruction stream for every lane: p -> log p, in place in
+    // this thread's own column of the staged rows (sorted order is the storage
+    // order or its reverse).  Strict monotonicity is checked for every level; ties
+    // and NaNs take scipy's argsort path (slow path).
+    bool sorted = n_ctm >= 8;
+    {
+      double prev = -CUDART_INF;
+#pragma unroll 4
+      for (int j = 0; j < L; ++j) {
+        const int row = L + row_of(j);
+        const double x = table_log(r.at(row), &tab);
+        r.set(row, x);
+        sorted = sorted && (prev < x);
+        prev = x;
+      }
     }
-    bool sorted = (x_lo < x_hi) && n_ctm >= 8;  // strict; ties and NaNs take scipy's argsort path
+    // Phase B: interp1d(xs, SW)(log p_model) as a merge: model levels run from the
+    // surface up, so the query only decreases and so does idx = searchsorted(xs, v,
+    // 'left').  The bracket [c-1, c], c = clip(idx, 1, L-1), lives in registers.
+    int idx = L, c = L - 1;
+    double x_hi = r.at(L + row_of(c)), x_lo = r.at(L + row_of(c - 1));
+    double y_hi = r.at(row_of(c)), y_lo = r.at(row_of(c - 1));
     double rden = 1.0 / (x_hi - x_lo);
     double qa[8], colsum = 0.0, scd = 0.0;
     float qb[8];
@@ -264,17 +346,8 @@ vertical_rows_kernel(const __grid_constant__ SplitParams P) {
               c = nc;
               x_hi = x_lo;
               y_hi = y_lo;
-              p_lo = xq[0];
-              x_lo = log(p_lo);
-              y_lo = yq[0];
-#pragma unroll
-              for (int q = 0; q + 1 < kQ; ++q) { xq[q] = xq[q + 1]; yq[q] = yq[q + 1]; }
-              {
-                const int j = c - 1 - kQ;  // new tail of the queue
-                xq[kQ - 1] = j >= 0 ? r.at(L + row_of(j)) : 0.0;
-                yq[kQ - 1] = j >= 0 ? r.at(row_of(j)) : 0.0;
-              }
-              sorted = sorted && (x_lo < x_hi);
+              x_lo = r.at(L + row_of(c - 1));
+              y_lo = r.at(row_of(c - 1));
               rden = 1.0 / (x_hi - x_lo);
             }
           }
@@ -304,15 +377,6 @@ vertical_rows_kernel(const __grid_constant__ SplitParams P) {
       colsum = (double)__fadd_rn(__fadd_rn(__fadd_rn(qb[0], qb[1]), __fadd_rn(qb[2], qb[3])),
                                  __fadd_rn(__fadd_rn(qb[4], qb[5]), __fadd_rn(qb[6], qb[7])));
     }
-    // levels the walk never reached must be sorted too, or scipy would have reordered them
-    {
-      double below = p_lo;  // pressures: log is monotone, only strictness could differ
-      for (int j = c - 2; j >= 0 && sorted; --j) {
-        const double xn = r.at(L + row_of(j));
-        sorted = xn < below;
-        below = xn;
-      }
-    }
     if (sorted) {
       new_amf = colsum != 0.0 ? scd / colsum : qnan();
     } else {
@@ -329,6 +393,25 @@ vertical_rows_kernel(const __grid_constant__ SplitParams P) {
 }  // namespace oisat
 
 using namespace oisat;
+
+static int upload_log_table() {
+  static std::once_flag once[64];
+  static int status[64];
+  int dev = 0;
+  OISAT_CHECK_CUDA(cudaGetDevice(&dev));
+  OISAT_CHECK_ARG(dev >= 0 && dev < 64, "device ordinal out of range");
+  std::call_once(once[dev], [dev]() {
+    LogTable h;
+    for (int i = 0; i < 128; ++i) {
+      const double c = 1.0 + (i + 0.5) / 128.0;
+      h.r[i] = 1.0 / c;
+      h.neg_log_r[i] = -std::log(h.r[i]);
+    }
+    status[dev] = (int)cudaMemcpyToSymbol(g_log_table, &h, sizeof(h));
+  });
+  OISAT_CHECK_CUDA((cudaError_t)status[dev]);
+  return OISAT_OK;
+}
 
 extern "C" int64_t oisat_rows_per_pair(int32_t n_sat_lev, int32_t has_trop) {
   return 2 * (int64_t)n_sat_lev + 1 + (has_trop ? 1 : 0);
@@ -354,14 +437,24 @@ extern "C" int oisat_fused_amf_split(const oisat_fused_args* h_args, double* row
   OISAT_CHECK_ARG(a.n_records > 0 && a.n_records * P.nchunk < ((int64_t)1 << 32),
                   "record block too large for 32-bit chunk indices: split the batch");
   cudaStream_t s = (cudaStream_t)stream;
+  if (int rc = upload_log_table()) return rc;
   const size_t tile_bytes = (size_t)P.nrow_out * 17 * sizeof(double);
   gather_rows_kernel<<<(unsigned)ceil_div(a.n_pairs * 16, kGatherThreads), kGatherThreads,
                        tile_bytes, s>>>(P);
   OISAT_CHECK_LAUNCH();
-  if (a.has_trop)
-    vertical_rows_kernel<true><<<(unsigned)ceil_div(a.n_pairs, 128), 128, 0, s>>>(P);
-  else
-    vertical_rows_kernel<false><<<(unsigned)ceil_div(a.n_pairs, 128), 128, 0, s>>>(P);
+  const size_t stage_bytes = (size_t)(kVerticalThreads / 16) * P.nrow_out * 16 * sizeof(double);
+  const unsigned vblocks = (unsigned)ceil_div(a.n_pairs, kVerticalThreads);
+  if (a.has_trop) {
+    OISAT_CHECK_CUDA(cudaFuncSetAttribute(vertical_rows_kernel<true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)stage_bytes));
+    vertical_rows_kernel<true><<<vblocks, kVerticalThreads, stage_bytes, s>>>(P);
+  } else {
+    OISAT_CHECK_CUDA(cudaFuncSetAttribute(vertical_rows_kernel<false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)stage_bytes));
+    vertical_rows_kernel<false><<<vblocks, kVerticalThreads, stage_bytes, s>>>(P);
+  }
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
 }
