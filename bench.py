@@ -333,11 +333,25 @@ def main():
     achieved = fused_bytes / (fused_ms * 1e-3) / 1e9
     # whole-pipeline view with SURVEY.md section 8d's per-pixel figure (427 B/px for OMI HCHO)
     pipe_bytes_px = 216 + (n_pairs / n_px) * (864 + 160) + 207936 * 14 * 8 / n_px
-    roofline = {"bound": "hbm", "kernel": "fused_amf_kernel", "achieved": achieved, "peak": peak,
+    # measured DRAM traffic of the same two kernels: one `ncu --set full` capture (profiles/), scaled
+    # linearly from the captured launch's pixel count to this launch's
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        per_px = sum(v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in tr["kernels"].items()
+                     if "rows_kernel" in k) / tr["n_px"]
+        traffic = per_px * n_px
+    except Exception:
+        pass
+    roofline = {"bound": "hbm",
+                "kernel": "gather_rows_kernel + vertical_rows_kernel (one oisat_fused_amf_split call)",
+                "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else
                                "fallback 6650 GB/s (of fallback)",
-                "traffic": None,
+                "traffic": traffic,
+                "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes_read+write, 120-granule "
+                                  "launch, scaled by pixel count)" if traffic else None,
                 "algorithmic_bytes_per_launch": fused_bytes,
                 "kernel_ms": fused_ms,
                 "pipeline": {"bytes_per_px": pipe_bytes_px,
