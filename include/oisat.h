@@ -118,6 +118,22 @@ int oisat_plan_fill(const int32_t* cells, int64_t n_cells, const int32_t* window
                     int32_t coord_dtype, const double* xs, int64_t W, const double* ys,
                     int32_t pair_major, int32_t* vert, double* w, void* stream);
 
+/* ---- nearest-neighbour gridding modes (interpolator.py:17-20 type 2, :28-33 type 4) ----
+ * node_px[f] <- index of the pixel nearest to mesh node f (squared Euclidean distance
+ * in degrees, float64, as scipy's KD-tree compares it; lowest index on exact ties), or
+ * INT32_MAX when no pixel lies within `radius` -- those nodes are NaN in the reference
+ * too (dists > 2*threshold, :19,32).  `work`: W*H uint64 of scratch. */
+int oisat_nearest_pixel(const void* px_lon, const void* px_lat, int32_t coord_dtype, int64_t n_px,
+                        const double* xs, int64_t W, const double* ys, int64_t H, double radius,
+                        uint64_t* work, int32_t* node_px, void* stream);
+
+/* nearest-neighbour stencil of the kept cells, in the layout of oisat_plan_fill: each
+ * window node contributes the triple (pixel, pixel, pixel) with weights (1, 0, 0), so the
+ * same apply / fused kernels serve both modes.  window == NULL: nwin = 1, node = cell. */
+int oisat_plan_fill_nearest(const int32_t* cells, int64_t n_cells, const int32_t* window,
+                            int32_t nwin, const int32_t* node_px, int32_t pair_major,
+                            int32_t* vert, double* w, void* stream);
+
 /* good[p] = (quality_flag[p] > thresh)  (interpolator.py:126-128) */
 int oisat_quality_mask(const void* qflag, int32_t dtype, int64_t n_px, double thresh,
                        uint8_t* good, void* stream);

@@ -61,6 +61,8 @@ PROTOTYPES = {
     "oisat_plan_cells": (C.c_int, [vp, i32, vp, i64, vp, vp, vp]),
     "oisat_plan_fill": (C.c_int, [vp, i64, vp, i32, vp, vp, vp, vp, i32, vp, i64, vp, i32, vp, vp,
                                   vp]),
+    "oisat_nearest_pixel": (C.c_int, [vp, vp, i32, i64, vp, i64, vp, i64, f64, vp, vp, vp]),
+    "oisat_plan_fill_nearest": (C.c_int, [vp, i64, vp, i32, vp, i32, vp, vp, vp]),
     "oisat_quality_mask": (C.c_int, [vp, i32, i64, f64, vp, vp]),
     "oisat_interp_apply": (C.c_int, [vp, vp, i32, i64, vp, C.POINTER(Field), i32, vp, i64, vp, vp]),
     "oisat_vertical_amf": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, i32,

@@ -126,9 +126,9 @@ def interpolator(interpolator_type: int, grid_size: float, sat_data, ctm_models_
     the model is finer than `grid_size`).  Mirrors interpolator.py:100-291:
     returns a new satellite_amf / satellite_opt, or None when the pixel centres
     cannot be triangulated or nothing of the granule falls on the grid."""
-    if interpolator_type != 1:
-        # types 2/3/4 (nearest, RBF, KD-tree; interpolator.py:17-33) are used by
-        # TROPOMI HCHO and TEMPO only -- SURVEY.md section 8(f-2), not built yet
+    if interpolator_type not in (1, 2, 4):
+        # type 3 (RBFInterpolator, interpolator.py:21-27) is not used by any reader
+        # (SURVEY.md section 8a-1) and not built; anything else raises there too (:34-36)
         raise Exception("other type of interpolation methods has not been implemented yet")
     _dev.require_cuda()
     kind = kind_of(sat_data)
@@ -136,7 +136,15 @@ def interpolator(interpolator_type: int, grid_size: float, sat_data, ctm_models_
     lat = np.asarray(sat_data.latitude_center)
     lon = np.asarray(sat_data.longitude_center)
     n_px = lat.size
-    gp = _plan.granule_plan(lon, lat, gpl, radius=grid_size * 2.0)
+    if interpolator_type == 1:
+        gp = _plan.granule_plan(lon, lat, gpl, radius=grid_size * 2.0)
+    else:
+        # nearest pixel: NearestNDInterpolator over the Delaunay points (type 2; the
+        # granule is skipped when the triangulation fails, :151-155) or the KD-tree
+        # query itself (type 4) -- the same answer
+        if interpolator_type == 2 and not _plan.triangulable(lon, lat):
+            return None
+        gp = _plan.nearest_plan(lon, lat, gpl, radius=grid_size * 2.0)
     if gp is None:
         return None
     n_out = int(np.prod(gpl.out_shape))

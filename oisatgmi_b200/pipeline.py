@@ -33,8 +33,11 @@ class _Granule:
 
 class MonthPipeline:
     def __init__(self, ctm_data, grid_size, flag_thresh, sensor="OMI", gas="NO2", error_ctm=50.0,
-                 process_group=None):
+                 process_group=None, interpolator_type=1):
         _dev.require_cuda()
+        if interpolator_type not in (1, 2, 4):  # interpolator.py:10-36; 3 (RBF) is not built
+            raise Exception("other type of interpolation methods has not been implemented yet")
+        self.interpolator_type = int(interpolator_type)
         self.ctm_data = ctm_data
         self.coords = {"Latitude": ctm_data[0].latitude, "Longitude": ctm_data[0].longitude}
         self.grid_size = float(grid_size)
@@ -123,10 +126,13 @@ class MonthPipeline:
         g.dev = {k: (None if h is None else h.to(dev, non_blocking=True))
                  for k, h in g.host.items()}
         if plan is None:
-            plan = _plan.granule_plan(np.asarray(sat.longitude_center),
-                                      np.asarray(sat.latitude_center), self.gplan,
-                                      radius=self.grid_size * 2.0,
-                                      lonlat_dev=(g.dev["lon"], g.dev["lat"]), cache=False)
+            lon, lat = np.asarray(sat.longitude_center), np.asarray(sat.latitude_center)
+            if self.interpolator_type == 1:
+                plan = _plan.granule_plan(lon, lat, self.gplan, radius=self.grid_size * 2.0,
+                                          lonlat_dev=(g.dev["lon"], g.dev["lat"]), cache=False)
+            elif self.interpolator_type == 4 or _plan.triangulable(lon, lat):
+                plan = _plan.nearest_plan(lon, lat, self.gplan, radius=self.grid_size * 2.0,
+                                          lonlat_dev=(g.dev["lon"], g.dev["lat"]))
         g.plan = plan
         g.slot = self._slot_of(sat.time)
         g.time = sat.time

@@ -387,6 +387,62 @@ def _plan_v1_device(tri_host, lonlat_dev, gplan, keep_dev):
     return GranulePlan(gplan, cells, keep=None, dev_pairs=(vert, w), builder="v1")
 
 
+def triangulable(lon, lat) -> bool:
+    """Would scipy.spatial.Delaunay accept these points?  Interpolator type 2 builds
+    the triangulation although NearestNDInterpolator only uses its points, and skips
+    the granule when that fails (interpolator.py:151-155): non-finite coordinates,
+    fewer than three points, or all points on one line."""
+    x = np.asarray(lon, dtype=np.float64).ravel()
+    y = np.asarray(lat, dtype=np.float64).ravel()
+    if x.size < 3 or not (np.isfinite(x).all() and np.isfinite(y).all()):
+        return False
+    d = np.flatnonzero((x != x[0]) | (y != y[0]))
+    if d.size == 0:
+        return False
+    j = d[0]
+    cross = (x - x[0]) * (y[j] - y[0]) - (y - y[0]) * (x[j] - x[0])
+    return bool(np.any(cross != 0.0))
+
+
+def nearest_plan(lon, lat, gplan: GridPlan, radius: float, lonlat_dev=None):
+    """Stencil of the nearest-neighbour gridding modes (interpolator.py:17-20,28-33):
+    every mesh node within `radius` of a pixel takes the value of its nearest pixel
+    (K0's scatter with an atomic minimum), then the same box window / nearest-node
+    composition as the linear mode.  Built entirely on the device."""
+    L = _lib.lib()
+    if lonlat_dev is None:
+        lonlat_dev = (_dev.to_device(coord_array(lon)), _dev.to_device(coord_array(lat)))
+    lo, la = lonlat_dev
+    xs, ys = gplan.dev_axes()
+    n_nodes = gplan.H * gplan.W
+    s = _dev.stream()
+    work = _dev.empty((n_nodes,), "int64")
+    node_px = _dev.empty((n_nodes,), "int32")
+    _lib.check(L.oisat_nearest_pixel(lo.data_ptr(), la.data_ptr(), _dev.dtype_code(lo), lo.numel(),
+                                     xs.data_ptr(), gplan.W, ys.data_ptr(), gplan.H, float(radius),
+                                     work.data_ptr(), node_px.data_ptr(), s))
+    if gplan.upscale:
+        window, nn_ok = gplan.dev_tables()
+        n_cell = int(np.prod(gplan.out_shape))
+        ok = _dev.empty((n_cell,), "uint8")
+        _lib.check(L.oisat_plan_cells(window.data_ptr(), gplan.nwin, nn_ok.data_ptr(), n_cell,
+                                      node_px.data_ptr(), ok.data_ptr(), s))
+        cells = np.flatnonzero(_dev.to_host(ok))
+        wptr = window.data_ptr()
+    else:
+        cells = np.flatnonzero(_dev.to_host(node_px) != 2 ** 31 - 1)
+        wptr = None
+    n = cells.size
+    S = 3 * gplan.nwin
+    vert = _dev.empty((n, S), "int32")
+    w = _dev.empty((n, S))
+    if n:
+        cells_d = _dev.to_device(cells.astype(np.int32))
+        _lib.check(L.oisat_plan_fill_nearest(cells_d.data_ptr(), n, wptr, gplan.nwin,
+                                             node_px.data_ptr(), 1, vert.data_ptr(), w.data_ptr(), s))
+    return GranulePlan(gplan, cells, keep=None, dev_pairs=(vert, w), builder="nearest")
+
+
 def granule_plan(lon, lat, gplan: GridPlan, radius: float, lonlat_dev=None, cache=True,
                  keep=None):
     """Build (or fetch) the stencil of one granule.  Returns None when the pixel

@@ -57,7 +57,7 @@ def amf_chain(ref, name):
     rcls = ref.config.satellite_amf
     grids = []
     for i, g in enumerate(c["granules"]):
-        r = quiet(ref.interpolator, 1, c["grid_size"], config.convert(cases.clone(g), rcls),
+        r = quiet(ref.interpolator, c["kind"], c["grid_size"], config.convert(cases.clone(g), rcls),
                   c["coords"], flag_thresh=c["flag_thresh"])
         assert r is not None
         put(store, "interp%d" % i, r, ["vcd", "amf", "tropopause", "uncertainty", "pressure_mid",

@@ -37,16 +37,21 @@ def amf_granules(product, seeds, nt, nxt, region=REGION, bad_fraction=0.25):
 
 
 CASES = {
-    # name: (product, grid_size, flag_thresh, seeds, nt, nxt)
+    # name: (product, grid_size, flag_thresh, seeds, nt, nxt[, interpolator type])
     "omi_no2": ("OMI_NO2", 0.25, 0.0, (3, 4, 5), 260, 60),
     "omi_hcho": ("OMI_HCHO", 0.25, 0.0, (7, 8), 260, 60),
     "tropomi_no2": ("TROPOMI_NO2", 0.10, 0.75, (9,), 620, 140),
+    # the nearest-neighbour gridding modes (interpolator.py:17-20 type 2: TROPOMI HCHO,
+    # reader.py:698-700; :28-33 type 4: TEMPO, reader.py:528-530) on the same kind of data
+    "tropomi_nearest": ("TROPOMI_NO2", 0.10, 0.5, (12,), 420, 120, 2),
+    "omi_kdtree": ("OMI_HCHO", 0.25, 0.0, (13, 14), 200, 60, 4),
 }
 
 
 def amf_case(name):
-    product, gs, thr, seeds, nt, nxt = CASES[name]
-    return dict(product=product, grid_size=gs, flag_thresh=thr,
+    product, gs, thr, seeds, nt, nxt = CASES[name][:6]
+    kind = CASES[name][6] if len(CASES[name]) > 6 else 1
+    return dict(product=product, grid_size=gs, flag_thresh=thr, kind=kind,
                 granules=amf_granules(product, seeds, nt, nxt), coords=coords(), ctm=ctm(),
                 sensor=product.split("_")[0], gas=product.split("_")[1])
 

@@ -19,7 +19,7 @@ def amf_chain(impl, name, stop_after=None):
     store = {}
     grids = []
     for i, g in enumerate(c["granules"]):
-        r = impl.interpolator(1, c["grid_size"], cases.clone(g), c["coords"],
+        r = impl.interpolator(c["kind"], c["grid_size"], cases.clone(g), c["coords"],
                               flag_thresh=c["flag_thresh"])
         assert r is not None
         put(store, "interp%d" % i, r, ["vcd", "amf", "tropopause", "uncertainty", "pressure_mid",

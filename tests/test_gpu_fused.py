@@ -20,7 +20,7 @@ def run_pipeline(name):
     from oisatgmi_b200.pipeline import MonthPipeline
     c = cases.amf_case(name)
     pipe = MonthPipeline(c["ctm"], c["grid_size"], c["flag_thresh"], sensor=c["sensor"],
-                         gas=c["gas"], error_ctm=50.0)
+                         gas=c["gas"], error_ctm=50.0, interpolator_type=c["kind"])
     for g in c["granules"]:
         assert pipe.add_granule(cases.clone(g))
     res = pipe.results_to_host(pipe.run())

@@ -76,6 +76,43 @@ def test_distance_predicate_is_bit_exact():
     assert np.array_equal(got.astype(bool), want.ravel())
 
 
+def test_nearest_pixel_matches_kdtree_query():
+    """oisat_nearest_pixel against cKDTree.query: the same pixel index for every node
+    inside the radius, INT32_MAX outside; both output layouts of the stencil."""
+    from scipy.spatial import cKDTree
+    from oisatgmi_b200 import _dev, plan
+    c = cases.amf_case("omi_kdtree")
+    radius = 2 * c["grid_size"]
+    for region_coords in (c["coords"], None):
+        if region_coords is None:   # a model finer than the working mesh: output on the mesh
+            lat = np.arange(30.0, 50.0, 0.1)
+            lon = np.arange(-105.0, -75.0, 0.1)
+            X, Y = np.meshgrid(lon, lat)
+            region_coords = {"Latitude": Y, "Longitude": X}
+        gpl = plan.grid_plan(region_coords, c["grid_size"])
+        g = c["granules"][0]
+        lon = np.asarray(g.longitude_center)
+        lat = np.asarray(g.latitude_center)
+        gp = plan.nearest_plan(lon, lat, gpl, radius)
+        X, Y = gpl.mesh()
+        pts = np.column_stack((lon.ravel().astype(np.float64), lat.ravel().astype(np.float64)))
+        d, idx = cKDTree(pts).query(np.column_stack((X.ravel(), Y.ravel())))
+        inside = ~(d > radius)
+        if gpl.upscale:
+            valid = gpl.nn_ok & inside[gpl.window].all(axis=1)
+            cells = np.flatnonzero(valid)
+            want = idx[gpl.window[cells]]                     # (n, nwin)
+        else:
+            cells = np.flatnonzero(inside)
+            want = idx[cells][:, None]
+        assert np.array_equal(gp.cells, cells)
+        vert = gp.vert.reshape(gp.nwin, 3, -1)                # stencil-major (3*nwin, n)
+        assert np.array_equal(vert[:, 0, :].T, want)
+        assert np.array_equal(vert[:, 1, :], vert[:, 0, :]) and np.array_equal(vert[:, 2, :], vert[:, 0, :])
+        w = gp.w.reshape(gp.nwin, 3, -1)
+        assert np.all(w[:, 0, :] == 1.0) and np.all(w[:, 1:, :] == 0.0)
+
+
 def test_oi_knee_index_and_means_are_bit_exact():
     """The 99 nanmean(AK_r) follow numpy's pairwise order -> identical floats ->
     identical discrete knee decision."""
