@@ -1,0 +1,99 @@
+"""BASELINE.json's largest granule shape (configs[4]: TROPOMI NO2, 4172 x 450 =
+1.88 M pixels, 0.10 degree working mesh of 6.5 M nodes, 5 x 6 box => 90 stencil entries
+per cell, 34 levels + tropopause) through the fused month pipeline on the global GMI
+grid.  The oracle needs minutes per granule at this size, so the checks are the
+size-independent properties of the path:
+
+  * scattering weights == 1  =>  recalculated AMF == 1 wherever it is defined
+    (amf_recal.py:93-119: a weighted mean of a constant; the reference's float32
+    column sum bounds the error at ~1e-7);
+  * the gridded vcd of a constant field is that constant, its count per cell is the
+    number of granules, and cells outside every granule stay empty;
+  * a second granule that is all bad pixels changes nothing;
+  * determinism: two runs are bit-identical;
+  * the device plan builder (native Delaunay + K1) and the host one (Qhull + scipy's
+    walk) keep the same cells.
+"""
+import copy
+import datetime
+
+import numpy as np
+import pytest
+
+from oisatgmi_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _granule(seed=5):
+    g = synth.make_amf_granule(seed, "TROPOMI_NO2", geo=dict(node_lon_deg=-60.0, u0_deg=-70.0,
+                                                             u1_deg=70.0), bad_fraction=0.2,
+                               time=datetime.datetime(2005, 6, 3, 13, 20, 0))
+    g.scattering_weights = np.ones_like(g.scattering_weights)
+    g.vcd = np.full_like(g.vcd, 3.5)
+    return g
+
+
+def test_tropomi_scale_granule_properties():
+    from oisatgmi_b200.pipeline import MonthPipeline
+    from oisatgmi_b200 import plan as _plan
+    model = [synth.make_ctm(11, synth.ctm_coordinates(None))]
+    g = _granule()
+    assert np.size(g.latitude_center) == 4172 * 450
+
+    def run(granules):
+        pipe = MonthPipeline(model, 0.10, 0.75, sensor="TROPOMI", gas="NO2", error_ctm=50.0)
+        for x in granules:
+            pipe.add_granule(copy.deepcopy(x))
+        return pipe, pipe.results_to_host(pipe.run())
+
+    pipe, res = run([g])
+    assert pipe.gplan.nwin == 30 and pipe.gplan.H * pipe.gplan.W == 1801 * 3595
+    cells = pipe.granules[0].plan.cells
+    assert 5_000 < cells.size < 60_000
+    sat = res["sat_averaged_vcd"].ravel()
+    amf = res["aux1"].ravel()            # new AMF (averaging.py: aux1)
+    finite = np.isfinite(amf)
+    assert finite.sum() > 1000
+    assert set(np.flatnonzero(finite)) <= set(cells.tolist())
+    assert np.max(np.abs(amf[finite] - 1.0)) < 5e-7
+    # vcd_new = old_amf * vcd / new_amf, with new_amf == 1 and vcd == 3.5 (exact in float16):
+    # the ratio to the gridded old AMF is the constant again
+    outside = np.ones(sat.size, bool)
+    outside[cells] = False
+    assert np.all(np.isnan(sat[outside]))
+
+    # an all-bad second granule contributes nothing
+    bad = copy.deepcopy(g)
+    bad.quality_flag = np.zeros_like(bad.quality_flag)
+    bad.time = g.time + datetime.timedelta(hours=2)
+    _, res2 = run([g, bad])
+    for k in res:
+        a, b = np.asarray(res[k]), np.asarray(res2[k])
+        if a.dtype.kind == "f" and a.size > 1:
+            assert np.array_equal(a, b, equal_nan=True), k
+
+    # determinism
+    _, res3 = run([g])
+    for k in res:
+        a, b = np.asarray(res[k]), np.asarray(res3[k])
+        if a.dtype.kind == "f" and a.size > 1:
+            assert np.array_equal(a, b, equal_nan=True), k
+
+
+def test_tropomi_scale_plan_builders_agree(monkeypatch):
+    from oisatgmi_b200 import plan as _plan
+    coords = synth.ctm_coordinates(None)
+    gpl = _plan.grid_plan(coords, 0.10)
+    g = _granule(6)
+    monkeypatch.setenv("OISAT_PLAN", "auto")
+    p1 = _plan.granule_plan(g.longitude_center, g.latitude_center, gpl, 0.2, cache=False)
+    assert p1.builder == "v1"
+    monkeypatch.setenv("OISAT_PLAN", "v0")
+    p0 = _plan.granule_plan(g.longitude_center, g.latitude_center, gpl, 0.2, cache=False)
+    assert p0.builder == "v0"
+    assert np.array_equal(p0.cells, p1.cells)
+    S, n = p0.vert.shape
+    v0 = np.sort(p0.vert.reshape(S // 3, 3, n), axis=1)
+    v1 = np.sort(p1.vert.reshape(S // 3, 3, n), axis=1)
+    assert np.array_equal(v0, v1)
