@@ -143,6 +143,51 @@ class MonthPipeline:
         self._buf = None
         return True
 
+    def add_day(self, sats, hosts=None, pin=False):
+        """A batch of reader records (one day of orbits): every array is queued for
+        upload first (asynchronous DMA when the host tensors are pinned), then the
+        geometry plans of the whole batch are built -- triangulations on the host
+        thread pool, the device part granule by granule -- while the copies are in
+        flight.  Returns the number of granules kept."""
+        dev = _dev.device()
+        staged = []
+        for i, sat in enumerate(sats):
+            g = _Granule()
+            g.host = hosts[i] if hosts is not None else self.host_arrays(sat, pin=pin)
+            g.n_px = int(np.size(sat.latitude_center))
+            g.nlev = np.shape(sat.pressure_mid)[0]
+            g.has_trop = g.host["trop"] is not None
+            g.dev = {}
+            for k in ("lon", "lat"):          # the plan builders need these first
+                g.dev[k] = g.host[k].to(dev, non_blocking=True)
+            staged.append(g)
+        for g in staged:
+            for k, h in g.host.items():
+                if k not in g.dev:
+                    g.dev[k] = None if h is None else h.to(dev, non_blocking=True)
+        lons = [np.asarray(s.longitude_center) for s in sats]
+        lats = [np.asarray(s.latitude_center) for s in sats]
+        lonlat = [(g.dev["lon"], g.dev["lat"]) for g in staged]
+        radius = self.grid_size * 2.0
+        if self.interpolator_type == 1:
+            plans = _plan.granule_plans(lons, lats, self.gplan, radius, lonlat_dev=lonlat)
+        else:
+            plans = [(_plan.nearest_plan(lons[i], lats[i], self.gplan, radius, lonlat_dev=lonlat[i])
+                      if self.interpolator_type == 4 or _plan.triangulable(lons[i], lats[i])
+                      else None) for i in range(len(sats))]
+        kept = 0
+        for g, sat, plan in zip(staged, sats, plans):
+            g.plan = plan
+            g.slot = self._slot_of(sat.time)
+            g.time = sat.time
+            if plan is None or plan.n_cells == 0:
+                continue
+            self.granules.append(g)
+            kept += 1
+        self._tables = None
+        self._buf = None
+        return kept
+
     def refresh_inputs(self):
         """Host -> device copy of every granule's reader arrays (the per-step
         upload of the end-to-end measurement).  Returns the bytes copied."""

@@ -506,16 +506,19 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
         return [granule_plan(lons[i], lats[i], gplan, radius, lonlat_dev=lonlat_dev[i], cache=False)
                 for i in range(n)]
     workers = max(1, min(n, workers or os.cpu_count() or 1))
-    out = []
+    from concurrent.futures import as_completed
+    out = [None] * n
     with ThreadPoolExecutor(workers) as ex:
-        # map() yields in order as results arrive: the device part of granule i runs
-        # while the triangulations of the later granules are still on the pool
-        for i, (tri, ties) in enumerate(ex.map(lambda i: native_delaunay(lons[i], lats[i]),
-                                               range(n))):
+        # the device part of a granule runs as soon as ITS triangulation is done,
+        # while the others are still on the pool
+        futures = {ex.submit(native_delaunay, lons[i], lats[i]): i for i in range(n)}
+        for fut in as_completed(futures):
+            i = futures[fut]
+            tri, ties = fut.result()
             if tri is None:
-                out.append(None)
-            elif ties == 0 or _plan_mode() == "v1":
-                out.append(_plan_v1_device(tri, lonlat_dev[i], gplan, keeps[i]))
+                continue
+            if ties == 0 or _plan_mode() == "v1":
+                out[i] = _plan_v1_device(tri, lonlat_dev[i], gplan, keeps[i])
             else:
-                out.append(_plan_v0(lons[i], lats[i], gplan, _dev.to_host(keeps[i]).astype(bool)))
+                out[i] = _plan_v0(lons[i], lats[i], gplan, _dev.to_host(keeps[i]).astype(bool))
     return out
