@@ -45,12 +45,25 @@ CASES = {
     # reader.py:698-700; :28-33 type 4: TEMPO, reader.py:528-530) on the same kind of data
     "tropomi_nearest": ("TROPOMI_NO2", 0.10, 0.5, (12,), 420, 120, 2),
     "omi_kdtree": ("OMI_HCHO", 0.25, 0.0, (13, 14), 200, 60, 4),
+    # a model FINER than the working mesh (HiGMI / CMAQ / FREE, amf_recal.py:58-83): the
+    # gridded granule stays on the mesh (ctm_upscaled_needed) and amf_recal brings the model's
+    # pressure and partial column to it with _upscaler, level by level
+    "omi_no2_fine_model": ("OMI_NO2", 0.25, 0.0, (15, 16), 200, 60, 1),
 }
+REGION_FINE = (36.0, 46.0, -98.0, -84.0)
+FINE_MODEL_SPACING = {"omi_no2_fine_model": 0.125}   # degrees, both directions
 
 
 def amf_case(name):
     product, gs, thr, seeds, nt, nxt = CASES[name][:6]
     kind = CASES[name][6] if len(CASES[name]) > 6 else 1
+    if name in FINE_MODEL_SPACING:
+        d = FINE_MODEL_SPACING[name]
+        c = synth.ctm_coordinates(REGION_FINE, dlat=d, dlon=d)
+        model = [synth.make_ctm(17, c, averaged=True)]
+        return dict(product=product, grid_size=gs, flag_thresh=thr, kind=kind,
+                    granules=amf_granules(product, seeds, nt, nxt, region=REGION_FINE), coords=c,
+                    ctm=model, sensor=product.split("_")[0], gas=product.split("_")[1])
     return dict(product=product, grid_size=gs, flag_thresh=thr, kind=kind,
                 granules=amf_granules(product, seeds, nt, nxt), coords=coords(), ctm=ctm(),
                 sensor=product.split("_")[0], gas=product.split("_")[1])

@@ -27,7 +27,7 @@ def run_pipeline(name):
     return pipe, res
 
 
-@pytest.mark.parametrize("name", list(cases.CASES))
+@pytest.mark.parametrize("name", [n for n in cases.CASES if n not in cases.FINE_MODEL_SPACING])
 def test_fused_pipeline_matches_oracle_chain(name, golden):
     pipe, res = run_pipeline(name)
     want, _ = chains.amf_chain(chains.oracle_impl(), name)
