@@ -134,6 +134,43 @@ int oisat_plan_fill_nearest(const int32_t* cells, int64_t n_cells, const int32_t
                             int32_t nwin, const int32_t* node_px, int32_t pair_major,
                             int32_t* vert, double* w, void* stream);
 
+/* ---- K7: reader front-end (reader.py:807-903 OMI NO2, :906-983 OMI
+ * HCHO, :707-804 TROPOMI NO2): file variables -> the arrays `interpolator` receives.
+ * All bit-exact with the numpy expressions of the readers (promotion rules included).
+ *
+ * out[i] = float16(((src[i] * f0) * f1) * f2), products in src's dtype (float32 or
+ * float64); n_factors = 0 is a plain cast (any float dtype or int32).  h_factors: HOST. */
+int oisat_reader_scale_f16(const void* src, int32_t dtype, int64_t n, const double* h_factors,
+                           int32_t n_factors, void* out, void* stream);
+
+/* quality_flag (float64).  mode 0, OMI NO2 (reader.py:849-870): -100 when bits 0 and 1 of
+ * the flag are both set, else 1; times float16(cloud) < float16(0.3); times
+ * float16(terrain) < float16(0.2).  mode 1, OMI HCHO (:939-949): (flag == 0) *
+ * (float16(cloud) < float16(0.4)); terrain unused. */
+int oisat_reader_quality(int32_t mode, const void* flags, int32_t flags_dtype, const void* cloud,
+                         int32_t cloud_dtype, const void* terrain, int32_t terrain_dtype, int64_t n,
+                         double* quality_flag, void* stream);
+
+/* scattering weights as float16 [n_lev][n_px]: cast, optional per-pixel factor (TROPOMI:
+ * averaging kernel x total AMF, product in the factor's dtype, :773-774), then NaN / inf /
+ * > 100 / < 0 -> 0 (:887-888).  pixel_major: src is [n_px][n_lev] (OMI NO2, TROPOMI files). */
+int oisat_reader_weights(const void* src, int32_t dtype, int32_t pixel_major, int32_t n_lev,
+                         int64_t n_px, const void* scale, int32_t scale_dtype, void* out,
+                         void* stream);
+
+/* mid-level pressures as float16 [n_lev][n_px].  mode 0: out[l][.] = a[l] (OMI NO2's fixed
+ * levels).  mode 1 (OMI HCHO, :965-966): x = float16(ps); 0.5*((a[l]+b[l]x)+(a[l+1]+b[l+1]x)).
+ * mode 2 (TROPOMI, :763,772-773): x = float32(ps)/float32(ps_div);
+ * 0.5*(((a[l]+b[l]x)+a[l+1])+b[l+1]x) in float64; mode 3: the same expression in float32
+ * (files that store the tm5 coefficients as float32).  a, b: n_lev+1 float64 on the device. */
+int oisat_reader_pmid(int32_t mode, const double* a, const double* b, const void* ps,
+                      int32_t ps_dtype, double ps_div, int32_t n_lev, int64_t n_px, void* out,
+                      void* stream);
+
+/* tropopause[p] = p_mid[layer[p]][p] when 0 < layer[p] < n_lev, else NaN (:781-789) */
+int oisat_reader_tropopause(const int32_t* layer, const void* p_mid, int32_t n_lev, int64_t n_px,
+                            void* out, void* stream);
+
 /* good[p] = (quality_flag[p] > thresh)  (interpolator.py:126-128) */
 int oisat_quality_mask(const void* qflag, int32_t dtype, int64_t n_px, double thresh,
                        uint8_t* good, void* stream);

@@ -129,12 +129,47 @@ def gosat_chain(ref):
     return store
 
 
+READER_CALLS = [("omi_no2", (True,)), ("omi_no2", (False,)), ("omi_hcho", ()),
+                ("tropomi_no2", (True,)), ("tropomi_no2", (False,))]
+READER_FIELDS = ("vcd", "amf", "tropopause", "latitude_center", "longitude_center", "uncertainty",
+                 "quality_flag", "pressure_mid", "scattering_weights")
+
+
+def reader_chain(ref, product):
+    """Outputs of the reference's own reader functions (reader.py:707-983) with their file
+    access (`_read_group_nc`) answered from cases.reader_vars()."""
+    rd = sys.modules["oisatgmi.reader"]
+    fn = {"omi_no2": rd.omi_reader_no2, "omi_hcho": rd.omi_reader_hcho,
+          "tropomi_no2": rd.tropomi_reader_no2}[product]
+    v = cases.reader_vars(product)
+    saved = rd._read_group_nc
+    rd._read_group_nc = lambda fname, group, var: np.squeeze(np.array(v[var]))
+    store = {}
+    try:
+        for prod, args in READER_CALLS:
+            if prod != product:
+                continue
+            r = quiet(fn, "dir/granule.nc", None, True) if product == "omi_hcho" else \
+                quiet(fn, "dir/granule.nc", args[0], None, True)
+            tag = "trop%d" % int(args[0]) if args else "all"
+            store[tag + ".time"] = np.array(r.time.isoformat())
+            for n in READER_FIELDS:
+                a = np.asarray(getattr(r, n))
+                if a.size > 1:
+                    store["%s.%s" % (tag, n)] = a
+    finally:
+        rd._read_group_nc = saved
+    return store
+
+
 def main():
     ref = ref_shim.load_reference()
     os.makedirs(GOLDEN, exist_ok=True)
     jobs = {name: (lambda n=name: amf_chain(ref, n)) for name in cases.CASES}
     jobs["mopitt_co"] = lambda: mopitt_chain(ref)
     jobs["gosat_xch4"] = lambda: gosat_chain(ref)
+    for product in cases.READER_PRODUCTS:
+        jobs["reader_" + product] = lambda p=product: reader_chain(ref, p)
     only = sys.argv[1:]
     for name, job in jobs.items():
         if only and name not in only:

@@ -100,3 +100,79 @@ def subset_levels(a):
     if a.ndim == 3:
         return a[list(LEVEL_SUBSET)]
     return a
+
+
+# ---------------------------------------------------------------- reader front-end
+READER_PRODUCTS = ("omi_no2", "omi_hcho", "tropomi_no2")
+
+
+def reader_vars(product, seed=3, nt=90, nxt=24):
+    """File variables of one level-2 granule as `_read_group_nc` (reader.py:51-67) hands
+    them to the readers: names, shapes and dtypes of the real products, synthetic values
+    with the awkward ones included (fill values, negative / huge / NaN scattering weights,
+    cloud fractions exactly on the float16 image of the threshold, every flag pattern)."""
+    rng = np.random.default_rng(seed)
+    geo = synth.regional_geo(REGION)
+    lat, lon = synth.swath_geolocation(nt, nxt, rng=rng, **geo)
+    shape = (nt, nxt)
+
+    def f32(a):
+        return np.asarray(a, dtype=np.float32)
+
+    def weights(L, pixel_major):
+        sw = rng.uniform(0.05, 3.0, shape + (L,)) if pixel_major else rng.uniform(0.05, 3.0, (L,) + shape)
+        bad = rng.uniform(size=sw.shape)
+        sw[bad < 0.01] = np.nan
+        sw[(bad >= 0.01) & (bad < 0.02)] = -0.3
+        sw[(bad >= 0.02) & (bad < 0.03)] = 250.0
+        sw[(bad >= 0.03) & (bad < 0.035)] = np.inf
+        sw[(bad >= 0.035) & (bad < 0.04)] = 1e6       # overflows float16 -> inf
+        return f32(sw)
+
+    cloud = rng.uniform(0.0, 1.0, shape)
+    cloud[0, :4] = [0.3, np.float16(0.3), 0.4, np.float16(0.4)]   # threshold images
+    cloud[1, :2] = [0.2998046875, 0.39990234375]
+    if product == "omi_no2":
+        v = {"Time": np.full(nt, 3.91e8) + np.arange(nt) * 2.0,
+             "Latitude": lat.astype(np.float32), "Longitude": lon.astype(np.float32),
+             "CloudFraction": f32(cloud),
+             "TerrainReflectivity": f32(rng.uniform(0.0, 0.4, shape)),
+             "VcdQualityFlags": rng.integers(0, 16, shape).astype(np.int16),
+             "ScatteringWeightPressure": f32(synth.OMI_NO2_PRESSURES),
+             "ScatteringWeight": weights(35, True),
+             "TropopausePressure": f32(rng.uniform(90.0, 320.0, shape))}
+        for sfx in ("", "Trop"):
+            col = np.exp(rng.normal(35.0, 1.0, shape))
+            col[rng.uniform(size=shape) < 0.02] = -1.2676506e30        # the product's fill value
+            v["ColumnAmountNO2" + sfx] = f32(col)
+            v["ColumnAmountNO2" + sfx + "Std"] = f32(np.exp(rng.normal(33.5, 0.5, shape)))
+            v["Amf" + sfx] = f32(rng.uniform(0.4, 2.5, shape))
+        return v
+    if product == "omi_hcho":
+        return {"time": np.full(nt, 3.92e8) + np.arange(nt) * 2.0,
+                "latitude": lat.astype(np.float32), "longitude": lon.astype(np.float32),
+                "column_amount": np.exp(rng.normal(36.0, 1.0, shape)),           # float64 in the file
+                "column_uncertainty": np.exp(rng.normal(35.0, 0.5, shape)),
+                "amf": f32(rng.uniform(0.4, 2.5, shape)),
+                "cloud_fraction": f32(cloud),
+                "main_data_quality_flag": rng.integers(0, 3, shape).astype(np.int8),
+                "surface_pressure": f32(rng.uniform(600.0, 1030.0, shape)),
+                "scattering_weights": weights(47, False)}
+    if product == "tropomi_no2":
+        a, b = synth._hybrid_table(35)
+        v = {"time": np.float64(1.7e8), "delta_time": (np.arange(nt) * 840).astype(np.int64)[:, None]
+             * np.ones((1, 1), np.int64),
+             "latitude": lat.astype(np.float32), "longitude": lon.astype(np.float32),
+             "air_mass_factor_total": f32(rng.uniform(0.8, 3.0, shape)),
+             "air_mass_factor_troposphere": f32(rng.uniform(0.4, 2.5, shape)),
+             "qa_value": f32(rng.integers(0, 101, shape) / 100.0),
+             "tm5_constant_a": f32(np.stack([a[:-1], a[1:]], axis=1) * 100.0),
+             "tm5_constant_b": f32(np.stack([b[:-1], b[1:]], axis=1)),
+             "surface_pressure": f32(rng.uniform(60000.0, 103000.0, shape)),
+             "averaging_kernel": weights(34, True),
+             "tm5_tropopause_layer_index": rng.integers(-1, 36, shape).astype(np.int32)}
+        for name in ("nitrogendioxide_total_column", "nitrogendioxide_tropospheric_column"):
+            v[name] = f32(np.exp(rng.normal(-9.5, 1.0, shape)))               # mol m-2
+            v[name + "_precision"] = f32(np.exp(rng.normal(-11.0, 0.5, shape)))
+        return v
+    raise KeyError(product)

@@ -106,3 +106,36 @@ def cuda_impl():
         amf_recal=amf_recal.amf_recal, ak_conv_mopitt=ak_conv_mopitt.ak_conv_mopitt,
         ak_conv_gosat=ak_conv_gosat.ak_conv_gosat, averaging=averaging.averaging,
         OI=optimal_interpolation.OI, bias=driver.BIAS_CORRECTION)
+
+
+READER_CALLS = [("omi_no2", (True,)), ("omi_no2", (False,)), ("omi_hcho", ()),
+                ("tropomi_no2", (True,)), ("tropomi_no2", (False,))]
+READER_FIELDS = ("vcd", "amf", "tropopause", "latitude_center", "longitude_center", "uncertainty",
+                 "quality_flag", "pressure_mid", "scattering_weights")
+
+
+def reader_chain(module, product):
+    """Reader front-end of one product through `module` (oracle.reader or
+    oisatgmi_b200.reader_frontend): same keys as oracle/make_golden.py's reader_chain.
+    Arrays keep their dtypes: the comparison is bit for bit."""
+    v = cases.reader_vars(product)
+    store = {}
+    for prod, args in READER_CALLS:
+        if prod != product:
+            continue
+        r = getattr(module, product)(v, *args)
+        tag = "trop%d" % int(args[0]) if args else "all"
+        store[tag + ".time"] = np.array(r.time.isoformat())
+        for n in READER_FIELDS:
+            a = np.asarray(getattr(r, n))
+            if a.size > 1:
+                store["%s.%s" % (tag, n)] = a
+    return store
+
+
+def same_bits(store, gold):
+    assert set(store) == set(gold), sorted(set(store) ^ set(gold))
+    for k, a in store.items():
+        b = gold[k]
+        assert a.dtype == b.dtype and a.shape == b.shape, (k, a.dtype, b.dtype, a.shape, b.shape)
+        assert np.array_equal(a, b, equal_nan=(a.dtype.kind == "f")), k

@@ -49,3 +49,9 @@ def test_inputs_did_not_drift(golden):
                 if isinstance(v, np.ndarray):
                     h.update(np.ascontiguousarray(v).tobytes())
         assert h.hexdigest() == str(golden(name)["input_sha256"]), name
+
+
+@pytest.mark.parametrize("product", cases.READER_PRODUCTS)
+def test_reader_front_end_matches_reference_fixture(product, golden):
+    from oracle import reader as oreader
+    chains.same_bits(chains.reader_chain(oreader, product), golden("reader_" + product))

@@ -232,3 +232,15 @@ def test_gpu_plan_builder_equals_host_plan(name, monkeypatch):
         w0 = np.take_along_axis(p0.w.reshape(S // 3, 3, n), o0, axis=1)
         w1 = np.take_along_axis(p1.w.reshape(S // 3, 3, n), o1, axis=1)
         assert np.max(np.abs(w0 - w1)) < 1e-12
+
+
+@pytest.mark.parametrize("product", cases.READER_PRODUCTS)
+def test_reader_front_end_is_bit_exact(product, golden):
+    """K7 (reader.py:707-983 between the file reads and the interpolator call) against the
+    oracle and against the fixture the reference's own reader functions produced: same
+    dtypes, same bits -- float16 roundings, flag decoding, -0.0 and NaN patterns included."""
+    from oisatgmi_b200 import reader_frontend
+    from oracle import reader as oreader
+    got = chains.reader_chain(reader_frontend, product)
+    chains.same_bits(got, chains.reader_chain(oreader, product))
+    chains.same_bits(got, golden("reader_" + product))
