@@ -217,7 +217,7 @@ def reference_arm(args):
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": "px/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------- B200 arm
@@ -434,8 +434,27 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks,
     }
-    print(json.dumps(line))
+    emit(line)
 
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's
+    version banner, for one): everything written to file descriptor 1 while the
+    benchmark runs goes to stderr instead, and emit() writes the line to the real
+    stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 if __name__ == "__main__":
+    _REAL_STDOUT = _quiet_stdout()
     main()
