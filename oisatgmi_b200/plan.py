@@ -505,7 +505,11 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
     if not gplan.upscale or _plan_mode() == "v0":
         return [granule_plan(lons[i], lats[i], gplan, radius, lonlat_dev=lonlat_dev[i], cache=False)
                 for i in range(n)]
-    workers = max(1, min(n, workers or os.cpu_count() or 1))
+    if workers is None:
+        # one process per GPU: the ranks of a node share its cores
+        local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+        workers = max(1, (os.cpu_count() or 1) // local)
+    workers = max(1, min(n, workers))
     from concurrent.futures import as_completed
     out = [None] * n
     with ThreadPoolExecutor(workers) as ex:
