@@ -287,6 +287,15 @@ int oisat_oi_apply(const double* xa, const double* y, const double* Sa, const do
                    int64_t n, double factor, double* xb, double* ak, double* inc, double* err,
                    void* stream);
 
+/* ---- K8: the data side of driver.write_to_nc (driver.py:156-227) ------------------
+ * out: float32 [9][n] in the order the reference stores its variables: sat_averaged_vcd,
+ * ctm_averaged_vcd_prior, ctm_averaged_vcd_posterior, sat_averaged_error, ak_OI, error_OI,
+ * scaling_factor (= posterior / prior in float64, NaN / inf / 0 -> 1, :203-206), aux1, aux2. */
+int oisat_output_fields(int64_t n, const double* sat_vcd, const double* ctm_prior,
+                        const double* ctm_posterior, const double* sat_error, const double* ak,
+                        const double* error_oi, const double* aux1, const double* aux2, float* out,
+                        void* stream);
+
 /* ---- fused month pipeline for float16 `satellite_amf` products ----------------
  * (OMI NO2/HCHO, TROPOMI NO2: the BASELINE configurations)
  *

@@ -82,3 +82,52 @@ class oisatgmi(object):
         (self.ctm_averaged_vcd_corrected, self.ak_OI, self.increment_OI, self.error_OI) = OI(
             xa, y, (xa * error_ctm / 100.0) ** 2, self.sat_averaged_error ** 2,
             regularization_on=True)
+
+    OUTPUT_NAMES = ("sat_averaged_vcd", "ctm_averaged_vcd_prior", "ctm_averaged_vcd_posterior",
+                    "sat_averaged_error", "ak_OI", "error_OI", "scaling_factor", "aux1", "aux2")
+
+    def output_fields(self):
+        """The float32 variables driver.write_to_nc stores (driver.py:180-222), made on
+        the GPU in one pass (K8): name -> float32 array, plus lon/lat of the first
+        granule and the time string, as the reference writes them."""
+        import numpy as np
+        from . import _dev, _lib
+        _dev.require_cuda()
+        shape = np.shape(self.sat_averaged_vcd)
+        src = [self.sat_averaged_vcd, self.ctm_averaged_vcd, self.ctm_averaged_vcd_corrected,
+               self.sat_averaged_error, self.ak_OI, self.error_OI, self.aux1, self.aux2]
+        dev = [_dev.to_device(np.ascontiguousarray(a, dtype=np.float64).ravel()) for a in src]
+        n = dev[0].numel()
+        out = _dev.empty((9, n), "float32")
+        _lib.check(_lib.lib().oisat_output_fields(n, *[d.data_ptr() for d in dev], out.data_ptr(),
+                                                  _dev.stream()))
+        host = _dev.to_host(out)
+        fields = {name: host[k].reshape(shape) for k, name in enumerate(self.OUTPUT_NAMES)}
+        first = next(s for s in self.reader_obj.sat_data if s is not None)
+        fields["lon"] = np.asarray(first.longitude_center).astype(np.float32)
+        fields["lat"] = np.asarray(first.latitude_center).astype(np.float32)
+        fields["time"] = self.avg_time.strftime("%Y-%m-%d %H:%M:%S")
+        return fields
+
+    def write_to_nc(self, output_file, output_folder='diag'):
+        """driver.py:156-227.  The NetCDF container is file I/O (netCDF4, the reference's
+        dependency, outside this package): written when that module is importable."""
+        import os
+        import numpy as np
+        try:
+            from netCDF4 import Dataset
+        except Exception as exc:
+            raise RuntimeError("write_to_nc needs the netCDF4 package; output_fields() returns "
+                               "the variables it would store") from exc
+        fields = self.output_fields()
+        os.makedirs(output_folder, exist_ok=True)
+        nc = Dataset(output_folder + '/' + output_file + '.nc', 'w')
+        nx, ny = np.shape(fields["sat_averaged_vcd"])
+        nc.createDimension('x', nx)
+        nc.createDimension('y', ny)
+        nc.createDimension('t', None)
+        nc.createVariable('time', 'S1', ('t'))[:] = np.array(list(fields["time"]), 'S1')
+        order = self.OUTPUT_NAMES[:7] + ("lon", "lat") + self.OUTPUT_NAMES[7:]
+        for name in order:
+            nc.createVariable(name, 'f', ('x', 'y'))[:, :] = fields[name]
+        nc.close()

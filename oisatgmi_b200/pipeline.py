@@ -432,5 +432,19 @@ class MonthPipeline:
             out[k] = _dev.to_host(v).reshape(shape) if hasattr(v, "data_ptr") else v
         return out
 
+    def output_fields(self, res):
+        """The nine float32 variables driver.write_to_nc stores (driver.py:180-222), from the
+        device results of run(): one K8 launch and one float32 device -> host copy."""
+        from .driver import oisatgmi
+        n = self.n_cell
+        out = _dev.empty((9, n), "float32")
+        keys = ("sat_averaged_vcd", "ctm_averaged_vcd", "ctm_averaged_vcd_corrected",
+                "sat_averaged_error", "ak_OI", "error_OI", "aux1", "aux2")
+        _lib.check(_lib.lib().oisat_output_fields(n, *[res[k].data_ptr() for k in keys],
+                                                  out.data_ptr(), _dev.stream()))
+        host = _dev.to_host(out)
+        shape = self.gplan.out_shape
+        return {name: host[k].reshape(shape) for k, name in enumerate(oisatgmi.OUTPUT_NAMES)}
+
     def n_pixels(self):
         return int(sum(g.n_px for g in self.granules))

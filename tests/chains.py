@@ -139,3 +139,23 @@ def same_bits(store, gold):
         b = gold[k]
         assert a.dtype == b.dtype and a.shape == b.shape, (k, a.dtype, b.dtype, a.shape, b.shape)
         assert np.array_equal(a, b, equal_nan=(a.dtype.kind == "f")), k
+
+
+def month_object(impl, name="omi_no2"):
+    """Attributes `driver.oisatgmi` holds after average() -> bias_correct() -> oi(), from
+    the amf chain of `impl` (used for the write_to_nc data side, driver.py:156-227)."""
+    import datetime
+    import types
+    store, grids = amf_chain(impl, name)
+    o = types.SimpleNamespace(
+        sat_averaged_vcd=store["oi.y"], sat_averaged_error=store["avg.sat_err"],
+        ctm_averaged_vcd=store["avg.ctm_vcd"].copy(), aux1=store["avg.aux1"], aux2=store["avg.aux2"],
+        ctm_averaged_vcd_corrected=store["oi.ctm_averaged_vcd_corrected"], ak_OI=store["oi.ak_OI"],
+        increment_OI=store["oi.increment_OI"], error_OI=store["oi.error_OI"],
+        avg_time=datetime.datetime(2005, 6, 16, 12, 0, 0),
+        reader_obj=types.SimpleNamespace(sat_data=[None] + list(grids)))
+    # the cases the clean-up of the scaling factor exists for (driver.py:204-206)
+    o.ctm_averaged_vcd[0, :4] = [0.0, np.nan, np.inf, 1.0]
+    o.ctm_averaged_vcd_corrected = o.ctm_averaged_vcd_corrected.copy()
+    o.ctm_averaged_vcd_corrected[0, :4] = [1.0, 2.0, 3.0, 0.0]
+    return o

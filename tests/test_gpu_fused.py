@@ -98,3 +98,27 @@ def test_pack_roundtrip():
     for r in range(rows.shape[0]):
         slot = (r % nchunk) * 8 + r // nchunk
         assert np.array_equal(rec[:, slot], rows[r], equal_nan=True), r
+
+
+def test_pipeline_output_fields_match_float32_casts():
+    """MonthPipeline.output_fields (K8) == what driver.write_to_nc would store from the
+    pipeline's float64 results (driver.py:180-222)."""
+    from oisatgmi_b200.pipeline import MonthPipeline
+    c = cases.amf_case("omi_hcho")
+    pipe = MonthPipeline(c["ctm"], c["grid_size"], c["flag_thresh"], sensor=c["sensor"],
+                         gas=c["gas"], error_ctm=50.0)
+    for g in c["granules"]:
+        assert pipe.add_granule(cases.clone(g))
+    dev = pipe.run()
+    f32 = pipe.output_fields(dev)
+    f64 = pipe.results_to_host(dev)
+    pairs = {"sat_averaged_vcd": "sat_averaged_vcd", "ctm_averaged_vcd_prior": "ctm_averaged_vcd",
+             "ctm_averaged_vcd_posterior": "ctm_averaged_vcd_corrected",
+             "sat_averaged_error": "sat_averaged_error", "ak_OI": "ak_OI", "error_OI": "error_OI",
+             "aux1": "aux1", "aux2": "aux2"}
+    for name, src in pairs.items():
+        assert np.array_equal(f32[name], f64[src].astype(np.float32), equal_nan=True), name
+    with np.errstate(all="ignore"):
+        s = f64["ctm_averaged_vcd_corrected"] / f64["ctm_averaged_vcd"]
+    s[np.isnan(s) | np.isinf(s) | (s == 0.0)] = 1.0
+    assert np.array_equal(f32["scaling_factor"], s.astype(np.float32))

@@ -244,3 +244,23 @@ def test_reader_front_end_is_bit_exact(product, golden):
     got = chains.reader_chain(reader_frontend, product)
     chains.same_bits(got, chains.reader_chain(oreader, product))
     chains.same_bits(got, golden("reader_" + product))
+
+
+def test_output_fields_are_bit_exact():
+    """K8 (the data side of driver.write_to_nc, driver.py:156-227) against the oracle:
+    float32 casts and the cleaned scaling factor, bit for bit, on the CUDA chain's month."""
+    from oisatgmi_b200 import driver
+    from oracle import output as ooutput
+    obj = chains.month_object(chains.cuda_impl())
+    d = driver.oisatgmi()
+    d.__dict__.update(obj.__dict__)
+    got = d.output_fields()
+    want = ooutput.output_fields(obj)
+    assert set(got) == set(want)
+    for k, a in want.items():
+        if k == "time":
+            assert got[k] == a
+        else:
+            assert got[k].dtype == np.float32 and np.array_equal(got[k], a, equal_nan=True), k
+    s = got["scaling_factor"]
+    assert np.all(s[0, :4] == 1.0)          # x/0, x/NaN, x/inf and 0/x all become 1

@@ -115,3 +115,52 @@ def test_reader_front_end_is_bit_identical_to_reference(product, args):
         if b.size > 1:
             assert a.dtype == b.dtype and a.shape == b.shape, n
             assert np.array_equal(a, b, equal_nan=True), n
+
+
+def test_output_fields_are_bit_identical_to_write_to_nc(tmp_path):
+    """driver.write_to_nc (driver.py:156-227), unmodified, writing into a recording
+    stand-in for netCDF4.Dataset: every stored array equals oracle.output's."""
+    import sys
+    from oracle import output as ooutput
+    ref_shim.load_reference()
+    drv = sys.modules["oisatgmi.driver"]
+    stored = {}
+
+    class Var:
+        def __init__(self, name, kind):
+            self.name, self.kind = name, kind
+
+        def __setitem__(self, key, value):
+            a = np.asarray(value)
+            stored[self.name] = a.astype(np.float32) if self.kind == "f" else a
+
+    class RecordingDataset:
+        def __init__(self, path, mode):
+            pass
+
+        def createDimension(self, *a):
+            pass
+
+        def createVariable(self, name, kind, dims):
+            return Var(name, kind)
+
+        def close(self):
+            pass
+
+    obj = chains.month_object(chains.oracle_impl())
+    ref_obj = drv.oisatgmi()
+    ref_obj.__dict__.update(obj.__dict__)
+    saved = drv.Dataset
+    drv.Dataset = RecordingDataset
+    try:
+        ref_obj.write_to_nc("month", output_folder=str(tmp_path))
+    finally:
+        drv.Dataset = saved
+    got = ooutput.output_fields(obj)
+    assert set(stored) == set(got)
+    for k, a in stored.items():
+        if k == "time":
+            assert b"".join(a.tolist()).decode() == got[k]
+        else:
+            assert a.dtype == got[k].dtype == np.float32
+            assert np.array_equal(a, got[k], equal_nan=True), k
