@@ -229,47 +229,60 @@ __device__ __noinline__ double amf_slow_path(const RowView& r, int L, int n_ctm,
   return vcd_m != 0.0 ? scd / vcd_m : qnan();
 }
 
-constexpr int kVerticalThreads = 64;   // four 16-pair tiles of the row buffer per block
+constexpr int kQuad = 8;                        // threads per pair (4: 10.6 ms, 8: 10.0, 16: 10.6)
+constexpr int kVerticalThreads = 16 * kQuad;    // one 16-pair tile of the row buffer per block
 
-// The rows of a block's pairs are one contiguous piece of the buffer (4 tiles x
-// nrow_out x 16 doubles, ~48 KB for OMI HCHO): one bulk asynchronous copy brings
-// it into shared memory while the other resident blocks compute.  Before this,
-// every bracket shift of the walk below waited for its own global load -- and a
-// warp shifts whenever ANY of its lanes does, ~150 exposed DRAM round trips per
-// warp (ncu: 60% of the stall samples were long-scoreboard, IPC 0.3).
+// One block = one tile of the row buffer (16 pairs), FOUR threads per pair.
+//
+// The rows of the tile are one contiguous ~12 KB piece of the buffer: one bulk
+// asynchronous copy brings it into shared memory.  (Before the rows were staged,
+// every bracket shift of the walk waited for its own global load -- and a warp
+// shifts whenever ANY of its lanes does, ~150 exposed DRAM round trips per warp.)
+//
+// The walk over the model column is serial in nature (a merge), and with one thread
+// per pair the kernel ran 8 warps per SM waiting on float64 dependency chains (ncu:
+// issue slots 31% busy, 42% of the stalls fixed-latency waits).  So the column is cut
+// into kQuad contiguous pieces: each thread finds its starting bracket with one
+// binary search (the same searchsorted the merge tracks incrementally) and walks its
+// piece; the per-level products go to shared memory and ONE thread per pair adds them
+// in numpy's order (eight running sums, then the tree), so the result does not
+// depend on how the column was cut.  Thread t of pair p is threadIdx.x = 16 t + p: a
+// half warp reads 16 different columns of the tile, each in its own bank pair.
 template <bool HAS_TROP>
 __global__ void __launch_bounds__(kVerticalThreads)
 vertical_rows_kernel(const __grid_constant__ SplitParams P) {
-  extern __shared__ __align__(128) double rows_s[];  // [4][nrow_out][16]
+  extern __shared__ __align__(128) unsigned char vsm[];
   __shared__ LogTable tab;
   __shared__ __align__(8) unsigned long long mbar;
+  __shared__ int unsorted[16];
+  __shared__ double part_a[8 * 16];
+  __shared__ float part_b[8 * 16];
   const oisat_fused_args& A = P.a;
   const int L = A.n_sat_lev, n_ctm = A.n_ctm_lev;
-  const int64_t tile0 = (int64_t)blockIdx.x * (kVerticalThreads / 16);
-  const int64_t n_tiles = (A.n_pairs + 15) >> 4;
-  const int tiles_here = (int)(n_tiles - tile0 < kVerticalThreads / 16 ? n_tiles - tile0
-                                                                       : kVerticalThreads / 16);
+  double* rows_s = reinterpret_cast<double*>(vsm);                 // [nrow_out][16]
+  double* prod_a = rows_s + (size_t)P.nrow_out * 16;               // [n_ctm][16]
+  float* prod_b = reinterpret_cast<float*>(prod_a + (size_t)n_ctm * 16);   // [n_ctm][16]
+  const int p = threadIdx.x & 15, t = threadIdx.x >> 4;
+  const int64_t tile = blockIdx.x;
   const uint32_t tile_bytes = (uint32_t)P.nrow_out * 16u * (uint32_t)sizeof(double);
   const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar);
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                 ::"r"(bar), "r"(tile_bytes * (uint32_t)tiles_here) : "memory");
+                 ::"r"(bar), "r"(tile_bytes) : "memory");
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"((uint32_t)__cvta_generic_to_shared(rows_s)),
-          "l"(P.rows + tile0 * (int64_t)P.nrow_out * 16), "r"(tile_bytes * (uint32_t)tiles_here),
-          "r"(bar)
+          "l"(P.rows + tile * (int64_t)P.nrow_out * 16), "r"(tile_bytes), "r"(bar)
         : "memory");
   }
   for (int i = threadIdx.x; i < 128; i += kVerticalThreads) {
     tab.r[i] = g_log_table.r[i];
     tab.neg_log_r[i] = g_log_table.neg_log_r[i];
   }
+  if (threadIdx.x < 16) unsorted[threadIdx.x] = n_ctm >= 8 ? 0 : 1;
   __syncthreads();  // barrier initialised, table staged
-  const int64_t pair = (int64_t)blockIdx.x * kVerticalThreads + threadIdx.x;
-  if (pair >= A.n_pairs) return;
   {
     uint32_t done = 0;
     while (!done)
@@ -278,63 +291,84 @@ vertical_rows_kernel(const __grid_constant__ SplitParams P) {
                    "  selp.b32 %0, 1, 0, p; }"
                    : "=r"(done) : "r"(bar) : "memory");
   }
-  RowView r{rows_s + (threadIdx.x >> 4) * (P.nrow_out * 16) + (threadIdx.x & 15)};
+  const int64_t pair = tile * 16 + p;
+  const bool live = pair < A.n_pairs;
+  RowView r{rows_s + p};
   const double vcd = r.at(2 * L);
-  const double old_amf = A.staged[4 * A.n_pairs + pair];
-  double new_amf = qnan(), vnew = qnan(), col = qnan();
-  if (vcd == vcd) {  // amf_recal.py:99-100
-    const double trop = HAS_TROP ? r.at(2 * L + 1) : 0.0;
-    // model column of this pair's cell: consecutive pairs are consecutive cells, so
-    // the 32 lanes of a warp read (mostly) one or two 128-byte lines per level
+  const bool work = live && vcd == vcd;  // amf_recal.py:99-100
+  const double trop = HAS_TROP ? r.at(2 * L + 1) : 0.0;
+  // scipy sorts the levels ascending in log p: xs[j], j = 0..L-1; for a monotone
+  // profile that is the storage order or its reverse.
+  const bool descending = r.at(L) > r.at(2 * L - 1);
+  auto row_of = [&](int j) { return descending ? L - 1 - j : j; };
+  auto xs = [&](int j) { return r.at(L + row_of(j)); };
+  __syncthreads();  // every thread has read the pressures it needs before they turn into logs
+  // Phase A: p -> log p in place, level j by thread j mod kQuad
+  if (work)
+    for (int j = t; j < L; j += kQuad) {
+      const int row = L + row_of(j);
+      r.set(row, table_log(r.at(row), &tab));
+    }
+  __syncthreads();
+  // strict monotonicity of every level; ties and NaNs take scipy's argsort path
+  if (work) {
+    bool bad = false;
+    for (int j = t; j < L; j += kQuad) {
+      const double x = xs(j);
+      const double prev = j > 0 ? xs(j - 1) : -CUDART_INF;
+      bad = bad || !(prev < x);
+    }
+    if (bad) unsorted[p] = 1;
+  }
+  __syncthreads();
+  const bool sorted = unsorted[p] == 0;
+  // model column of this pair's cell: consecutive pairs are consecutive cells, so a
+  // half warp reads (mostly) one 64-byte piece of a line per level
+  const float* lp = A.ctm_logp;
+  const float* pc = A.ctm_pcol;
+  const float* pm = A.ctm_pmid;
+  const int64_t stride = A.n_cell;
+  if (work) {
     const int64_t off = (int64_t)A.gran_slot[A.pair_granule[pair]] * n_ctm * A.n_cell +
                         A.pair_cell[pair];
-    const float* lp = A.ctm_logp + off;
-    const float* pc = A.ctm_pcol + off;
-    const float* pm = HAS_TROP ? A.ctm_pmid + off : lp;
-    const int64_t stride = A.n_cell;
-    // scipy sorts the levels ascending in log p: xs[j], j = 0..L-1; for a monotone
-    // profile that is the storage order or its reverse.
-    const bool descending = r.at(L) > r.at(2 * L - 1);
-    auto row_of = [&](int j) { return descending ? L - 1 - j : j; };
-    // Phase A, the same instruction stream for every lane: p -> log p, in place in
-    // this thread's own column of the staged rows (sorted order is the storage
-    // order or its reverse).  Strict monotonicity is checked for every level; ties
-    // and NaNs take scipy's argsort path (slow path).
-    bool sorted = n_ctm >= 8;
+    lp += off;
+    pc += off;
+    pm = HAS_TROP ? pm + off : lp;
+  }
+  // Phase B: interp1d(xs, SW)(log p_model) over this thread's piece of the column.
+  // Model levels run from the surface up, so the query only decreases and so does
+  // idx = searchsorted(xs, v, 'left'); the bracket [c-1, c], c = clip(idx, 1, L-1),
+  // lives in registers and only ever moves one way.
+  const int per = (n_ctm + kQuad - 1) / kQuad;
+  const int k_begin = t * per, k_end = (t + 1) * per < n_ctm ? (t + 1) * per : n_ctm;
+  if (work && sorted && k_begin < k_end) {
+    int idx = 0;
     {
-      double prev = -CUDART_INF;
-#pragma unroll 4
-      for (int j = 0; j < L; ++j) {
-        const int row = L + row_of(j);
-        const double x = table_log(r.at(row), &tab);
-        r.set(row, x);
-        sorted = sorted && (prev < x);
-        prev = x;
+      const double v0 = (double)__ldg(lp + (int64_t)k_begin * stride);
+      for (int step = 1 << (31 - __clz(L)); step >= 1; step >>= 1) {
+        const int tt = idx + step;
+        const int probe = (tt <= L ? tt : L) - 1;
+        idx = (tt <= L && xs(probe) < v0) ? tt : idx;
       }
     }
-    // Phase B: interp1d(xs, SW)(log p_model) as a merge: model levels run from the
-    // surface up, so the query only decreases and so does idx = searchsorted(xs, v,
-    // 'left').  The bracket [c-1, c], c = clip(idx, 1, L-1), lives in registers.
-    int idx = L, c = L - 1;
-    double x_hi = r.at(L + row_of(c)), x_lo = r.at(L + row_of(c - 1));
+    int c = idx < 1 ? 1 : (idx > L - 1 ? L - 1 : idx);
+    double x_hi = xs(c), x_lo = xs(c - 1);
     double y_hi = r.at(row_of(c)), y_lo = r.at(row_of(c - 1));
     double rden = 1.0 / (x_hi - x_lo);
-    double qa[8], colsum = 0.0, scd = 0.0;
-    float qb[8];
-    const int body = n_ctm - (n_ctm % 8);
-    for (int k0 = 0; k0 < n_ctm && sorted; k0 += 8) {
-      float lpv[8], pcv8[8], pmv[8];
+    constexpr int kBatch = 6;
+    for (int k0 = k_begin; k0 < k_end; k0 += kBatch) {
+      float lpv[kBatch], pcv8[kBatch], pmv[kBatch];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {  // eight levels of the model column in flight at once
-        const int k = k0 + j < n_ctm ? k0 + j : n_ctm - 1;
+      for (int j = 0; j < kBatch; ++j) {  // several levels of the model column in flight at once
+        const int k = k0 + j < k_end ? k0 + j : k_end - 1;
         lpv[j] = __ldg(lp + (int64_t)k * stride);
         pcv8[j] = __ldg(pc + (int64_t)k * stride);
         pmv[j] = HAS_TROP ? __ldg(pm + (int64_t)k * stride) : 0.0f;
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < kBatch; ++j) {
         const int k = k0 + j;
-        if (k < n_ctm) {
+        if (k < k_end) {
           const double v = (double)lpv[j];
           double pcv = (double)pcv8[j];
           while (idx > 0) {
@@ -346,7 +380,7 @@ vertical_rows_kernel(const __grid_constant__ SplitParams P) {
               c = nc;
               x_hi = x_lo;
               y_hi = y_lo;
-              x_lo = r.at(L + row_of(c - 1));
+              x_lo = xs(c - 1);
               y_lo = r.at(row_of(c - 1));
               rden = 1.0 / (x_hi - x_lo);
             }
@@ -355,29 +389,44 @@ vertical_rows_kernel(const __grid_constant__ SplitParams P) {
           if (isinf(sw)) sw = 0.0;
           if (HAS_TROP && (double)pmv[j] < trop) { sw = qnan(); pcv = qnan(); }
           const double prod = sw * pcv;
-          const double a = prod != prod ? 0.0 : prod;        // nansum
-          const float b = pcv != pcv ? 0.0f : (float)pcv;
-          if (k < body) {                                    // numpy's eight running sums
-            if (k0 == 0) { qa[j] = a; qb[j] = b; }
-            else { qa[j] = qa[j] + a; qb[j] = __fadd_rn(qb[j], b); }
-          } else {                                           // scalar tail after the tree
-            if (k == body) {
-              scd = ((qa[0] + qa[1]) + (qa[2] + qa[3])) + ((qa[4] + qa[5]) + (qa[6] + qa[7]));
-              colsum = (double)__fadd_rn(__fadd_rn(__fadd_rn(qb[0], qb[1]), __fadd_rn(qb[2], qb[3])),
-                                         __fadd_rn(__fadd_rn(qb[4], qb[5]), __fadd_rn(qb[6], qb[7])));
-            }
-            scd = scd + a;
-            colsum = (double)__fadd_rn((float)colsum, b);
-          }
+          prod_a[k * 16 + p] = prod != prod ? 0.0 : prod;        // nansum terms
+          prod_b[k * 16 + p] = pcv != pcv ? 0.0f : (float)pcv;
         }
       }
     }
-    if (sorted && body == n_ctm) {
-      scd = ((qa[0] + qa[1]) + (qa[2] + qa[3])) + ((qa[4] + qa[5]) + (qa[6] + qa[7]));
-      colsum = (double)__fadd_rn(__fadd_rn(__fadd_rn(qb[0], qb[1]), __fadd_rn(qb[2], qb[3])),
-                                 __fadd_rn(__fadd_rn(qb[4], qb[5]), __fadd_rn(qb[6], qb[7])));
+  }
+  __syncthreads();
+  // Phase C: the terms are added in numpy's order -- eight running sums over k mod 8
+  // (thread t owns sum t), then the fixed tree and the scalar tail by one thread
+  static_assert(kQuad == 8, "phase C maps numpy's eight running sums onto the eight threads");
+  const int body = n_ctm - (n_ctm % 8);
+  if (work && sorted) {
+    double qa = prod_a[t * 16 + p];
+    float qb = prod_b[t * 16 + p];
+    for (int k = t + 8; k < body; k += 8) {
+      qa = qa + prod_a[k * 16 + p];
+      qb = __fadd_rn(qb, prod_b[k * 16 + p]);
     }
+    part_a[t * 16 + p] = qa;
+    part_b[t * 16 + p] = qb;
+  }
+  __syncthreads();
+  if (t != 0 || !live) return;
+  const double old_amf = A.staged[4 * A.n_pairs + pair];
+  double new_amf = qnan(), vnew = qnan(), col = qnan();
+  if (work) {
+    double colsum = 0.0;
     if (sorted) {
+      auto qa = [&](int j) { return part_a[j * 16 + p]; };
+      auto qb = [&](int j) { return part_b[j * 16 + p]; };
+      double scd = ((qa(0) + qa(1)) + (qa(2) + qa(3))) + ((qa(4) + qa(5)) + (qa(6) + qa(7)));
+      float cs = __fadd_rn(__fadd_rn(__fadd_rn(qb(0), qb(1)), __fadd_rn(qb(2), qb(3))),
+                           __fadd_rn(__fadd_rn(qb(4), qb(5)), __fadd_rn(qb(6), qb(7))));
+      for (int k = body; k < n_ctm; ++k) {   // scalar tail after the tree
+        scd = scd + prod_a[k * 16 + p];
+        cs = __fadd_rn(cs, prod_b[k * 16 + p]);
+      }
+      colsum = (double)cs;
       new_amf = colsum != 0.0 ? scd / colsum : qnan();
     } else {
       new_amf = amf_slow_path(r, L, n_ctm, HAS_TROP, trop, lp, pc, pm, stride, &colsum);
@@ -442,8 +491,9 @@ extern "C" int oisat_fused_amf_split(const oisat_fused_args* h_args, double* row
   gather_rows_kernel<<<(unsigned)ceil_div(a.n_pairs * 16, kGatherThreads), kGatherThreads,
                        tile_bytes, s>>>(P);
   OISAT_CHECK_LAUNCH();
-  const size_t stage_bytes = (size_t)(kVerticalThreads / 16) * P.nrow_out * 16 * sizeof(double);
-  const unsigned vblocks = (unsigned)ceil_div(a.n_pairs, kVerticalThreads);
+  const size_t stage_bytes = (size_t)P.nrow_out * 16 * sizeof(double) +
+                             (size_t)a.n_ctm_lev * 16 * (sizeof(double) + sizeof(float));
+  const unsigned vblocks = (unsigned)ceil_div(a.n_pairs, 16);
   if (a.has_trop) {
     OISAT_CHECK_CUDA(cudaFuncSetAttribute(vertical_rows_kernel<true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
