@@ -66,6 +66,10 @@ gather_rows_kernel(const __grid_constant__ SplitParams P) {
   const int64_t rec0 = A.gran_record0[g];
   const int64_t px0 = A.gran_px0[g];
   const uint4* records = reinterpret_cast<const uint4*>(A.records);
+  extern __shared__ __align__(16) unsigned char gsm[];
+  const int sweep = S < 15 ? S : 15;                                  // entries staged at a time
+  uint4* stage = reinterpret_cast<uint4*>(gsm);                        // [16][sweep][nchunk] chunks
+  double* tile = reinterpret_cast<double*>(gsm + (size_t)16 * sweep * P.nchunk * sizeof(uint4));  // [nrow_out][17]
   double acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.0;
@@ -83,23 +87,29 @@ gather_rows_kernel(const __grid_constant__ SplitParams P) {
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) za += __shfl_xor_sync(0xffffffffu, za, o, 16);
     acc_amf += za;
-    for (int node = 0; node < nk; node += 3) {
-      uint4 u[3];
-      double wk[3];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const uint32_t ck = __shfl_sync(0xffffffffu, cix, node + j, 16);
-        wk[j] = __shfl_sync(0xffffffffu, wt, node + j, 16);
-        if (gl < P.nchunk) u[j] = __ldg(&records[ck + gl]);
-      }
+    // All nk records of the sweep are requested at once with asynchronous copies into
+    // this lane's own slots of shared memory (cp.async: no registers held while they
+    // are in flight).  The kernel is bound by the latency of these loads -- with
+    // register-staged loads, three per lane, 49% of the stall samples were long-
+    // scoreboard waits -- so bytes in flight per SM are what counts.
+    uint4* slot = stage + ((threadIdx.x >> 4) * sweep) * P.nchunk + gl;   // [pair][entry][chunk]
+    for (int e = 0; e < nk; ++e) {
+      const uint32_t ck = __shfl_sync(0xffffffffu, cix, e, 16);
       if (gl < P.nchunk) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + e * P.nchunk);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(records + ck + gl)
+                     : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    for (int e = 0; e < nk; ++e) {
+      const double wk = __shfl_sync(0xffffffffu, wt, e, 16);
+      if (gl < P.nchunk) {
+        double z[8];
+        h8_to_f64(slot[e * P.nchunk], z);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          double z[8];
-          h8_to_f64(u[j], z);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = fma(wk[j], z[e], acc[e]);
-        }
+        for (int k = 0; k < 8; ++k) acc[k] = fma(wk, z[k], acc[k]);
       }
     }
   }
@@ -107,7 +117,6 @@ gather_rows_kernel(const __grid_constant__ SplitParams P) {
   // transposed through shared memory ([row][pair], pitch 17: conflict-free for a
   // half warp writing consecutive rows) so that the global stores are full 128-byte
   // lines instead of one 8-byte store per row and pair.
-  extern __shared__ double tile[];  // [nrow_out][17]
   const int col = threadIdx.x >> 4;
   if (gl < P.nchunk) {
 #pragma unroll
@@ -354,7 +363,7 @@ vertical_rows_kernel(const __grid_constant__ SplitParams P) {
     int c = idx < 1 ? 1 : (idx > L - 1 ? L - 1 : idx);
     double x_hi = xs(c), x_lo = xs(c - 1);
     double y_hi = r.at(row_of(c)), y_lo = r.at(row_of(c - 1));
-    double rden = 1.0 / (x_hi - x_lo);
+    double rden = __drcp_rn(x_hi - x_lo);
     constexpr int kBatch = 6;
     for (int k0 = k_begin; k0 < k_end; k0 += kBatch) {
       float lpv[kBatch], pcv8[kBatch], pmv[kBatch];
@@ -382,7 +391,7 @@ vertical_rows_kernel(const __grid_constant__ SplitParams P) {
               y_hi = y_lo;
               x_lo = xs(c - 1);
               y_lo = r.at(row_of(c - 1));
-              rden = 1.0 / (x_hi - x_lo);
+              rden = __drcp_rn(x_hi - x_lo);   // correctly rounded, = 1.0 / x bit for bit
             }
           }
           double sw = ((v - x_lo) * rden) * y_hi + ((x_hi - v) * rden) * y_lo;  // interp1d._call_linear
@@ -487,7 +496,11 @@ extern "C" int oisat_fused_amf_split(const oisat_fused_args* h_args, double* row
                   "record block too large for 32-bit chunk indices: split the batch");
   cudaStream_t s = (cudaStream_t)stream;
   if (int rc = upload_log_table()) return rc;
-  const size_t tile_bytes = (size_t)P.nrow_out * 17 * sizeof(double);
+  const int sweep = 3 * a.nwin < 15 ? 3 * a.nwin : 15;
+  const size_t tile_bytes = (size_t)16 * sweep * P.nchunk * sizeof(uint4) +
+                            (size_t)P.nrow_out * 17 * sizeof(double);
+  OISAT_CHECK_CUDA(cudaFuncSetAttribute(gather_rows_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
   gather_rows_kernel<<<(unsigned)ceil_div(a.n_pairs * 16, kGatherThreads), kGatherThreads,
                        tile_bytes, s>>>(P);
   OISAT_CHECK_LAUNCH();
