@@ -206,7 +206,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // chunk from eight staged rows and stores it, consecutive threads to consecutive
 // chunks.  Granules whose arrays are not 16-byte aligned (or whose pixel count is
 // not a multiple of 8) take pack_block.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 pack_batch_kernel(const oisat_pack_item* __restrict__ items, int n_items, int L, int has_trop,
                   int qflag_dtype, double thresh, int amf_dtype, __half* __restrict__ records,
                   double* __restrict__ amf_masked, int use_bulk) {
