@@ -52,7 +52,9 @@ oi_sweep_leaf_kernel(const double* __restrict__ Sa, const double* __restrict__ S
   int mine = 0;
   for (int i = j; i < body; i += 8) { sa[mine] = Sa[start + i]; so[mine] = So[start + i]; ++mine; }
   const unsigned group_mask = 0xffu << (threadIdx.x & 24);
-  for (int f = 0; f < fac.n; ++f) {
+  // the factors are dealt to gridDim.y blocks: one block per leaf group would leave most
+  // SMs idle (1,625 leaves of 8 lanes = 51 blocks) behind a 99-factor serial loop
+  for (int f = blockIdx.y; f < fac.n; f += gridDim.y) {
     const double r = fac.r[f];
     double acc = 0.0, cnt = 0.0, K, Sb, AK;
     for (int m = 0; m < mine; ++m) {
@@ -255,8 +257,11 @@ extern "C" int oisat_oi_sweep(const double* Sa, const double* So, int64_t n,
   Factors fac;
   fac.n = n_factors;
   for (int i = 0; i < n_factors; ++i) fac.r[i] = h_factors[i];
-  oi_sweep_leaf_kernel<<<(unsigned)ceil_div(nl * 8, 256), 256, 0, s>>>(Sa, So, d_start, nl, fac,
-                                                                      d_val, 2 * nl, d_cnt);
+  const unsigned leaf_blocks = (unsigned)ceil_div(nl * 8, 256);
+  unsigned fac_blocks = leaf_blocks >= 592 ? 1 : (592 + leaf_blocks - 1) / leaf_blocks;  // ~4 per SM
+  if (fac_blocks > (unsigned)n_factors) fac_blocks = (unsigned)n_factors;
+  oi_sweep_leaf_kernel<<<dim3(leaf_blocks, fac_blocks), 256, 0, s>>>(Sa, So, d_start, nl, fac, d_val,
+                                                                    2 * nl, d_cnt);
   OISAT_CHECK_LAUNCH();
   oi_sweep_combine_kernel<<<(unsigned)n_factors, 256, 0, s>>>(d_val, 2 * nl, d_cnt, nl, d_left,
                                                              d_right, d_level, n_levels, sums,
