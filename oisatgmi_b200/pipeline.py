@@ -3,10 +3,10 @@
 materialising a gridded granule.
 
     reader records (host) --upload--> HBM
-    K0  oisat_distmask        \\  geometry plan per granule (host Qhull + walk,
-    plan.granule_plan         /   oisatgmi_b200/plan.py), concatenated into pair tables
-    oisat_quality_mask, oisat_pack_granule      pixel-major float16 records
-    oisat_fused_amf           gather-interpolate + AMF recalculation per (granule, cell)
+    K0  oisat_distmask        \\  geometry plan per granule (native Delaunay on the host,
+    plan.granule_plan(s)      /   K1 point location on the GPU), concatenated into pair tables
+    oisat_pack_batch          quality mask + pixel-major float16 records, one launch per month
+    oisat_fused_amf_split     gather-interpolate, then AMF recalculation per (granule, cell)
     oisat_accum_pairs         ordered segmented reduction -> [10][n_cell] sums / counts
     (torch.distributed all_reduce of the accumulator block when sharded, section 8e)
     oisat_accum_finalize, oisat_oi_prepare, oisat_oi_sweep, knee (host), oisat_oi_apply
@@ -18,7 +18,7 @@ functions), and is what `bench.py` times.
 from __future__ import annotations
 
 import ctypes as C
-
+import os
 import numpy as np
 
 from . import _dev, _lib, _vertical as _v, plan as _plan
@@ -277,18 +277,43 @@ class MonthPipeline:
             items[i].n_px, items[i].px0, items[i].block0 = g.n_px, int(p0), block0
             block0 += int(L.oisat_pack_blocks(g.n_px))
         raw = np.frombuffer(bytes(items), dtype=np.uint8).copy()
+        # OISAT_GUARD=1 (tests): every output buffer sits between two canary zones that
+        # check_guards() inspects after a run -- the out-of-bounds-write check of this path
+        self._guards = []
+        guard = os.environ.get("OISAT_GUARD") == "1"
+
+        def out(shape, dtype="float64", zero=False):
+            if not guard:
+                return (_dev.zeros if zero else _dev.empty)(shape, dtype)
+            n = int(np.prod(shape))
+            pad = 4096
+            big = _dev.full((n + 2 * pad,), 77, dtype)
+            self._guards.append((big, pad, n))
+            view = big[pad:pad + n]
+            if zero:
+                view.zero_()
+            return view.reshape(shape)
+
         self._buf = dict(
-            records=_dev.empty((host["total_px"], R), "float16"),
-            amf_masked=_dev.empty((host["total_px"],)),
-            staged=_dev.empty((5, host["n_pairs"])),
-            acc=_dev.zeros((10, self.n_cell)),
-            ctm_logp=t.empty_like(pm), ctm_pcol=t.empty_like(pm),
-            rows=(_dev.empty(((host["n_pairs"] + 15) // 16,
-                              int(L.oisat_rows_per_pair(g0.nlev, int(g0.has_trop))), 16))
+            records=out((host["total_px"], R), "float16"),
+            amf_masked=out((host["total_px"],)),
+            staged=out((5, host["n_pairs"])),
+            acc=out((10, self.n_cell), zero=True),
+            ctm_logp=out(tuple(pm.shape), "float32"), ctm_pcol=out(tuple(pm.shape), "float32"),
+            rows=(out(((host["n_pairs"] + 15) // 16,
+                       int(L.oisat_rows_per_pair(g0.nlev, int(g0.has_trop))), 16))
                   if self.split else None),
             pack_items=_dev.to_device(raw), pack_blocks=block0,
         )
         return self._buf
+
+    def check_guards(self):
+        """True when no kernel wrote outside its output buffers (needs OISAT_GUARD=1)."""
+        _dev.torch().cuda.synchronize()
+        for big, pad, n in self._guards:
+            if not bool((big[:pad] == 77).all()) or not bool((big[pad + n:] == 77).all()):
+                return False
+        return bool(self._guards)
 
     def run_prepare(self):
         """Derived model fields (float32 log pressure, partial column)."""

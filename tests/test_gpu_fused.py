@@ -122,3 +122,19 @@ def test_pipeline_output_fields_match_float32_casts():
         s = f64["ctm_averaged_vcd_corrected"] / f64["ctm_averaged_vcd"]
     s[np.isnan(s) | np.isinf(s) | (s == 0.0)] = 1.0
     assert np.array_equal(f32["scaling_factor"], s.astype(np.float32))
+
+
+@pytest.mark.parametrize("name", ["omi_hcho", "tropomi_no2", "tropomi_nearest"])
+def test_no_kernel_writes_outside_its_buffers(name, monkeypatch):
+    """Every output buffer of the month pipeline between canary zones (OISAT_GUARD=1):
+    records, masked AMF, row buffer, staged values, accumulator, derived model fields.
+    The pool offers no compute-sanitizer, so this is the out-of-bounds-write check --
+    ragged pixel counts, partial tiles and the last block of every kernel included."""
+    monkeypatch.setenv("OISAT_GUARD", "1")
+    pipe, res = run_pipeline(name)
+    assert pipe.check_guards()
+    monkeypatch.setenv("OISAT_FUSED", "single")
+    pipe2, res2 = run_pipeline(name)
+    assert pipe2.check_guards()
+    for k in ("sat_averaged_vcd", "aux1", "ctm_averaged_vcd"):
+        assert_field(res2[k], res[k], k, rtol=1e-12)
