@@ -82,8 +82,10 @@ __device__ __forceinline__ __half clean_weight(__half w) {
 // float16 weights, level-major out[l][p]; `scale` (may be null) multiplies the float16
 // value in scale's dtype before the result is rounded back to float16 (TROPOMI:
 // averaging kernel x total AMF, reader.py:773-774).  Pixel-major input ([p][l], OMI NO2
-// and TROPOMI files) goes through a 32 x 32 shared-memory tile so that both the loads
-// and the stores are coalesced.
+// and TROPOMI files) goes through shared memory so that both the loads and the stores
+// are coalesced.
+constexpr int kWeightPixels = 128;
+
 __global__ void __launch_bounds__(256)
 rd_weights_kernel(const void* __restrict__ src, int dtype, int pixel_major, int L, int64_t n_px,
                   const void* __restrict__ scale, int sdtype, __half* __restrict__ out) {
@@ -101,20 +103,30 @@ rd_weights_kernel(const void* __restrict__ src, int dtype, int pixel_major, int 
     if (i < (int64_t)L * n_px) out[i] = finish(to_half(src, dtype, i), i % n_px);
     return;
   }
-  __shared__ __half tile[32][33];
-  const int64_t p0 = (int64_t)blockIdx.x * 32;
-  const int l0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-  for (int r = ty; r < 32; r += 8) {       // r: pixel inside the tile, tx: level
-    const int64_t p = p0 + r;
-    const int l = l0 + tx;
-    if (p < n_px && l < L) tile[r][tx] = to_half(src, dtype, p * L + l);
+  // pixel-major: kWeightPixels pixels x L levels are ONE contiguous piece of the file
+  // array: coalesced loads into shared memory, then level rows of kWeightPixels pixels
+  // written two pixels per thread (128 bytes per level and warp)
+  extern __shared__ __half wtile[];          // [kWeightPixels][L + 1]
+  const int pitch = L + 1;
+  const int64_t p0 = (int64_t)blockIdx.x * kWeightPixels;
+  const int64_t left = n_px - p0;
+  const int n_here = left < kWeightPixels ? (int)left : kWeightPixels;
+  for (int i = threadIdx.x; i < n_here * L; i += blockDim.x) {
+    const int px = i / L, l = i - px * L;
+    wtile[px * pitch + l] = to_half(src, dtype, p0 * L + i);
   }
   __syncthreads();
-  for (int r = ty; r < 32; r += 8) {       // r: level inside the tile, tx: pixel
-    const int64_t p = p0 + tx;
-    const int l = l0 + r;
-    if (p < n_px && l < L) out[(int64_t)l * n_px + p] = finish(tile[tx][r], p);
+  for (int i = threadIdx.x; i < L * (kWeightPixels / 2); i += blockDim.x) {
+    const int l = i / (kWeightPixels / 2), px = 2 * (i - l * (kWeightPixels / 2));
+    if (px + 1 < n_here && ((n_px & 1) == 0)) {
+      const __half a = finish(wtile[px * pitch + l], p0 + px);
+      const __half b = finish(wtile[(px + 1) * pitch + l], p0 + px + 1);
+      *reinterpret_cast<__half2*>(out + (int64_t)l * n_px + p0 + px) = __halves2half2(a, b);
+    } else {
+      if (px < n_here) out[(int64_t)l * n_px + p0 + px] = finish(wtile[px * pitch + l], p0 + px);
+      if (px + 1 < n_here)
+        out[(int64_t)l * n_px + p0 + px + 1] = finish(wtile[(px + 1) * pitch + l], p0 + px + 1);
+    }
   }
 }
 
@@ -229,8 +241,10 @@ extern "C" int oisat_reader_weights(const void* src, int32_t dtype, int32_t pixe
   OISAT_CHECK_ARG(!scale || scale_dtype == OISAT_F32 || scale_dtype == OISAT_F64, "bad scale dtype");
   cudaStream_t s = (cudaStream_t)stream;
   if (pixel_major) {
-    const dim3 grid((unsigned)ceil_div(n_px, 32), (unsigned)ceil_div((int64_t)n_lev, 32));
-    rd_weights_kernel<<<grid, 256, 0, s>>>(src, dtype, 1, n_lev, n_px, scale, scale_dtype, (__half*)out);
+    const size_t smem = (size_t)kWeightPixels * (n_lev + 1) * sizeof(__half);
+    OISAT_CHECK_ARG(smem <= 48 * 1024, "too many levels");
+    rd_weights_kernel<<<(unsigned)ceil_div(n_px, kWeightPixels), 256, smem, s>>>(
+        src, dtype, 1, n_lev, n_px, scale, scale_dtype, (__half*)out);
   } else {
     rd_weights_kernel<<<(unsigned)ceil_div((int64_t)n_lev * n_px, 256), 256, 0, s>>>(
         src, dtype, 0, n_lev, n_px, scale, scale_dtype, (__half*)out);
