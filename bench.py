@@ -338,13 +338,17 @@ def main():
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        per_px = sum(v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in tr["kernels"].items()
-                     if "rows_kernel" in k) / tr["n_px"]
-        traffic = per_px * n_px
+        want = "fused_tile_kernel" if pipe.fused_form == "tile" else "rows_kernel"
+        hit = [v for k, v in tr["kernels"].items() if want in k]
+        if hit:
+            traffic = sum(v["dram_bytes_read"] + v["dram_bytes_write"] for v in hit) / tr["n_px"] * n_px
     except Exception:
         pass
     roofline = {"bound": "hbm",
-                "kernel": "gather_rows_kernel + vertical_rows_kernel (one oisat_fused_amf_split call)",
+                "kernel": {"tile": "fused_tile_kernel (one oisat_fused_amf_tile call)",
+                           "split": "gather_rows_kernel + vertical_rows_kernel (one "
+                                    "oisat_fused_amf_split call)",
+                           "single": "fused_amf_kernel (oisat_fused_amf)"}[pipe.fused_form],
                 "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else

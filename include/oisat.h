@@ -399,6 +399,14 @@ int oisat_fused_amf(const oisat_fused_args* h_args, void* stream);
 int64_t oisat_rows_per_pair(int32_t n_sat_lev, int32_t has_trop);
 int oisat_fused_amf_split(const oisat_fused_args* h_args, double* rows, void* stream);
 
+/* Tile form, same results bit for bit in ONE launch and without the row buffer: a block
+ * owns 16 consecutive pairs, gathers their gridded columns into shared memory and runs
+ * the vertical operator there on all of its threads (bisection instead of the merge, so
+ * no data-dependent control flow; running sums kept in registers in numpy's order).
+ * Preferred whenever a record has fewer than 16 chunks and n_sat_lev <= 62.  The tile
+ * table of the args is not used; pair_granule / pair_cell are. */
+int oisat_fused_amf_tile(const oisat_fused_args* h_args, void* stream);
+
 /* ordered segmented reduction of the staged pair values into the accumulators:
  * for model cell c the pairs seg_pair[seg_start[c] .. seg_start[c+1]) are listed
  * in granule order, so the running sums equal numpy's sequential nanmean

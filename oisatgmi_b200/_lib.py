@@ -94,6 +94,7 @@ PROTOTYPES = {
     "oisat_fused_amf": (C.c_int, [C.POINTER(FusedArgs), vp]),
     "oisat_rows_per_pair": (i64, [i32, i32]),
     "oisat_fused_amf_split": (C.c_int, [C.POINTER(FusedArgs), vp, vp]),
+    "oisat_fused_amf_tile": (C.c_int, [C.POINTER(FusedArgs), vp]),
     "oisat_accum_pairs": (C.c_int, [vp, i64, vp, vp, vp, i64, vp]),
 }
 

@@ -448,6 +448,328 @@ vertical_rows_kernel(const __grid_constant__ SplitParams P) {
   A.staged[3 * A.n_pairs + pair] = new_amf;
 }
 
+
+// ---------------------------------------------------------------------------
+// one kernel per 16-pair tile: gather, then the vertical operator from shared memory
+// ---------------------------------------------------------------------------
+// The two kernels above exchange the gridded columns through a row buffer in HBM
+// (2 x 8 bytes x rows per pair: 11 GB of the 26 GB the pair of them moves for an OMI
+// HCHO month).  Here the 16 pairs of a block never leave the SM: the gather phase is the
+// one of gather_rows_kernel (same arithmetic, bit for bit), its tile stays in shared
+// memory, and the vertical operator runs on all 256 threads of the block with no
+// data-dependent control flow:
+//   * phase A: log p of every gridded level by table (in place, and a copy in
+//     ascending order padded with +inf to 63 rows), then the reciprocal width of every
+//     bracket once per pair (the merge of vertical_rows_kernel recomputed it whenever
+//     any lane of the warp shifted its bracket -- 13% of its instructions, 20% of its
+//     stall samples);
+//   * phase B: thread (t, p) evaluates interp1d at model levels k = (t mod 8) + 8 i of
+//     pair p -- searchsorted as a six-step bisection over the padded copy (no bounds
+//     test), the bracket from shared memory -- and adds the terms in registers in
+//     numpy's order: level k belongs to running sum k mod 8, which threads t and t + 8
+//     share (first and second half of i; the second half continues the first half's
+//     partial sum after a barrier), so no per-level products are staged at all;
+//   * phase C: the fixed tree over the eight running sums and the scalar tail.
+// Profiles that are not strictly monotone take amf_slow_path, as before.
+constexpr int kTileThreads = 256;
+constexpr int kTP = 17;           // pitch (doubles) of the shared tiles: 16 pairs + 1
+constexpr int kSearchRows = 63;   // six bisection steps reach row 62
+
+template <int PITCH>
+struct RowViewP {
+  double* base;
+  __device__ __forceinline__ double at(int row) const { return base[row * PITCH]; }
+  __device__ __forceinline__ void set(int row, double v) const { base[row * PITCH] = v; }
+};
+
+// amf_slow_path for a tile of pitch kTP (same code, different view)
+__device__ __noinline__ double amf_slow_path_tile(const RowViewP<kTP>& r, int L, int n_ctm,
+                                                  bool has_trop, double trop, const float* lp,
+                                                  const float* pc, const float* pm, int64_t stride,
+                                                  double* col) {
+  double xs[kMaxSatLev], ys[kMaxSatLev];
+  for (int i = 0; i < L; ++i) {
+    const double xi = r.at(L + i);
+    int rank = 0;
+    for (int j = 0; j < L; ++j) {
+      const double xj = r.at(L + j);
+      const bool eq = (xj == xi) || (xj != xj && xi != xi);
+      rank += (nan_less(xj, xi) || (eq && j < i)) ? 1 : 0;
+    }
+    xs[rank] = xi;
+    ys[rank] = r.at(i);
+  }
+  double va[kMaxCtmLev];
+  float vb[kMaxCtmLev];
+  for (int k = 0; k < n_ctm; ++k) {
+    double p = (double)pc[(int64_t)k * stride];
+    double sw = interp1d_linear<true>(xs, ys, L, (double)lp[(int64_t)k * stride]);
+    if (isinf(sw)) sw = 0.0;
+    if (has_trop && (double)pm[(int64_t)k * stride] < trop) { sw = qnan(); p = qnan(); }
+    const double prod = sw * p;
+    va[k] = prod != prod ? 0.0 : prod;
+    vb[k] = p != p ? 0.0f : (float)p;
+  }
+  const double scd = np_sum_f64(va, n_ctm);
+  const double vcd_m = (double)np_sum_f32(vb, n_ctm);
+  *col = vcd_m;
+  return vcd_m != 0.0 ? scd / vcd_m : qnan();
+}
+
+struct TileSmem {   // static part
+  LogTable tab;
+  double part_a[8 * 16];
+  double tail_a[8 * 16];
+  double old_amf[16];
+  float part_b[8 * 16];
+  float tail_b[8 * 16];
+  int unsorted[16];
+};
+
+// H = levels per thread and half (ceil(ceil(n_ctm / 8) / 2) <= H)
+template <bool HAS_TROP, int H>
+__global__ void __launch_bounds__(kTileThreads, 4)
+fused_tile_kernel(const __grid_constant__ SplitParams P) {
+  const oisat_fused_args& A = P.a;
+  extern __shared__ __align__(16) unsigned char tsm[];
+  __shared__ TileSmem sm;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & 15;
+  const int col = threadIdx.x >> 4;                                    // pair of the tile (gather phase)
+  const int L = A.n_sat_lev, n_ctm = A.n_ctm_lev;
+  const int S = 3 * A.nwin;
+  const int sweep = S < 15 ? S : 15;
+  // dynamic shared memory: [tile | union(gather stage, {xs, rd})]
+  double* tile = reinterpret_cast<double*>(tsm);                       // [nrow_out][kTP]
+  unsigned char* uni = tsm + (((size_t)P.nrow_out * kTP * sizeof(double) + 15) & ~(size_t)15);
+  uint4* stage = reinterpret_cast<uint4*>(uni);                        // [16][sweep][nchunk]
+  double* xs_s = reinterpret_cast<double*>(uni);                       // [kSearchRows][kTP], ascending
+  double* rd_s = xs_s + kSearchRows * kTP;                             // [L][kTP], 1 / (xs[c] - xs[c-1])
+  for (int i = threadIdx.x; i < 128; i += kTileThreads) {
+    sm.tab.r[i] = g_log_table.r[i];
+    sm.tab.neg_log_r[i] = g_log_table.neg_log_r[i];
+  }
+  if (threadIdx.x < 16) sm.unsorted[threadIdx.x] = n_ctm >= 8 ? 0 : 1;
+  // ------------------------------------------------------------ gather phase
+  {
+    const int64_t pair_raw = (int64_t)blockIdx.x * 16 + col;
+    const bool mine = pair_raw < A.n_pairs;
+    const int64_t pair = mine ? pair_raw : A.n_pairs - 1;  // shadow work keeps the warp converged
+    const int g = A.pair_granule[pair];
+    const int64_t rec0 = A.gran_record0[g];
+    const int64_t px0 = A.gran_px0[g];
+    const uint4* records = reinterpret_cast<const uint4*>(A.records);
+    double acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.0;
+    double acc_amf = 0.0;
+    uint4* slot = stage + (col * sweep) * P.nchunk + gl;               // [pair][entry][chunk]
+    const bool has_chunk = gl < P.nchunk;
+    for (int base = 0; base < S; base += 15) {
+      const int nk = (S - base) < 15 ? (S - base) : 15;
+      uint32_t cix = 0;
+      double wt = 0.0, za = 0.0;
+      if (gl < nk) {
+        const int32_t v = A.vert[pair * S + base + gl];
+        wt = A.w[pair * S + base + gl];
+        cix = (uint32_t)((rec0 + v) * P.nchunk);
+        za = wt * A.amf_masked[px0 + v];
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) za += __shfl_xor_sync(0xffffffffu, za, o, 16);
+      acc_amf += za;
+      for (int e = 0; e < nk; ++e) {
+        const uint32_t ck = __shfl_sync(0xffffffffu, cix, e, 16);
+        if (has_chunk) {
+          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + e * P.nchunk);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(records + ck + gl)
+                       : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      for (int e = 0; e < nk; ++e) {
+        const double wk = __shfl_sync(0xffffffffu, wt, e, 16);
+        if (has_chunk) {
+          double z[8];
+          h8_to_f64(slot[e * P.nchunk], z);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = fma(wk, z[k], acc[k]);
+        }
+      }
+    }
+    // rows of this lane: gl + nchunk * e; the variance row (2L+1) leaves as sigma
+    const int sig_row = 2 * L + 1;
+    double sig = 0.0;
+    if (has_chunk) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int row = gl + P.nchunk * e;
+        if (row == sig_row) sig = acc[e];
+        const int orow = row <= 2 * L ? row : row - 1;                 // tropopause follows vcd
+        if (row < P.nrow && row != sig_row) tile[orow * kTP + col] = acc[e] * A.box_weight;
+      }
+    }
+    if (mine && gl == sig_row % P.nchunk)
+      A.staged[1 * A.n_pairs + pair] = sqrt(sig * A.box_weight_err);   // interpolator.py:188
+    if (gl == 0) sm.old_amf[col] = acc_amf * A.box_weight;
+    if (mine && gl == 0) A.staged[4 * A.n_pairs + pair] = acc_amf * A.box_weight;
+  }
+  __syncthreads();   // tile complete; the stage area is free
+  // ---------------------------------------------------------- vertical phase
+  const int p = threadIdx.x & 15, t = threadIdx.x >> 4;
+  const int64_t pair = (int64_t)blockIdx.x * 16 + p;
+  const bool live = pair < A.n_pairs;
+  RowViewP<kTP> r{tile + p};
+  const double vcd = r.at(2 * L);
+  const bool work = live && vcd == vcd;  // amf_recal.py:99-100
+  const double trop = HAS_TROP ? r.at(2 * L + 1) : 0.0;
+  const bool descending = r.at(L) > r.at(2 * L - 1);
+  __syncthreads();   // every thread has read the raw pressures it needs before they turn into logs
+  // phase A: p -> log p in place + ascending copy; padding rows = +inf
+  for (int row = t; row < kSearchRows; row += 16) {
+    if (row < L) {
+      if (work) {
+        const double lg = table_log(r.at(L + row), &sm.tab);
+        r.set(L + row, lg);
+        xs_s[(descending ? L - 1 - row : row) * kTP + p] = lg;
+      }
+    } else {
+      xs_s[row * kTP + p] = CUDART_INF;
+    }
+  }
+  __syncthreads();
+  if (work) {
+    bool bad = false;
+    for (int j = t; j < L; j += 16) {
+      const double x = xs_s[j * kTP + p];
+      const double prev = j > 0 ? xs_s[(j - 1) * kTP + p] : -CUDART_INF;
+      bad = bad || !(prev < x);
+      if (j > 0) rd_s[j * kTP + p] = __drcp_rn(x - prev);              // = 1.0 / (x - prev) bit for bit
+    }
+    if (bad) sm.unsorted[p] = 1;
+  }
+  __syncthreads();
+  const bool sorted = sm.unsorted[p] == 0;
+  const float* lp = A.ctm_logp;
+  const float* pc = A.ctm_pcol;
+  const float* pm = A.ctm_pmid;
+  const int64_t stride = A.n_cell;
+  if (work) {
+    const int64_t off = (int64_t)A.gran_slot[A.pair_granule[pair]] * n_ctm * A.n_cell +
+                        A.pair_cell[pair];
+    lp += off;
+    pc += off;
+    pm = HAS_TROP ? pm + off : lp;
+  }
+  // phase B
+  const int body = n_ctm - (n_ctm % 8);
+  const int nb = body >> 3;                 // terms per running sum
+  const int half = (nb + 1) >> 1;           // <= H
+  const int j8 = t & 7;
+  const int i0 = t < 8 ? 0 : half;
+  const int cnt = t < 8 ? half : nb - half;
+  const bool go = work && sorted;
+  // signed row stride of the scattering weights in ascending-pressure order
+  const double* y0 = tile + (descending ? L - 1 : 0) * kTP + p;
+  const int ystep = descending ? -kTP : kTP;
+  auto term = [&](float lpf, float pcf, float pmf, double& ta, float& tb) {
+    const double v = (double)lpf;
+    double pcv = (double)pcf;
+    int idx = 0;
+#pragma unroll
+    for (int step = 32; step >= 1; step >>= 1)
+      idx += (xs_s[(idx + step - 1) * kTP + p] < v) ? step : 0;         // searchsorted(xs, v, 'left')
+    const int c = idx < 1 ? 1 : (idx > L - 1 ? L - 1 : idx);
+    const double x_hi = xs_s[c * kTP + p], x_lo = xs_s[(c - 1) * kTP + p];
+    const double rden = rd_s[c * kTP + p];
+    const double y_hi = y0[c * ystep], y_lo = y0[(c - 1) * ystep];
+    double sw = ((v - x_lo) * rden) * y_hi + ((x_hi - v) * rden) * y_lo;  // interp1d._call_linear
+    if (isinf(sw)) sw = 0.0;
+    if (HAS_TROP && (double)pmf < trop) { sw = qnan(); pcv = qnan(); }
+    const double prod = sw * pcv;
+    ta = prod != prod ? 0.0 : prod;        // nansum terms
+    tb = pcv != pcv ? 0.0f : (float)pcv;
+  };
+  double ta[H];
+  float tb[H];
+  if (go) {
+    float lpv[H], pcv8[H], pmv[H];
+#pragma unroll
+    for (int i = 0; i < H; ++i) {           // the whole piece of the model column in flight at once
+      const int ii = i < cnt ? i : (cnt > 0 ? cnt - 1 : 0);
+      const int64_t k = j8 + 8 * (i0 + ii);
+      const bool ok = cnt > 0;
+      lpv[i] = ok ? __ldg(lp + k * stride) : 0.0f;
+      pcv8[i] = ok ? __ldg(pc + k * stride) : 0.0f;
+      pmv[i] = (HAS_TROP && ok) ? __ldg(pm + k * stride) : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      ta[i] = 0.0;
+      tb[i] = 0.0f;
+      if (i < cnt) term(lpv[i], pcv8[i], pmv[i], ta[i], tb[i]);
+    }
+    // scalar tail of numpy's pairwise sum: levels body .. n_ctm-1, one per thread t < 8
+    if (t < 8 && body + t < n_ctm) {
+      const int64_t k = body + t;
+      double a;
+      float b;
+      term(__ldg(lp + k * stride), __ldg(pc + k * stride), HAS_TROP ? __ldg(pm + k * stride) : 0.0f,
+           a, b);
+      sm.tail_a[t * 16 + p] = a;
+      sm.tail_b[t * 16 + p] = b;
+    }
+    if (t < 8) {                            // running sum j8, first half: r = a[j]; r += a[j + 8 i]
+      double qa = ta[0];
+      float qb = tb[0];
+#pragma unroll
+      for (int i = 1; i < H; ++i)
+        if (i < cnt) { qa = qa + ta[i]; qb = __fadd_rn(qb, tb[i]); }
+      sm.part_a[j8 * 16 + p] = qa;
+      sm.part_b[j8 * 16 + p] = qb;
+    }
+  }
+  __syncthreads();
+  if (go && t >= 8) {                       // second half continues the same running sum
+    double qa = sm.part_a[j8 * 16 + p];
+    float qb = sm.part_b[j8 * 16 + p];
+#pragma unroll
+    for (int i = 0; i < H; ++i)
+      if (i < cnt) { qa = qa + ta[i]; qb = __fadd_rn(qb, tb[i]); }
+    sm.part_a[j8 * 16 + p] = qa;
+    sm.part_b[j8 * 16 + p] = qb;
+  }
+  __syncthreads();
+  // phase C
+  if (t != 0 || !live) return;
+  const double old_amf = sm.old_amf[p];
+  double new_amf = qnan(), vnew = qnan(), colv = qnan();
+  if (work) {
+    double colsum = 0.0;
+    if (sorted) {
+      auto qa = [&](int j) { return sm.part_a[j * 16 + p]; };
+      auto qb = [&](int j) { return sm.part_b[j * 16 + p]; };
+      double scd = ((qa(0) + qa(1)) + (qa(2) + qa(3))) + ((qa(4) + qa(5)) + (qa(6) + qa(7)));
+      float cs = __fadd_rn(__fadd_rn(__fadd_rn(qb(0), qb(1)), __fadd_rn(qb(2), qb(3))),
+                           __fadd_rn(__fadd_rn(qb(4), qb(5)), __fadd_rn(qb(6), qb(7))));
+      for (int k = body; k < n_ctm; ++k) {   // scalar tail after the tree
+        scd = scd + sm.tail_a[(k - body) * 16 + p];
+        cs = __fadd_rn(cs, sm.tail_b[(k - body) * 16 + p]);
+      }
+      colsum = (double)cs;
+      new_amf = colsum != 0.0 ? scd / colsum : qnan();
+    } else {
+      new_amf = amf_slow_path_tile(r, L, n_ctm, HAS_TROP, trop, lp, pc, pm, stride, &colsum);
+    }
+    vnew = (old_amf * vcd) / new_amf;                        // amf_recal.py:179
+    colv = (vnew != vnew || isinf(vnew)) ? qnan() : colsum;  // :180-181
+  }
+  A.staged[0 * A.n_pairs + pair] = vnew;
+  A.staged[2 * A.n_pairs + pair] = colv;
+  A.staged[3 * A.n_pairs + pair] = new_amf;
+}
+
 }  // namespace oisat
 
 using namespace oisat;
@@ -520,4 +842,46 @@ extern "C" int oisat_fused_amf_split(const oisat_fused_args* h_args, double* row
   }
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
+}
+
+template <bool HAS_TROP, int H>
+static int launch_tile(const SplitParams& P, size_t smem, cudaStream_t s) {
+  OISAT_CHECK_CUDA(cudaFuncSetAttribute(fused_tile_kernel<HAS_TROP, H>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fused_tile_kernel<HAS_TROP, H><<<(unsigned)ceil_div(P.a.n_pairs, 16), kTileThreads, smem, s>>>(P);
+  OISAT_CHECK_LAUNCH();
+  return OISAT_OK;
+}
+
+extern "C" int oisat_fused_amf_tile(const oisat_fused_args* h_args, void* stream) {
+  OISAT_CHECK_ARG(h_args != nullptr, "null args");
+  const oisat_fused_args& a = *h_args;
+  if (a.n_pairs == 0) return OISAT_OK;
+  OISAT_CHECK_ARG(a.vert && a.w && a.gran_record0 && a.gran_px0 && a.gran_slot && a.records &&
+                      a.amf_masked && a.ctm_logp && a.ctm_pcol && a.staged && a.pair_cell &&
+                      a.pair_granule, "null pointer");
+  OISAT_CHECK_ARG(!a.has_trop || a.ctm_pmid, "tropopause masking needs the model p_mid");
+  OISAT_CHECK_ARG(a.nwin >= 1 && a.n_sat_lev >= 2 && a.n_sat_lev <= kSearchRows - 1, "bad stencil");
+  OISAT_CHECK_ARG(a.n_ctm_lev >= 2 && a.n_ctm_lev <= kMaxCtmLev, "bad model level count");
+  SplitParams P;
+  P.a = a;
+  P.rows = nullptr;
+  P.nrow = rec_rows(a.n_sat_lev, a.has_trop);
+  P.nchunk = rec_chunks(a.n_sat_lev, a.has_trop);
+  P.nrow_out = (int)oisat_rows_per_pair(a.n_sat_lev, a.has_trop);
+  OISAT_CHECK_ARG(P.nchunk < 16, "record too wide for the half-warp gather: use oisat_fused_amf");
+  OISAT_CHECK_ARG(a.n_records > 0 && a.n_records * P.nchunk < ((int64_t)1 << 32),
+                  "record block too large for 32-bit chunk indices: split the batch");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (int rc = upload_log_table()) return rc;
+  const int sweep = 3 * a.nwin < 15 ? 3 * a.nwin : 15;
+  const size_t tile_bytes = ((size_t)P.nrow_out * kTP * sizeof(double) + 15) & ~(size_t)15;
+  const size_t stage_bytes = (size_t)16 * sweep * P.nchunk * sizeof(uint4);
+  const size_t vert_bytes = (size_t)(kSearchRows + a.n_sat_lev) * kTP * sizeof(double);
+  const size_t smem = tile_bytes + (stage_bytes > vert_bytes ? stage_bytes : vert_bytes);
+  const int half = ((a.n_ctm_lev / 8) + 1) / 2;
+  if (half <= 5) {
+    return a.has_trop ? launch_tile<true, 5>(P, smem, s) : launch_tile<false, 5>(P, smem, s);
+  }
+  return a.has_trop ? launch_tile<true, 8>(P, smem, s) : launch_tile<false, 8>(P, smem, s);
 }

@@ -372,19 +372,34 @@ class MonthPipeline:
         return a
 
     @property
-    def split(self):
-        """Two-launch form (half-warp gather + thread-per-pair vertical operator):
-        needs records of fewer than 16 chunks; OISAT_FUSED=single forces the
-        one-kernel form."""
+    def fused_form(self):
+        """Which form of the fused step runs: "tile" (default: one launch, 16 pairs per
+        block, gridded columns kept in shared memory), "split" (two launches joined by a
+        row buffer in HBM) -- both need records of fewer than 16 chunks -- or "single"
+        (half warp per pair end to end, any record width).  OISAT_FUSED overrides."""
         import os
         g0 = self.granules[0]
         halfs = int(_lib.lib().oisat_pack_record_halfs(g0.nlev, int(g0.has_trop)))
-        return halfs // 8 < 16 and os.environ.get("OISAT_FUSED", "split") != "single"
+        want = os.environ.get("OISAT_FUSED", "tile")
+        if want not in ("tile", "split", "single"):
+            raise _lib.OisatError("OISAT_FUSED must be tile, split or single")
+        if halfs // 8 >= 16:
+            return "single"
+        if want == "tile" and g0.nlev > 62:
+            return "split"
+        return want
+
+    @property
+    def split(self):
+        return self.fused_form == "split"
 
     def run_fused(self):
         L = _lib.lib()
         a = self.fused_args()
-        if self.split:
+        form = self.fused_form
+        if form == "tile":
+            _lib.check(L.oisat_fused_amf_tile(C.byref(a), _dev.stream()))
+        elif form == "split":
             _lib.check(L.oisat_fused_amf_split(C.byref(a), self._buf["rows"].data_ptr(),
                                                _dev.stream()))
         else:

@@ -138,3 +138,25 @@ def test_no_kernel_writes_outside_its_buffers(name, monkeypatch):
     assert pipe2.check_guards()
     for k in ("sat_averaged_vcd", "aux1", "ctm_averaged_vcd"):
         assert_field(res2[k], res[k], k, rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["omi_hcho", "omi_no2", "tropomi_no2", "tropomi_nearest"])
+def test_tile_form_is_bit_identical_to_split_form(name, monkeypatch):
+    """oisat_fused_amf_tile (one launch, gridded columns in shared memory, bisection) and
+    oisat_fused_amf_split (two launches, row buffer, merge walk) evaluate the same
+    arithmetic in the same order: every staged value, hence every monthly field, is equal
+    bit for bit -- NaN patterns included."""
+    monkeypatch.setenv("OISAT_GUARD", "1")
+    monkeypatch.setenv("OISAT_FUSED", "tile")
+    pipe_t, res_t = run_pipeline(name)
+    assert pipe_t.fused_form == "tile" and pipe_t.check_guards()
+    staged_t = pipe_t._buf["staged"].cpu().numpy()
+    monkeypatch.setenv("OISAT_FUSED", "split")
+    pipe_s, res_s = run_pipeline(name)
+    assert pipe_s.fused_form == "split" and pipe_s.check_guards()
+    staged_s = pipe_s._buf["staged"].cpu().numpy()
+    assert staged_t.shape == staged_s.shape and staged_t.size > 0
+    assert np.array_equal(staged_t.view(np.uint64), staged_s.view(np.uint64))
+    for k in res_s:
+        if isinstance(res_s[k], np.ndarray):
+            assert np.array_equal(res_t[k], res_s[k], equal_nan=True), k
