@@ -21,6 +21,7 @@
 // Costs 2 x 8 bytes x rows per pair of extra HBM traffic for the row buffer and
 // buys ~4x fewer instructions for the vertical operator.
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 
 #include "vertical.cuh"
@@ -526,8 +527,12 @@ struct TileSmem {   // static part
   int unsorted[16];
 };
 
-// H = levels per thread and half (ceil(ceil(n_ctm / 8) / 2) <= H)
-template <bool HAS_TROP, int H>
+// H = levels per thread and half (ceil(ceil(n_ctm / 8) / 2) <= H).  CL / CS / CN: the
+// satellite level count, stencil size and model level count when known at compile time
+// (the BASELINE products), 0 = read from the arguments: with constants the record and
+// tile geometry fold into immediates and the loops unroll (the generic build spends more
+// than half of its instructions outside the arithmetic).
+template <bool HAS_TROP, int H, int CL, int CS, int CN>
 __global__ void __launch_bounds__(kTileThreads, 4)
 fused_tile_kernel(const __grid_constant__ SplitParams P) {
   const oisat_fused_args& A = P.a;
@@ -536,12 +541,16 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
   const int lane = threadIdx.x & 31;
   const int gl = lane & 15;
   const int col = threadIdx.x >> 4;                                    // pair of the tile (gather phase)
-  const int L = A.n_sat_lev, n_ctm = A.n_ctm_lev;
-  const int S = 3 * A.nwin;
+  const int L = CL > 0 ? CL : A.n_sat_lev;
+  const int n_ctm = CN > 0 ? CN : A.n_ctm_lev;
+  const int S = CS > 0 ? CS : 3 * A.nwin;
+  const int nrow = CL > 0 ? rec_rows(CL, HAS_TROP) : P.nrow;
+  const int nchunk = CL > 0 ? rec_chunks(CL, HAS_TROP) : P.nchunk;
+  const int nrow_out = CL > 0 ? 2 * CL + 1 + (HAS_TROP ? 1 : 0) : P.nrow_out;
   const int sweep = S < 15 ? S : 15;
   // dynamic shared memory: [tile | union(gather stage, {xs, rd})]
   double* tile = reinterpret_cast<double*>(tsm);                       // [nrow_out][kTP]
-  unsigned char* uni = tsm + (((size_t)P.nrow_out * kTP * sizeof(double) + 15) & ~(size_t)15);
+  unsigned char* uni = tsm + (((size_t)nrow_out * kTP * sizeof(double) + 15) & ~(size_t)15);
   uint4* stage = reinterpret_cast<uint4*>(uni);                        // [16][sweep][nchunk]
   double* xs_s = reinterpret_cast<double*>(uni);                       // [kSearchRows][kTP], ascending
   double* rd_s = xs_s + kSearchRows * kTP;                             // [L][kTP], 1 / (xs[c] - xs[c-1])
@@ -563,8 +572,8 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.0;
     double acc_amf = 0.0;
-    uint4* slot = stage + (col * sweep) * P.nchunk + gl;               // [pair][entry][chunk]
-    const bool has_chunk = gl < P.nchunk;
+    uint4* slot = stage + (col * sweep) * nchunk + gl;               // [pair][entry][chunk]
+    const bool has_chunk = gl < nchunk;
     for (int base = 0; base < S; base += 15) {
       const int nk = (S - base) < 15 ? (S - base) : 15;
       uint32_t cix = 0;
@@ -572,7 +581,7 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
       if (gl < nk) {
         const int32_t v = A.vert[pair * S + base + gl];
         wt = A.w[pair * S + base + gl];
-        cix = (uint32_t)((rec0 + v) * P.nchunk);
+        cix = (uint32_t)((rec0 + v) * nchunk);
         za = wt * A.amf_masked[px0 + v];
       }
 #pragma unroll
@@ -581,7 +590,7 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
       for (int e = 0; e < nk; ++e) {
         const uint32_t ck = __shfl_sync(0xffffffffu, cix, e, 16);
         if (has_chunk) {
-          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + e * P.nchunk);
+          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + e * nchunk);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(records + ck + gl)
                        : "memory");
         }
@@ -592,7 +601,7 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
         const double wk = __shfl_sync(0xffffffffu, wt, e, 16);
         if (has_chunk) {
           double z[8];
-          h8_to_f64(slot[e * P.nchunk], z);
+          h8_to_f64(slot[e * nchunk], z);
 #pragma unroll
           for (int k = 0; k < 8; ++k) acc[k] = fma(wk, z[k], acc[k]);
         }
@@ -604,13 +613,13 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
     if (has_chunk) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const int row = gl + P.nchunk * e;
+        const int row = gl + nchunk * e;
         if (row == sig_row) sig = acc[e];
         const int orow = row <= 2 * L ? row : row - 1;                 // tropopause follows vcd
-        if (row < P.nrow && row != sig_row) tile[orow * kTP + col] = acc[e] * A.box_weight;
+        if (row < nrow && row != sig_row) tile[orow * kTP + col] = acc[e] * A.box_weight;
       }
     }
-    if (mine && gl == sig_row % P.nchunk)
+    if (mine && gl == sig_row % nchunk)
       A.staged[1 * A.n_pairs + pair] = sqrt(sig * A.box_weight_err);   // interpolator.py:188
     if (gl == 0) sm.old_amf[col] = acc_amf * A.box_weight;
     if (mine && gl == 0) A.staged[4 * A.n_pairs + pair] = acc_amf * A.box_weight;
@@ -651,17 +660,15 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
   }
   __syncthreads();
   const bool sorted = sm.unsorted[p] == 0;
+  // model column of this pair's cell: element offsets fit 32 bits (checked by the host)
   const float* lp = A.ctm_logp;
   const float* pc = A.ctm_pcol;
-  const float* pm = A.ctm_pmid;
-  const int64_t stride = A.n_cell;
-  if (work) {
-    const int64_t off = (int64_t)A.gran_slot[A.pair_granule[pair]] * n_ctm * A.n_cell +
-                        A.pair_cell[pair];
-    lp += off;
-    pc += off;
-    pm = HAS_TROP ? pm + off : lp;
-  }
+  const float* pm = HAS_TROP ? A.ctm_pmid : A.ctm_logp;
+  const uint32_t stride = (uint32_t)A.n_cell;
+  uint32_t off = 0;
+  if (work)
+    off = (uint32_t)A.gran_slot[A.pair_granule[pair]] * (uint32_t)n_ctm * stride +
+          (uint32_t)A.pair_cell[pair];
   // phase B
   const int body = n_ctm - (n_ctm % 8);
   const int nb = body >> 3;                 // terms per running sum
@@ -698,11 +705,11 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
 #pragma unroll
     for (int i = 0; i < H; ++i) {           // the whole piece of the model column in flight at once
       const int ii = i < cnt ? i : (cnt > 0 ? cnt - 1 : 0);
-      const int64_t k = j8 + 8 * (i0 + ii);
+      const uint32_t at = off + (uint32_t)(j8 + 8 * (i0 + ii)) * stride;
       const bool ok = cnt > 0;
-      lpv[i] = ok ? __ldg(lp + k * stride) : 0.0f;
-      pcv8[i] = ok ? __ldg(pc + k * stride) : 0.0f;
-      pmv[i] = (HAS_TROP && ok) ? __ldg(pm + k * stride) : 0.0f;
+      lpv[i] = ok ? __ldg(lp + at) : 0.0f;
+      pcv8[i] = ok ? __ldg(pc + at) : 0.0f;
+      pmv[i] = (HAS_TROP && ok) ? __ldg(pm + at) : 0.0f;
     }
 #pragma unroll
     for (int i = 0; i < H; ++i) {
@@ -712,11 +719,10 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
     }
     // scalar tail of numpy's pairwise sum: levels body .. n_ctm-1, one per thread t < 8
     if (t < 8 && body + t < n_ctm) {
-      const int64_t k = body + t;
+      const uint32_t at = off + (uint32_t)(body + t) * stride;
       double a;
       float b;
-      term(__ldg(lp + k * stride), __ldg(pc + k * stride), HAS_TROP ? __ldg(pm + k * stride) : 0.0f,
-           a, b);
+      term(__ldg(lp + at), __ldg(pc + at), HAS_TROP ? __ldg(pm + at) : 0.0f, a, b);
       sm.tail_a[t * 16 + p] = a;
       sm.tail_b[t * 16 + p] = b;
     }
@@ -760,7 +766,8 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
       colsum = (double)cs;
       new_amf = colsum != 0.0 ? scd / colsum : qnan();
     } else {
-      new_amf = amf_slow_path_tile(r, L, n_ctm, HAS_TROP, trop, lp, pc, pm, stride, &colsum);
+      new_amf = amf_slow_path_tile(r, L, n_ctm, HAS_TROP, trop, lp + off, pc + off, pm + off,
+                                     (int64_t)stride, &colsum);
     }
     vnew = (old_amf * vcd) / new_amf;                        // amf_recal.py:179
     colv = (vnew != vnew || isinf(vnew)) ? qnan() : colsum;  // :180-181
@@ -844,11 +851,12 @@ extern "C" int oisat_fused_amf_split(const oisat_fused_args* h_args, double* row
   return OISAT_OK;
 }
 
-template <bool HAS_TROP, int H>
+template <bool HAS_TROP, int H, int CL, int CS, int CN>
 static int launch_tile(const SplitParams& P, size_t smem, cudaStream_t s) {
-  OISAT_CHECK_CUDA(cudaFuncSetAttribute(fused_tile_kernel<HAS_TROP, H>,
+  OISAT_CHECK_CUDA(cudaFuncSetAttribute(fused_tile_kernel<HAS_TROP, H, CL, CS, CN>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fused_tile_kernel<HAS_TROP, H><<<(unsigned)ceil_div(P.a.n_pairs, 16), kTileThreads, smem, s>>>(P);
+  fused_tile_kernel<HAS_TROP, H, CL, CS, CN>
+      <<<(unsigned)ceil_div(P.a.n_pairs, 16), kTileThreads, smem, s>>>(P);
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
 }
@@ -879,9 +887,19 @@ extern "C" int oisat_fused_amf_tile(const oisat_fused_args* h_args, void* stream
   const size_t stage_bytes = (size_t)16 * sweep * P.nchunk * sizeof(uint4);
   const size_t vert_bytes = (size_t)(kSearchRows + a.n_sat_lev) * kTP * sizeof(double);
   const size_t smem = tile_bytes + (stage_bytes > vert_bytes ? stage_bytes : vert_bytes);
-  const int half = ((a.n_ctm_lev / 8) + 1) / 2;
-  if (half <= 5) {
-    return a.has_trop ? launch_tile<true, 5>(P, smem, s) : launch_tile<false, 5>(P, smem, s);
-  }
-  return a.has_trop ? launch_tile<true, 8>(P, smem, s) : launch_tile<false, 8>(P, smem, s);
+  OISAT_CHECK_ARG((int64_t)a.n_ctm_lev * a.n_cell * 8 < ((int64_t)1 << 31) && a.n_cell < ((int64_t)1 << 31),
+                  "model fields too large for 32-bit element offsets: use oisat_fused_amf_split");
+  const int S = 3 * a.nwin, L = a.n_sat_lev, N = a.n_ctm_lev;
+  // the BASELINE products, compiled with their geometry as constants (OISAT_TILE_GENERIC=1
+  // forces the run-time build: the tests compare the two)
+  const char* gen = getenv("OISAT_TILE_GENERIC");
+  const bool generic = gen && gen[0] == '1';
+  if (generic) {
+  } else if (!a.has_trop && L == 47 && S == 12 && N == 72) return launch_tile<false, 5, 47, 12, 72>(P, smem, s);
+  else if (a.has_trop && L == 35 && S == 12 && N == 72) return launch_tile<true, 5, 35, 12, 72>(P, smem, s);
+  else if (a.has_trop && L == 34 && S == 90 && N == 72) return launch_tile<true, 5, 34, 90, 72>(P, smem, s);
+  const int half = ((N / 8) + 1) / 2;
+  if (half <= 5)
+    return a.has_trop ? launch_tile<true, 5, 0, 0, 0>(P, smem, s) : launch_tile<false, 5, 0, 0, 0>(P, smem, s);
+  return a.has_trop ? launch_tile<true, 8, 0, 0, 0>(P, smem, s) : launch_tile<false, 8, 0, 0, 0>(P, smem, s);
 }

@@ -160,3 +160,17 @@ def test_tile_form_is_bit_identical_to_split_form(name, monkeypatch):
     for k in res_s:
         if isinstance(res_s[k], np.ndarray):
             assert np.array_equal(res_t[k], res_s[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("name", ["omi_hcho", "omi_no2", "tropomi_no2"])
+def test_tile_form_generic_build_equals_specialised_build(name, monkeypatch):
+    """The BASELINE products run a build of the tile kernel with their level counts and
+    stencil size as compile-time constants; OISAT_TILE_GENERIC=1 forces the run-time build
+    every other shape takes.  Same staged values bit for bit."""
+    monkeypatch.setenv("OISAT_FUSED", "tile")
+    pipe_a, _ = run_pipeline(name)
+    a = pipe_a._buf["staged"].cpu().numpy()
+    monkeypatch.setenv("OISAT_TILE_GENERIC", "1")
+    pipe_b, _ = run_pipeline(name)
+    b = pipe_b._buf["staged"].cpu().numpy()
+    assert a.size > 0 and np.array_equal(a.view(np.uint64), b.view(np.uint64))
