@@ -559,6 +559,27 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
     sm.tab.neg_log_r[i] = g_log_table.neg_log_r[i];
   }
   if (threadIdx.x < 16) sm.unsorted[threadIdx.x] = n_ctm >= 8 ? 0 : 1;
+  // identity of this thread in the vertical phase (pair p = gather lane, t = gather pair):
+  // known now, so the model column's offset is loaded early and the column itself is
+  // prefetched into L2 while the records are in flight
+  const int p = threadIdx.x & 15, t = threadIdx.x >> 4;
+  const int64_t vpair = (int64_t)blockIdx.x * 16 + p;
+  const bool live = vpair < A.n_pairs;
+  const uint32_t stride = (uint32_t)A.n_cell;
+  uint32_t off = 0;
+  if (live)
+    off = (uint32_t)A.gran_slot[A.pair_granule[vpair]] * (uint32_t)n_ctm * stride +
+          (uint32_t)A.pair_cell[vpair];
+  const float* lp = A.ctm_logp;
+  const float* pc = A.ctm_pcol;
+  const float* pm = HAS_TROP ? A.ctm_pmid : A.ctm_logp;
+  // levels of phase B: k = j8 + 8 (i0 + i), i < cnt
+  const int body = n_ctm - (n_ctm % 8);
+  const int nb = body >> 3;                 // terms per running sum
+  const int half = (nb + 1) >> 1;           // <= H
+  const int j8 = t & 7;
+  const int i0 = t < 8 ? 0 : half;
+  const int cnt = t < 8 ? half : nb - half;
   // ------------------------------------------------------------ gather phase
   {
     const int64_t pair_raw = (int64_t)blockIdx.x * 16 + col;
@@ -572,38 +593,62 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.0;
     double acc_amf = 0.0;
-    uint4* slot = stage + (col * sweep) * nchunk + gl;               // [pair][entry][chunk]
+    uint4* slot = stage + (col * sweep) * nchunk + gl;                 // [pair][entry][chunk]
     const bool has_chunk = gl < nchunk;
+#pragma unroll 1
     for (int base = 0; base < S; base += 15) {
       const int nk = (S - base) < 15 ? (S - base) : 15;
       uint32_t cix = 0;
-      double wt = 0.0, za = 0.0;
+      int32_t v = 0;
+      double wt = 0.0;
       if (gl < nk) {
-        const int32_t v = A.vert[pair * S + base + gl];
+        v = A.vert[pair * S + base + gl];
         wt = A.w[pair * S + base + gl];
         cix = (uint32_t)((rec0 + v) * nchunk);
-        za = wt * A.amf_masked[px0 + v];
       }
+      // All nk records of the sweep are requested at once with asynchronous copies into this
+      // lane's own slots (no registers held while they are in flight) ...
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) za += __shfl_xor_sync(0xffffffffu, za, o, 16);
-      acc_amf += za;
-      for (int e = 0; e < nk; ++e) {
-        const uint32_t ck = __shfl_sync(0xffffffffu, cix, e, 16);
-        if (has_chunk) {
-          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + e * nchunk);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(records + ck + gl)
-                       : "memory");
+      for (int e = 0; e < 15; ++e) {
+        if (e < nk) {
+          const uint32_t ck = __shfl_sync(0xffffffffu, cix, e, 16) + (uint32_t)gl;   // 32-bit chunk index
+          if (has_chunk) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + e * nchunk);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(records + ck)
+                         : "memory");
+          }
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      for (int e = 0; e < nk; ++e) {
-        const double wk = __shfl_sync(0xffffffffu, wt, e, 16);
-        if (has_chunk) {
-          double z[8];
-          h8_to_f64(slot[e * nchunk], z);
+      // ... and while they are: the AMF term (a dependent load of its own) and, once, the
+      // prefetch of the model levels this thread evaluates in phase B
+      double za = 0.0;
+      if (gl < nk) za = wt * A.amf_masked[px0 + v];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = fma(wk, z[k], acc[k]);
+      for (int o = 8; o > 0; o >>= 1) za += __shfl_xor_sync(0xffffffffu, za, o, 16);
+      acc_amf += za;
+      if (base == 0 && live) {
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+          if (i < cnt) {
+            const uint32_t at = off + (uint32_t)(j8 + 8 * (i0 + i)) * stride;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + at));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + at));
+            if (HAS_TROP) asm volatile("prefetch.global.L2 [%0];" ::"l"(pm + at));
+          }
+        }
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+      for (int e = 0; e < 15; ++e) {
+        if (e < nk) {
+          const double wk = __shfl_sync(0xffffffffu, wt, e, 16);
+          if (has_chunk) {
+            double z[8];
+            h8_to_f64(slot[e * nchunk], z);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = fma(wk, z[k], acc[k]);
+          }
         }
       }
     }
@@ -626,9 +671,7 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
   }
   __syncthreads();   // tile complete; the stage area is free
   // ---------------------------------------------------------- vertical phase
-  const int p = threadIdx.x & 15, t = threadIdx.x >> 4;
-  const int64_t pair = (int64_t)blockIdx.x * 16 + p;
-  const bool live = pair < A.n_pairs;
+  const int64_t pair = vpair;
   RowViewP<kTP> r{tile + p};
   const double vcd = r.at(2 * L);
   const bool work = live && vcd == vcd;  // amf_recal.py:99-100
@@ -636,6 +679,7 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
   const bool descending = r.at(L) > r.at(2 * L - 1);
   __syncthreads();   // every thread has read the raw pressures it needs before they turn into logs
   // phase A: p -> log p in place + ascending copy; padding rows = +inf
+#pragma unroll
   for (int row = t; row < kSearchRows; row += 16) {
     if (row < L) {
       if (work) {
@@ -660,22 +704,7 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
   }
   __syncthreads();
   const bool sorted = sm.unsorted[p] == 0;
-  // model column of this pair's cell: element offsets fit 32 bits (checked by the host)
-  const float* lp = A.ctm_logp;
-  const float* pc = A.ctm_pcol;
-  const float* pm = HAS_TROP ? A.ctm_pmid : A.ctm_logp;
-  const uint32_t stride = (uint32_t)A.n_cell;
-  uint32_t off = 0;
-  if (work)
-    off = (uint32_t)A.gran_slot[A.pair_granule[pair]] * (uint32_t)n_ctm * stride +
-          (uint32_t)A.pair_cell[pair];
   // phase B
-  const int body = n_ctm - (n_ctm % 8);
-  const int nb = body >> 3;                 // terms per running sum
-  const int half = (nb + 1) >> 1;           // <= H
-  const int j8 = t & 7;
-  const int i0 = t < 8 ? 0 : half;
-  const int cnt = t < 8 ? half : nb - half;
   const bool go = work && sorted;
   // signed row stride of the scattering weights in ascending-pressure order
   const double* y0 = tile + (descending ? L - 1 : 0) * kTP + p;
