@@ -385,6 +385,12 @@ typedef struct oisat_fused_args {
   /* per-pair tables (split form only): granule and model cell of every pair */
   const int32_t* pair_granule;
   const int32_t* pair_cell;
+  /* optional (NULL = derive from the tables above), tile form only: the same facts per
+   * pair, so that a block's first loads do not wait for one another --
+   * pair_record0[p] = gran_record0[pair_granule[p]] (= gran_px0[...]: one pixel, one record),
+   * pair_ctm_off[p] = gran_slot[pair_granule[p]] * n_ctm_lev * n_cell + pair_cell[p] */
+  const int64_t* pair_record0;
+  const uint32_t* pair_ctm_off;
 } oisat_fused_args;
 
 int oisat_fused_amf(const oisat_fused_args* h_args, void* stream);

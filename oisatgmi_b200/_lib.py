@@ -40,6 +40,7 @@ class FusedArgs(C.Structure):
         ("has_trop", i32),
         ("ctm_pmid", vp), ("ctm_logp", vp), ("ctm_pcol", vp), ("n_ctm_lev", i32), ("n_cell", i64),
         ("staged", vp), ("pair_granule", vp), ("pair_cell", vp),
+        ("pair_record0", vp), ("pair_ctm_off", vp),
     ]
 
 

@@ -172,6 +172,24 @@ __device__ __forceinline__ double table_log(double x, const LogTable* __restrict
   return fma((double)e, 0.6931471805599453, tab->neg_log_r[i] + l1p);
 }
 
+// same, with r_i and -log(r_i) side by side: one 16-byte shared-memory load per logarithm
+// (the two separate look-ups are scattered over the table, ~6 wavefronts each)
+__device__ __forceinline__ double table_log2(double x, const double2* __restrict__ tab) {
+  if (!(x >= 2.2250738585072014e-308 && x <= 1.7976931348623157e308)) return log(x);
+  const long long bits = __double_as_longlong(x);
+  const int e = (int)(bits >> 52) - 1023;
+  const int i = (int)(bits >> 45) & 127;
+  const double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+  const double2 rn = tab[i];
+  const double z = fma(m, rn.x, -1.0);
+  double p = fma(z, -1.0 / 6.0, 0.2);
+  p = fma(z, p, -0.25);
+  p = fma(z, p, 1.0 / 3.0);
+  p = fma(z, p, -0.5);
+  const double l1p = fma(z * z, p, z);
+  return fma((double)e, 0.6931471805599453, rn.y + l1p);
+}
+
 // ---------------------------------------------------------------------------
 // one thread per pair
 // ---------------------------------------------------------------------------
@@ -473,7 +491,10 @@ vertical_rows_kernel(const __grid_constant__ SplitParams P) {
 //   * phase C: the fixed tree over the eight running sums and the scalar tail.
 // Profiles that are not strictly monotone take amf_slow_path, as before.
 constexpr int kTileThreads = 256;
-constexpr int kTP = 17;           // pitch (doubles) of the shared tiles: 16 pairs + 1
+constexpr int kTP = 17;           // pitch (doubles) of the gathered tile: 16 pairs + 1 (the gather writes rows per lane)
+constexpr int kXP = 16;           // pitch of the search arrays: pair p owns bank pair p, so ANY mix of rows
+                                  // across the 16 pairs of a half warp is conflict-free (phase B's probes are
+                                  // data dependent; with pitch 17 they cost ~3.5 wavefronts each instead of 2)
 constexpr int kSearchRows = 63;   // six bisection steps reach row 62
 
 template <int PITCH>
@@ -518,7 +539,7 @@ __device__ __noinline__ double amf_slow_path_tile(const RowViewP<kTP>& r, int L,
 }
 
 struct TileSmem {   // static part
-  LogTable tab;
+  double2 tab[128];   // (r_i, -log r_i)
   double part_a[8 * 16];
   double tail_a[8 * 16];
   double old_amf[16];
@@ -552,11 +573,10 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
   double* tile = reinterpret_cast<double*>(tsm);                       // [nrow_out][kTP]
   unsigned char* uni = tsm + (((size_t)nrow_out * kTP * sizeof(double) + 15) & ~(size_t)15);
   uint4* stage = reinterpret_cast<uint4*>(uni);                        // [16][sweep][nchunk]
-  double* xs_s = reinterpret_cast<double*>(uni);                       // [kSearchRows][kTP], ascending
-  double* rd_s = xs_s + kSearchRows * kTP;                             // [L][kTP], 1 / (xs[c] - xs[c-1])
+  double* xs_s = reinterpret_cast<double*>(uni);                       // [kSearchRows][kXP], ascending
+  double* rd_s = xs_s + kSearchRows * kXP;                             // [L][kXP], 1 / (xs[c] - xs[c-1])
   for (int i = threadIdx.x; i < 128; i += kTileThreads) {
-    sm.tab.r[i] = g_log_table.r[i];
-    sm.tab.neg_log_r[i] = g_log_table.neg_log_r[i];
+    sm.tab[i] = make_double2(g_log_table.r[i], g_log_table.neg_log_r[i]);
   }
   if (threadIdx.x < 16) sm.unsorted[threadIdx.x] = n_ctm >= 8 ? 0 : 1;
   // identity of this thread in the vertical phase (pair p = gather lane, t = gather pair):
@@ -568,8 +588,9 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
   const uint32_t stride = (uint32_t)A.n_cell;
   uint32_t off = 0;
   if (live)
-    off = (uint32_t)A.gran_slot[A.pair_granule[vpair]] * (uint32_t)n_ctm * stride +
-          (uint32_t)A.pair_cell[vpair];
+    off = A.pair_ctm_off ? A.pair_ctm_off[vpair]
+                         : (uint32_t)A.gran_slot[A.pair_granule[vpair]] * (uint32_t)n_ctm * stride +
+                               (uint32_t)A.pair_cell[vpair];
   const float* lp = A.ctm_logp;
   const float* pc = A.ctm_pcol;
   const float* pm = HAS_TROP ? A.ctm_pmid : A.ctm_logp;
@@ -585,9 +606,14 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
     const int64_t pair_raw = (int64_t)blockIdx.x * 16 + col;
     const bool mine = pair_raw < A.n_pairs;
     const int64_t pair = mine ? pair_raw : A.n_pairs - 1;  // shadow work keeps the warp converged
-    const int g = A.pair_granule[pair];
-    const int64_t rec0 = A.gran_record0[g];
-    const int64_t px0 = A.gran_px0[g];
+    int64_t rec0, px0;
+    if (A.pair_record0) {
+      rec0 = px0 = A.pair_record0[pair];
+    } else {
+      const int g = A.pair_granule[pair];
+      rec0 = A.gran_record0[g];
+      px0 = A.gran_px0[g];
+    }
     const uint4* records = reinterpret_cast<const uint4*>(A.records);
     double acc[8];
 #pragma unroll
@@ -683,22 +709,35 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
   for (int row = t; row < kSearchRows; row += 16) {
     if (row < L) {
       if (work) {
-        const double lg = table_log(r.at(L + row), &sm.tab);
+        const double lg = table_log2(r.at(L + row), sm.tab);
         r.set(L + row, lg);
-        xs_s[(descending ? L - 1 - row : row) * kTP + p] = lg;
+        xs_s[(descending ? L - 1 - row : row) * kXP + p] = lg;
       }
     } else {
-      xs_s[row * kTP + p] = CUDART_INF;
+      xs_s[row * kXP + p] = CUDART_INF;
     }
   }
   __syncthreads();
+  // this thread's piece of the model column (prefetched into L2 during the gather) is
+  // requested now, all of it at once, and arrives while the bracket widths are inverted
+  float lpv[H], pcv8[H], pmv[H];
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    const int ii = i < cnt ? i : (cnt > 0 ? cnt - 1 : 0);
+    const uint32_t at = off + (uint32_t)(j8 + 8 * (i0 + ii)) * stride;
+    const bool ok = work && cnt > 0;
+    lpv[i] = ok ? __ldg(lp + at) : 0.0f;
+    pcv8[i] = ok ? __ldg(pc + at) : 0.0f;
+    pmv[i] = (HAS_TROP && ok) ? __ldg(pm + at) : 0.0f;
+  }
   if (work) {
     bool bad = false;
+#pragma unroll
     for (int j = t; j < L; j += 16) {
-      const double x = xs_s[j * kTP + p];
-      const double prev = j > 0 ? xs_s[(j - 1) * kTP + p] : -CUDART_INF;
+      const double x = xs_s[j * kXP + p];
+      const double prev = j > 0 ? xs_s[(j - 1) * kXP + p] : -CUDART_INF;
       bad = bad || !(prev < x);
-      if (j > 0) rd_s[j * kTP + p] = __drcp_rn(x - prev);              // = 1.0 / (x - prev) bit for bit
+      if (j > 0) rd_s[j * kXP + p] = __drcp_rn(x - prev);              // = 1.0 / (x - prev) bit for bit
     }
     if (bad) sm.unsorted[p] = 1;
   }
@@ -715,10 +754,10 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
     int idx = 0;
 #pragma unroll
     for (int step = 32; step >= 1; step >>= 1)
-      idx += (xs_s[(idx + step - 1) * kTP + p] < v) ? step : 0;         // searchsorted(xs, v, 'left')
+      idx += (xs_s[(idx + step - 1) * kXP + p] < v) ? step : 0;         // searchsorted(xs, v, 'left')
     const int c = idx < 1 ? 1 : (idx > L - 1 ? L - 1 : idx);
-    const double x_hi = xs_s[c * kTP + p], x_lo = xs_s[(c - 1) * kTP + p];
-    const double rden = rd_s[c * kTP + p];
+    const double x_hi = xs_s[c * kXP + p], x_lo = xs_s[(c - 1) * kXP + p];
+    const double rden = rd_s[c * kXP + p];
     const double y_hi = y0[c * ystep], y_lo = y0[(c - 1) * ystep];
     double sw = ((v - x_lo) * rden) * y_hi + ((x_hi - v) * rden) * y_lo;  // interp1d._call_linear
     if (isinf(sw)) sw = 0.0;
@@ -730,16 +769,6 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
   double ta[H];
   float tb[H];
   if (go) {
-    float lpv[H], pcv8[H], pmv[H];
-#pragma unroll
-    for (int i = 0; i < H; ++i) {           // the whole piece of the model column in flight at once
-      const int ii = i < cnt ? i : (cnt > 0 ? cnt - 1 : 0);
-      const uint32_t at = off + (uint32_t)(j8 + 8 * (i0 + ii)) * stride;
-      const bool ok = cnt > 0;
-      lpv[i] = ok ? __ldg(lp + at) : 0.0f;
-      pcv8[i] = ok ? __ldg(pc + at) : 0.0f;
-      pmv[i] = (HAS_TROP && ok) ? __ldg(pm + at) : 0.0f;
-    }
 #pragma unroll
     for (int i = 0; i < H; ++i) {
       ta[i] = 0.0;
@@ -914,7 +943,7 @@ extern "C" int oisat_fused_amf_tile(const oisat_fused_args* h_args, void* stream
   const int sweep = 3 * a.nwin < 15 ? 3 * a.nwin : 15;
   const size_t tile_bytes = ((size_t)P.nrow_out * kTP * sizeof(double) + 15) & ~(size_t)15;
   const size_t stage_bytes = (size_t)16 * sweep * P.nchunk * sizeof(uint4);
-  const size_t vert_bytes = (size_t)(kSearchRows + a.n_sat_lev) * kTP * sizeof(double);
+  const size_t vert_bytes = (size_t)(kSearchRows + a.n_sat_lev) * kXP * sizeof(double);
   const size_t smem = tile_bytes + (stage_bytes > vert_bytes ? stage_bytes : vert_bytes);
   OISAT_CHECK_ARG((int64_t)a.n_ctm_lev * a.n_cell * 8 < ((int64_t)1 << 31) && a.n_cell < ((int64_t)1 << 31),
                   "model fields too large for 32-bit element offsets: use oisat_fused_amf_split");

@@ -369,6 +369,16 @@ class MonthPipeline:
         a.staged = buf["staged"].data_ptr()
         a.pair_granule = dev["pair_gran"].data_ptr()
         a.pair_cell = dev["pair_cell"].data_ptr()
+        if "pair_rec0" not in dev:     # per-pair copies of the per-granule facts (tile form)
+            t = _dev.torch()
+            gi = dev["pair_gran"].to(t.int64)
+            dev["pair_rec0"] = dev["gran_px0"][gi].contiguous()
+            off = dev["gran_slot"].to(t.int64)[gi] * (pm.shape[1] * self.n_cell) + dev["pair_cell"].to(t.int64)
+            if int(pm.shape[0]) * pm.shape[1] * self.n_cell >= 2 ** 31:
+                raise _lib.OisatError("model fields too large for 32-bit element offsets")
+            dev["pair_ctm_off"] = off.to(t.int32).contiguous()
+        a.pair_record0 = dev["pair_rec0"].data_ptr()
+        a.pair_ctm_off = dev["pair_ctm_off"].data_ptr()
         return a
 
     @property
