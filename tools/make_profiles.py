@@ -19,7 +19,7 @@ import sys
 
 HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PROF = os.path.join(HERE, "profiles")
-STEP = ["ctm_prepare_kernel", "pack_batch_kernel", "gather_rows_kernel", "vertical_rows_kernel",
+STEP = ["ctm_prepare_kernel", "pack_batch_kernel", "fused_tile_kernel", "gather_rows_kernel", "vertical_rows_kernel",
         "accum_pairs_kernel", "accum_finalize_kernel", "oi_prepare_kernel", "oi_sweep_leaf_kernel",
         "oi_sweep_combine_kernel", "oi_apply_kernel"]
 
@@ -65,10 +65,10 @@ def main():
     ph = bench["roofline"]["phase_ms"]
     s_ph = sum(ph.values())
     pack = sum(a[1] for k, a in in_step.items() if "pack" in k)
-    fused = sum(a[1] for k, a in in_step.items() if "rows_kernel" in k)
+    fused = sum(a[1] for k, a in in_step.items() if "rows_kernel" in k or "fused_tile" in k)
     out += ["", "bench.py CUDA-event phases of the same workload without ncu (`profiles/r01_bench_n1.json`): "
             + ", ".join("%s %.2f ms" % kv for kv in ph.items()) + " (step %.2f ms)." % bench["ms_per_step"],
-            "Shares agree: pack %.0f %% (events) vs %.0f %% (ncu), gather+vertical %.0f %% vs %.0f %%."
+            "Shares agree: pack %.0f %% (events) vs %.0f %% (ncu), fused step %.0f %% vs %.0f %%."
             % (100 * ph["pack"] / s_ph, 100 * pack / tot, 100 * ph["fused"] / s_ph, 100 * fused / tot)]
     open(os.path.join(PROF, "r01_launches_summary.md"), "w").write("\n".join(out) + "\n")
 
