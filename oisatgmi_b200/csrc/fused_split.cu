@@ -553,8 +553,8 @@ struct TileSmem {   // static part
 // (the BASELINE products), 0 = read from the arguments: with constants the record and
 // tile geometry fold into immediates and the loops unroll (the generic build spends more
 // than half of its instructions outside the arithmetic).
-template <bool HAS_TROP, int H, int CL, int CS, int CN>
-__global__ void __launch_bounds__(kTileThreads, 4)
+template <bool HAS_TROP, int H, int CL, int CS, int CN, int SW, int MINB>
+__global__ void __launch_bounds__(kTileThreads, MINB)
 fused_tile_kernel(const __grid_constant__ SplitParams P) {
   const oisat_fused_args& A = P.a;
   extern __shared__ __align__(16) unsigned char tsm[];
@@ -568,7 +568,7 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
   const int nrow = CL > 0 ? rec_rows(CL, HAS_TROP) : P.nrow;
   const int nchunk = CL > 0 ? rec_chunks(CL, HAS_TROP) : P.nchunk;
   const int nrow_out = CL > 0 ? 2 * CL + 1 + (HAS_TROP ? 1 : 0) : P.nrow_out;
-  const int sweep = S < 15 ? S : 15;
+  const int sweep = S < SW ? S : SW;   // entries staged at a time (SW <= 15: one lane per entry)
   // dynamic shared memory: [tile | union(gather stage, {xs, rd})]
   double* tile = reinterpret_cast<double*>(tsm);                       // [nrow_out][kTP]
   unsigned char* uni = tsm + (((size_t)nrow_out * kTP * sizeof(double) + 15) & ~(size_t)15);
@@ -622,8 +622,8 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
     uint4* slot = stage + (col * sweep) * nchunk + gl;                 // [pair][entry][chunk]
     const bool has_chunk = gl < nchunk;
 #pragma unroll 1
-    for (int base = 0; base < S; base += 15) {
-      const int nk = (S - base) < 15 ? (S - base) : 15;
+    for (int base = 0; base < S; base += SW) {
+      const int nk = (S - base) < SW ? (S - base) : SW;
       uint32_t cix = 0;
       int32_t v = 0;
       double wt = 0.0;
@@ -635,7 +635,7 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
       // All nk records of the sweep are requested at once with asynchronous copies into this
       // lane's own slots (no registers held while they are in flight) ...
 #pragma unroll
-      for (int e = 0; e < 15; ++e) {
+      for (int e = 0; e < SW; ++e) {
         if (e < nk) {
           const uint32_t ck = __shfl_sync(0xffffffffu, cix, e, 16) + (uint32_t)gl;   // 32-bit chunk index
           if (has_chunk) {
@@ -666,7 +666,7 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
       }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-      for (int e = 0; e < 15; ++e) {
+      for (int e = 0; e < SW; ++e) {
         if (e < nk) {
           const double wk = __shfl_sync(0xffffffffu, wt, e, 16);
           if (has_chunk) {
@@ -909,11 +909,17 @@ extern "C" int oisat_fused_amf_split(const oisat_fused_args* h_args, double* row
   return OISAT_OK;
 }
 
-template <bool HAS_TROP, int H, int CL, int CS, int CN>
-static int launch_tile(const SplitParams& P, size_t smem, cudaStream_t s) {
-  OISAT_CHECK_CUDA(cudaFuncSetAttribute(fused_tile_kernel<HAS_TROP, H, CL, CS, CN>,
+template <bool HAS_TROP, int H, int CL, int CS, int CN, int SW = 15, int MINB = 4>
+static int launch_tile(const SplitParams& P, cudaStream_t s) {
+  const oisat_fused_args& a = P.a;
+  const int sweep = 3 * a.nwin < SW ? 3 * a.nwin : SW;
+  const size_t tile_bytes = ((size_t)P.nrow_out * kTP * sizeof(double) + 15) & ~(size_t)15;
+  const size_t stage_bytes = (size_t)16 * sweep * P.nchunk * sizeof(uint4);
+  const size_t vert_bytes = (size_t)(kSearchRows + a.n_sat_lev) * kXP * sizeof(double);
+  const size_t smem = tile_bytes + (stage_bytes > vert_bytes ? stage_bytes : vert_bytes);
+  OISAT_CHECK_CUDA(cudaFuncSetAttribute(fused_tile_kernel<HAS_TROP, H, CL, CS, CN, SW, MINB>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fused_tile_kernel<HAS_TROP, H, CL, CS, CN>
+  fused_tile_kernel<HAS_TROP, H, CL, CS, CN, SW, MINB>
       <<<(unsigned)ceil_div(P.a.n_pairs, 16), kTileThreads, smem, s>>>(P);
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
@@ -940,11 +946,6 @@ extern "C" int oisat_fused_amf_tile(const oisat_fused_args* h_args, void* stream
                   "record block too large for 32-bit chunk indices: split the batch");
   cudaStream_t s = (cudaStream_t)stream;
   if (int rc = upload_log_table()) return rc;
-  const int sweep = 3 * a.nwin < 15 ? 3 * a.nwin : 15;
-  const size_t tile_bytes = ((size_t)P.nrow_out * kTP * sizeof(double) + 15) & ~(size_t)15;
-  const size_t stage_bytes = (size_t)16 * sweep * P.nchunk * sizeof(uint4);
-  const size_t vert_bytes = (size_t)(kSearchRows + a.n_sat_lev) * kXP * sizeof(double);
-  const size_t smem = tile_bytes + (stage_bytes > vert_bytes ? stage_bytes : vert_bytes);
   OISAT_CHECK_ARG((int64_t)a.n_ctm_lev * a.n_cell * 8 < ((int64_t)1 << 31) && a.n_cell < ((int64_t)1 << 31),
                   "model fields too large for 32-bit element offsets: use oisat_fused_amf_split");
   const int S = 3 * a.nwin, L = a.n_sat_lev, N = a.n_ctm_lev;
@@ -953,11 +954,11 @@ extern "C" int oisat_fused_amf_tile(const oisat_fused_args* h_args, void* stream
   const char* gen = getenv("OISAT_TILE_GENERIC");
   const bool generic = gen && gen[0] == '1';
   if (generic) {
-  } else if (!a.has_trop && L == 47 && S == 12 && N == 72) return launch_tile<false, 5, 47, 12, 72>(P, smem, s);
-  else if (a.has_trop && L == 35 && S == 12 && N == 72) return launch_tile<true, 5, 35, 12, 72>(P, smem, s);
-  else if (a.has_trop && L == 34 && S == 90 && N == 72) return launch_tile<true, 5, 34, 90, 72>(P, smem, s);
+  } else if (!a.has_trop && L == 47 && S == 12 && N == 72) return launch_tile<false, 5, 47, 12, 72>(P, s);
+  else if (a.has_trop && L == 35 && S == 12 && N == 72) return launch_tile<true, 5, 35, 12, 72>(P, s);
+  else if (a.has_trop && L == 34 && S == 90 && N == 72) return launch_tile<true, 5, 34, 90, 72>(P, s);
   const int half = ((N / 8) + 1) / 2;
   if (half <= 5)
-    return a.has_trop ? launch_tile<true, 5, 0, 0, 0>(P, smem, s) : launch_tile<false, 5, 0, 0, 0>(P, smem, s);
-  return a.has_trop ? launch_tile<true, 8, 0, 0, 0>(P, smem, s) : launch_tile<false, 8, 0, 0, 0>(P, smem, s);
+    return a.has_trop ? launch_tile<true, 5, 0, 0, 0>(P, s) : launch_tile<false, 5, 0, 0, 0>(P, s);
+  return a.has_trop ? launch_tile<true, 8, 0, 0, 0>(P, s) : launch_tile<false, 8, 0, 0, 0>(P, s);
 }
