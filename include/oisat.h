@@ -99,6 +99,23 @@ int64_t oisat_h_delaunay_swath(const double* h_x, const double* h_y, int64_t n_r
                                int64_t n_cols, int32_t* h_tri, int64_t tri_capacity,
                                int64_t* n_ties, int32_t* path);
 
+/* HOST function: oisat_h_delaunay_swath without its last pass.  h_half receives the twin
+ * half-edge of every triangle edge (3 per triangle, -1 on the hull); *n_ties reports the
+ * exact ties on the hull only, and oisat_near_ties (device) finishes the report from
+ * h_tri / h_half.  *path = 0: the general builder ran instead, *n_ties is complete and
+ * h_half was not written. */
+int64_t oisat_h_delaunay_swath_adj(const double* h_x, const double* h_y, int64_t n_rows,
+                                   int64_t n_cols, int32_t* h_tri, int64_t tri_capacity,
+                                   int32_t* h_half, int64_t* n_ties, int32_t* path);
+
+/* Device part of the tie report: edges whose fourth point lies within Qhull's tolerance of
+ * the circumcircle (2e-14 x max_abs_coord^2 x twice the triangle area; exact co-circular
+ * quadruples included).  tri / half: device copies of the arrays above; px / py: the
+ * pixel coordinates (f32 or f64, widened exactly); *n_ties: device counter (zeroed here). */
+int oisat_near_ties(const int32_t* tri, const int32_t* half, int64_t n_tri, const void* px,
+                    const void* py, int32_t coord_dtype, double max_abs_coord, uint64_t* n_ties,
+                    void* stream);
+
 /* node_tri[f] (caller pre-fills with INT32_MAX) <- lowest index of a triangle that
  * contains mesh node f by scipy's rule (barycentric coordinates within
  * [-eps, 1+eps], eps = 100*DBL_EPSILON); only nodes with keep[f] != 0 are tested.

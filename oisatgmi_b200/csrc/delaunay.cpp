@@ -526,6 +526,47 @@ extern "C" int64_t oisat_h_delaunay_swath(const double* h_x, const double* h_y, 
   return oisat_h_delaunay(h_x, h_y, n_rows * n_cols, h_tri, tri_capacity, n_ties);
 }
 
+// As oisat_h_delaunay_swath, but the near-tie scan (count_near_ties: one pass over every
+// interior edge, ~15% of the builder's time) is left to the device: the twin half-edge of
+// every emitted triangle edge goes to h_half (3 per triangle, -1 on the hull) and
+// *n_ties reports the exact hull ties only; oisat_near_ties finishes the report.
+// *path = 1: h_half is valid.  *path = 0: the lattice builder did not apply, the general
+// builder ran, *n_ties is the complete report and h_half is not written.
+extern "C" int64_t oisat_h_delaunay_swath_adj(const double* h_x, const double* h_y, int64_t n_rows,
+                                              int64_t n_cols, int32_t* h_tri, int64_t tri_capacity,
+                                              int32_t* h_half, int64_t* n_ties, int32_t* path) {
+  if (!h_x || !h_y || !h_tri || !h_half || n_rows < 1 || n_cols < 1 ||
+      n_rows * n_cols > (int64_t)0x3fffffff)
+    return OISAT_E_ARG;
+  LatticeBuilder g;
+  g.x = h_x;
+  g.y = h_y;
+  g.rows = n_rows;
+  g.cols = n_cols;
+  if (g.run() == 0) {
+    // compact numbering of the surviving triangles (emit() skips the former ghosts)
+    std::vector<int32_t> slot((size_t)g.ntri, -1);
+    int64_t m = 0;
+    for (int64_t t = 0; t < g.ntri; ++t)
+      if (g.tri[3 * t] >= 0) slot[(size_t)t] = (int32_t)m++;
+    if (m > tri_capacity) return OISAT_E_ARG;
+    for (int64_t t = 0; t < g.ntri; ++t) {
+      const int32_t u = slot[(size_t)t];
+      if (u < 0) continue;
+      for (int e = 0; e < 3; ++e) {
+        h_tri[3 * u + e] = g.tri[3 * t + e];
+        const int32_t h = g.half[3 * t + e];
+        h_half[3 * u + e] = h < 0 ? -1 : 3 * slot[(size_t)(h / 3)] + h % 3;
+      }
+    }
+    if (n_ties) *n_ties = g.ties;
+    if (path) *path = 1;
+    return m;
+  }
+  if (path) *path = 0;
+  return oisat_h_delaunay(h_x, h_y, n_rows * n_cols, h_tri, tri_capacity, n_ties);
+}
+
 extern "C" int64_t oisat_h_delaunay(const double* h_x, const double* h_y, int64_t n,
                                     int32_t* h_tri, int64_t tri_capacity, int64_t* n_ties) {
   if (!h_x || !h_y || !h_tri || n < 3 || n > (int64_t)0x3fffffff) return OISAT_E_ARG;

@@ -220,9 +220,60 @@ plan_fill_kernel(const int32_t* __restrict__ cells, int64_t n_cells,
   }
 }
 
+// Near ties of a triangulation (the scan of count_near_ties in delaunay.cpp, same
+// expressions in the same order -- both trees are compiled without FMA contraction):
+// one thread per half-edge, the lower-numbered twin tests the quadrilateral.
+template <typename T>
+__global__ void __launch_bounds__(256)
+near_ties_kernel(const int32_t* __restrict__ tri, const int32_t* __restrict__ half, int64_t n_half,
+                 Coords<T> P, double tol, unsigned long long* __restrict__ ties) {
+  const int64_t a64 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (a64 >= n_half) return;
+  const int32_t a = (int32_t)a64;
+  const int32_t b = half[a];
+  if (b < a) return;  // hull edge (-1) or the twin does it
+  const int32_t a0 = a - a % 3, b0 = b - b % 3;
+  const int32_t p0 = tri[a0 + (a + 2) % 3], pr = tri[a], pl = tri[a0 + (a + 1) % 3],
+                p1 = tri[b0 + (b + 2) % 3];
+  const double x0 = P.px(p0), y0 = P.py(p0), xl = P.px(pl), yl = P.py(pl), xr = P.px(pr),
+               yr = P.py(pr), x1 = P.px(p1), y1 = P.py(p1);
+  const double adx = x0 - x1, ady = y0 - y1, bdx = xl - x1, bdy = yl - y1, cdx = xr - x1,
+               cdy = yr - y1;
+  const double det = (adx * adx + ady * ady) * (bdx * cdy - cdx * bdy) +
+                     (bdx * bdx + bdy * bdy) * (cdx * ady - adx * cdy) +
+                     (cdx * cdx + cdy * cdy) * (adx * bdy - bdx * ady);
+  const double area2 = fabs((x0 - xr) * (yl - yr) - (y0 - yr) * (xl - xr));
+  if (fabs(det) <= tol * area2) atomicAdd(ties, 1ull);
+}
+
 }  // namespace oisat
 
 using namespace oisat;
+
+extern "C" int oisat_near_ties(const int32_t* tri, const int32_t* half, int64_t n_tri, const void* px,
+                               const void* py, int32_t coord_dtype, double max_abs_coord,
+                               uint64_t* n_ties, void* stream) {
+  OISAT_CHECK_ARG(n_ties != nullptr, "null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  OISAT_CHECK_CUDA(cudaMemsetAsync(n_ties, 0, sizeof(uint64_t), s));
+  if (n_tri <= 0) return OISAT_OK;
+  OISAT_CHECK_ARG(tri && half && px && py, "null pointer");
+  OISAT_CHECK_ARG(coord_dtype == OISAT_F32 || coord_dtype == OISAT_F64, "coords must be f32/f64");
+  OISAT_CHECK_ARG(3 * n_tri < (int64_t)INT_MAX, "bad extent");
+  const double m2 = max_abs_coord * max_abs_coord;
+  const double tol = 2e-14 * (m2 > 1e-300 ? m2 : 1e-300);
+  const unsigned blocks = (unsigned)ceil_div(3 * n_tri, 256);
+  if (coord_dtype == OISAT_F32)
+    near_ties_kernel<float><<<blocks, 256, 0, s>>>(tri, half, 3 * n_tri,
+                                                   Coords<float>{(const float*)px, (const float*)py},
+                                                   tol, (unsigned long long*)n_ties);
+  else
+    near_ties_kernel<double><<<blocks, 256, 0, s>>>(tri, half, 3 * n_tri,
+                                                    Coords<double>{(const double*)px, (const double*)py},
+                                                    tol, (unsigned long long*)n_ties);
+  OISAT_CHECK_LAUNCH();
+  return OISAT_OK;
+}
 
 extern "C" int oisat_locate(const int32_t* tri, int64_t n_tri, const void* px, const void* py,
                             int32_t coord_dtype, const double* xs, int64_t W, const double* ys,

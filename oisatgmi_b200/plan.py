@@ -296,6 +296,41 @@ def native_delaunay_path(lon, lat):
     return tri[:nt], int(ties.value), int(path.value)
 
 
+def native_delaunay_adj(lon, lat, pinned=False):
+    """Triangulation for builder v1 with the near-tie scan left to the device:
+    (tri, half, n_ties, max_abs_coord).  `half` (twin half-edge of every triangle edge) is
+    None when the general builder ran -- then n_ties is already the complete report."""
+    import ctypes as C
+    import os
+    L = _lib.lib()
+    shape = np.shape(lon)
+    if not (len(shape) == 2 and min(shape) >= 2 and os.environ.get("OISAT_DELAUNAY") != "general"
+            and os.environ.get("OISAT_NEAR_TIES") != "host"):
+        tri, ties = native_delaunay(lon, lat)
+        return tri, None, ties, 0.0
+    x = np.ascontiguousarray(np.asarray(lon, dtype=np.float64).ravel())
+    y = np.ascontiguousarray(np.asarray(lat, dtype=np.float64).ravel())
+    n = x.size
+    if pinned:   # page-locked outputs: their upload does not block the calling thread
+        t = _dev.torch()
+        tri = t.empty((2 * n, 3), dtype=t.int32, pin_memory=True).numpy()
+        half = t.empty((2 * n, 3), dtype=t.int32, pin_memory=True).numpy()
+    else:
+        tri = np.empty((2 * n, 3), dtype=np.int32)
+        half = np.empty((2 * n, 3), dtype=np.int32)
+    ties = C.c_int64(0)
+    path = C.c_int32(0)
+    nt = L.oisat_h_delaunay_swath_adj(x.ctypes.data, y.ctypes.data, shape[0], shape[1],
+                                      tri.ctypes.data, 2 * n, half.ctypes.data, C.byref(ties),
+                                      C.byref(path))
+    if nt <= 0:
+        return None, None, 0, 0.0
+    if not path.value:
+        return tri[:nt], None, int(ties.value), 0.0
+    maxabs = float(max(np.abs(x).max(), np.abs(y).max()))
+    return tri[:nt], half[:nt], int(ties.value), maxabs
+
+
 def locate(tri, qx, qy):
     """Containing simplex and barycentric weights of each query point, evaluated
     the way scipy's LinearNDInterpolator does (qhull._barycentric_coordinates)."""
@@ -353,18 +388,28 @@ def _plan_v0(lon, lat, gplan, keep):
     return GranulePlan(gplan, cells, vert.astype(np.int32), w, keep, builder="v0")
 
 
-def _plan_v1_device(tri_host, lonlat_dev, gplan, keep_dev):
-    """Device part of the v1 plan: point location (K1), per-cell validity, and the
-    stencil fill.  Only the per-cell flags (n_cell bytes) visit the host."""
+def _plan_v1_enqueue(tri_host, lonlat_dev, gplan, keep_dev, half_host=None, maxabs=0.0):
+    """First half of the device part of a v1 plan, queued without waiting for anything:
+    upload of the triangulation, near-tie scan (with `half_host`, native_delaunay_adj),
+    point location (K1), per-cell validity, and the copy of the per-cell flags (n_cell
+    bytes) + tie count to pinned host memory.  Returns the state _plan_v1_finish needs."""
     L = _lib.lib()
     t = _dev.torch()
+    dev = _dev.device()
     lo, la = lonlat_dev
     xs, ys = gplan.dev_axes()
     window, nn_ok = gplan.dev_tables()
-    tri = _dev.to_device(tri_host)
+    s = _dev.stream()
+    tri = t.from_numpy(tri_host).to(dev, non_blocking=True)    # asynchronous when pinned
+    ties_dev = None
+    if half_host is not None:
+        half = t.from_numpy(half_host).to(dev, non_blocking=True)
+        ties_dev = _dev.empty((1,), "int64")
+        _lib.check(L.oisat_near_ties(tri.data_ptr(), half.data_ptr(), tri.shape[0], lo.data_ptr(),
+                                     la.data_ptr(), _dev.dtype_code(lo), float(maxabs),
+                                     ties_dev.data_ptr(), s))
     node_tri = _dev.full((gplan.H * gplan.W,), 2 ** 31 - 1, "int32")
     code = _dev.dtype_code(lo)
-    s = _dev.stream()
     work = _dev.empty((2 * tri.shape[0] + 2,), "int32")
     _lib.check(L.oisat_locate(tri.data_ptr(), tri.shape[0], lo.data_ptr(), la.data_ptr(), code,
                               xs.data_ptr(), gplan.W, ys.data_ptr(), gplan.H, keep_dev.data_ptr(),
@@ -373,18 +418,46 @@ def _plan_v1_device(tri_host, lonlat_dev, gplan, keep_dev):
     ok = _dev.empty((n_cell,), "uint8")
     _lib.check(L.oisat_plan_cells(window.data_ptr(), gplan.nwin, nn_ok.data_ptr(), n_cell,
                                   node_tri.data_ptr(), ok.data_ptr(), s))
-    cells = np.flatnonzero(_dev.to_host(ok))
+    ok_host = t.empty((n_cell,), dtype=t.uint8, pin_memory=True)
+    ok_host.copy_(ok, non_blocking=True)
+    ties_host = None
+    if ties_dev is not None:
+        ties_host = t.empty((1,), dtype=t.int64, pin_memory=True)
+        ties_host.copy_(ties_dev, non_blocking=True)
+    done = t.cuda.Event()
+    done.record()
+    return dict(tri=tri, node_tri=node_tri, ok_host=ok_host, ties_host=ties_host, done=done,
+                lonlat=lonlat_dev, code=code, keep=(tri_host, half_host, work, ok, ties_dev))
+
+
+def _plan_v1_finish(st, gplan):
+    """Second half: waits for ITS flags only, lists the kept cells on the host and queues
+    the stencil fill.  None when the near-tie scan found a tie (the caller takes v0)."""
+    L = _lib.lib()
+    st["done"].synchronize()
+    if st["ties_host"] is not None and int(st["ties_host"][0]) != 0 and _plan_mode() != "v1":
+        return None   # not unique (or inside Qhull's tolerance): Qhull's own answer is needed
+    cells = np.flatnonzero(st["ok_host"].numpy())
+    lo, la = st["lonlat"]
+    xs, ys = gplan.dev_axes()
+    window, _ = gplan.dev_tables()
     n = cells.size
     S = 3 * gplan.nwin
     vert = _dev.empty((n, S), "int32")
     w = _dev.empty((n, S))
     if n:
-        cells_d = _dev.to_device(cells.astype(np.int32))
+        cells_d = _dev.to_device(cells.astype(np.int32), pin=True)
         _lib.check(L.oisat_plan_fill(cells_d.data_ptr(), n, window.data_ptr(), gplan.nwin,
-                                     node_tri.data_ptr(), tri.data_ptr(), lo.data_ptr(),
-                                     la.data_ptr(), code, xs.data_ptr(), gplan.W, ys.data_ptr(), 1,
-                                     vert.data_ptr(), w.data_ptr(), s))
+                                     st["node_tri"].data_ptr(), st["tri"].data_ptr(), lo.data_ptr(),
+                                     la.data_ptr(), st["code"], xs.data_ptr(), gplan.W, ys.data_ptr(), 1,
+                                     vert.data_ptr(), w.data_ptr(), _dev.stream()))
     return GranulePlan(gplan, cells, keep=None, dev_pairs=(vert, w), builder="v1")
+
+
+def _plan_v1_device(tri_host, lonlat_dev, gplan, keep_dev, half_host=None, maxabs=0.0):
+    """Device part of the v1 plan for one granule (enqueue + finish)."""
+    return _plan_v1_finish(_plan_v1_enqueue(tri_host, lonlat_dev, gplan, keep_dev, half_host, maxabs),
+                           gplan)
 
 
 def triangulable(lon, lat) -> bool:
@@ -471,11 +544,11 @@ def granule_plan(lon, lat, gplan: GridPlan, radius: float, lonlat_dev=None, cach
         keep_dev = distance_mask(lonlat_dev[0], lonlat_dev[1], gplan, radius)  # async
         use_v1 = gplan.upscale and _plan_mode() != "v0"
         if use_v1:
-            tri, ties = native_delaunay(lon, lat)   # runs while K0 is in flight
+            tri, half, ties, maxabs = native_delaunay_adj(lon, lat)   # runs while K0 is in flight
             if tri is None:
                 return None
             if ties == 0 or _plan_mode() == "v1":
-                plan = _plan_v1_device(tri, lonlat_dev, gplan, keep_dev)
+                plan = _plan_v1_device(tri, lonlat_dev, gplan, keep_dev, half, maxabs)
         if plan is None:
             plan = _plan_v0(lon, lat, gplan, _dev.to_host(keep_dev).astype(bool))
     if plan is not None and cache:
@@ -512,17 +585,25 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
     workers = max(1, min(n, workers))
     from concurrent.futures import as_completed
     out = [None] * n
+    pending = []
     with ThreadPoolExecutor(workers) as ex:
-        # the device part of a granule runs as soon as ITS triangulation is done,
-        # while the others are still on the pool
-        futures = {ex.submit(native_delaunay, lons[i], lats[i]): i for i in range(n)}
+        # The first half of a granule's device part (uploads, near-tie scan, point location,
+        # flags to pinned memory) is queued as soon as ITS triangulation is done, while the
+        # others are still on the pool -- and without waiting for the GPU: with a
+        # synchronisation per granule the 15 device parts of a day (2 ms each) ran one after
+        # the other behind the slowest triangulation.
+        futures = {ex.submit(native_delaunay_adj, lons[i], lats[i], True): i for i in range(n)}
         for fut in as_completed(futures):
             i = futures[fut]
-            tri, ties = fut.result()
+            tri, half, ties, maxabs = fut.result()
             if tri is None:
                 continue
             if ties == 0 or _plan_mode() == "v1":
-                out[i] = _plan_v1_device(tri, lonlat_dev[i], gplan, keeps[i])
+                pending.append((i, _plan_v1_enqueue(tri, lonlat_dev[i], gplan, keeps[i], half, maxabs)))
             else:
                 out[i] = _plan_v0(lons[i], lats[i], gplan, _dev.to_host(keeps[i]).astype(bool))
+    for i, st in pending:     # second half: kept cells on the host, stencil fill queued
+        out[i] = _plan_v1_finish(st, gplan)
+        if out[i] is None:
+            out[i] = _plan_v0(lons[i], lats[i], gplan, _dev.to_host(keeps[i]).astype(bool))
     return out

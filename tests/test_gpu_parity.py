@@ -264,3 +264,26 @@ def test_output_fields_are_bit_exact():
             assert got[k].dtype == np.float32 and np.array_equal(got[k], a, equal_nan=True), k
     s = got["scaling_factor"]
     assert np.all(s[0, :4] == 1.0)          # x/0, x/NaN, x/inf and 0/x all become 1
+
+
+def test_near_tie_scan_on_the_device_equals_the_host_scan():
+    """oisat_near_ties (device) == count_near_ties inside oisat_h_delaunay_swath (host) on
+    a swath without ties, an exactly regular lattice (ties everywhere) and a half-regular
+    one; float32 and float64 coordinates."""
+    import ctypes as C  # noqa: F401
+    from oisatgmi_b200 import _dev, _lib, plan
+    from test_host_logic import _adjacency_cases
+    L = _lib.lib()
+    for name, lon, lat in _adjacency_cases():
+        for dt in (np.float64, np.float32):
+            lo, la = lon.astype(dt), lat.astype(dt)
+            tri, half, hull_ties, maxabs = plan.native_delaunay_adj(lo, la)
+            _, total, path = plan.native_delaunay_path(lo, la)
+            assert path == 1 and half is not None
+            d_tri, d_half = _dev.to_device(tri), _dev.to_device(half)
+            d_lo, d_la = _dev.to_device(lo.ravel()), _dev.to_device(la.ravel())
+            out = _dev.empty((1,), "int64")
+            _lib.check(L.oisat_near_ties(d_tri.data_ptr(), d_half.data_ptr(), tri.shape[0],
+                                         d_lo.data_ptr(), d_la.data_ptr(), _dev.dtype_code(d_lo),
+                                         float(maxabs), out.data_ptr(), _dev.stream()))
+            assert hull_ties + int(out.item()) == total, (name, dt)

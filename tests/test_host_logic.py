@@ -334,3 +334,52 @@ def test_lattice_delaunay_randomised_against_qhull():
                 assert gen_ties == 0 and _tri_set(tri) == _tri_set(gen), (trial, rows, cols)
             checked += 1
     assert checked >= 40
+
+
+def _near_ties_numpy(x, y, tri, half):
+    """count_near_ties (csrc/delaunay.cpp) restated with numpy from (tri, half)."""
+    x = np.asarray(x, np.float64).ravel()
+    y = np.asarray(y, np.float64).ravel()
+    t = tri.ravel()
+    h = half.ravel()
+    a = np.flatnonzero(h > np.arange(h.size))
+    b = h[a]
+    a0, b0 = a - a % 3, b - b % 3
+    p0, pr, pl, p1 = t[a0 + (a + 2) % 3], t[a], t[a0 + (a + 1) % 3], t[b0 + (b + 2) % 3]
+    adx, ady, bdx, bdy, cdx, cdy = x[p0] - x[p1], y[p0] - y[p1], x[pl] - x[p1], y[pl] - y[p1], \
+        x[pr] - x[p1], y[pr] - y[p1]
+    det = (adx * adx + ady * ady) * (bdx * cdy - cdx * bdy) + \
+        (bdx * bdx + bdy * bdy) * (cdx * ady - adx * cdy) + \
+        (cdx * cdx + cdy * cdy) * (adx * bdy - bdx * ady)
+    area2 = np.abs((x[p0] - x[pr]) * (y[pl] - y[pr]) - (y[p0] - y[pr]) * (x[pl] - x[pr]))
+    m = max(np.abs(x).max(), np.abs(y).max())
+    return int((np.abs(det) <= 2e-14 * max(m * m, 1e-300) * area2).sum())
+
+
+def _adjacency_cases():
+    rng = np.random.default_rng(9)
+    lat, lon = synth.swath_geolocation(120, 30, rng=rng, **synth.regional_geo(cases.REGION))
+    gx, gy = np.meshgrid(np.arange(13.0), np.arange(9.0))
+    return [("swath", lon.astype(np.float64), lat.astype(np.float64)),
+            ("regular", gx, gy),
+            ("half-regular", gx + np.where(gy > 4, 0.17 * np.sin(gx), 0.0), gy)]
+
+
+def test_delaunay_adjacency_output_is_the_twin_map_and_carries_the_tie_report():
+    """oisat_h_delaunay_swath_adj: same triangles as oisat_h_delaunay_swath, `half` pairs
+    every interior edge with its reversed twin, and hull ties + the near-tie scan over
+    (tri, half) equal the complete report of the one-call form."""
+    for name, lon, lat in _adjacency_cases():
+        tri, half, hull_ties, maxabs = plan.native_delaunay_adj(lon, lat)
+        ref, ties_ref, path = plan.native_delaunay_path(lon, lat)
+        assert path == 1 and half is not None, name
+        assert np.array_equal(tri, ref), name
+        t, h = tri.ravel(), half.ravel()
+        inner = np.flatnonzero(h >= 0)
+        assert np.array_equal(h[h[inner]], inner), name
+        nxt = lambda e: e - e % 3 + (e + 1) % 3   # noqa: E731
+        assert np.array_equal(t[inner], t[nxt(h[inner])]) and np.array_equal(t[nxt(inner)], t[h[inner]])
+        assert (h < 0).sum() >= 3, name
+        assert maxabs == max(np.abs(lon).max(), np.abs(lat).max())
+        assert hull_ties + _near_ties_numpy(lon, lat, tri, half) == ties_ref, name
+    assert ties_ref > 0   # the last case does have ties
