@@ -437,7 +437,7 @@ def _plan_v1_finish(st, gplan):
     st["done"].synchronize()
     if st["ties_host"] is not None and int(st["ties_host"][0]) != 0 and _plan_mode() != "v1":
         return None   # not unique (or inside Qhull's tolerance): Qhull's own answer is needed
-    cells = np.flatnonzero(st["ok_host"].numpy())
+    cells = np.flatnonzero(st["ok_host"].numpy().view(np.bool_))   # flags are 0 / 1
     lo, la = st["lonlat"]
     xs, ys = gplan.dev_axes()
     window, _ = gplan.dev_tables()
@@ -592,6 +592,9 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
         # others are still on the pool -- and without waiting for the GPU: with a
         # synchronisation per granule the 15 device parts of a day (2 ms each) ran one after
         # the other behind the slowest triangulation.
+        import time as _time
+        trace = [] if os.environ.get("OISAT_PLAN_TRACE") == "1" else None
+        t_start = _time.perf_counter()
         futures = {ex.submit(native_delaunay_adj, lons[i], lats[i], True): i for i in range(n)}
         for fut in as_completed(futures):
             i = futures[fut]
@@ -599,11 +602,20 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
             if tri is None:
                 continue
             if ties == 0 or _plan_mode() == "v1":
+                t_a = _time.perf_counter()
                 pending.append((i, _plan_v1_enqueue(tri, lonlat_dev[i], gplan, keeps[i], half, maxabs)))
+                if trace is not None:
+                    trace.append("%d:%.0f+%.1f" % (i, (t_a - t_start) * 1e3, (_time.perf_counter() - t_a) * 1e3))
             else:
                 out[i] = _plan_v0(lons[i], lats[i], gplan, _dev.to_host(keeps[i]).astype(bool))
+    t_pool = _time.perf_counter()
     for i, st in pending:     # second half: kept cells on the host, stencil fill queued
         out[i] = _plan_v1_finish(st, gplan)
         if out[i] is None:
             out[i] = _plan_v0(lons[i], lats[i], gplan, _dev.to_host(keeps[i]).astype(bool))
+    if trace is not None:
+        import sys
+        print("granule_plans trace: pool %.1f ms, finish %.1f ms; (granule:ready+enqueue ms) %s" %
+              ((t_pool - t_start) * 1e3, (_time.perf_counter() - t_pool) * 1e3, " ".join(trace)),
+              file=sys.stderr, flush=True)
     return out

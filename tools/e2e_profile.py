@@ -36,14 +36,22 @@ def main():
         p = new_pipe()
         if ctm_dev is not None:
             p._ctm_dev = ctm_dev
+        pra = cProfile.Profile()
+        if os.environ.get("OISAT_PLAN_TRACE") != "1":
+            pra.enable()
         p.add_day(day, hosts=hosts)
+        ta = time.perf_counter()
         torch.cuda.synchronize()
+        pra.disable()
         t1 = time.perf_counter()
         pr.enable()
         p.allocate()
         torch.cuda.synchronize()
         pr.disable()
         t2 = time.perf_counter()
+        if it == 2:
+            print("add_day returned after %.1f ms, drained after %.1f ms" % ((ta - t0) * 1e3, (t1 - t0) * 1e3))
+            pstats.Stats(pra).sort_stats("cumulative").print_stats(25)
         out = p.results_to_host(p.run())
         torch.cuda.synchronize()
         t3 = time.perf_counter()
