@@ -49,7 +49,35 @@ CASES = {
     # gridded granule stays on the mesh (ctm_upscaled_needed) and amf_recal brings the model's
     # pressure and partial column to it with _upscaler, level by level
     "omi_no2_fine_model": ("OMI_NO2", 0.25, 0.0, (15, 16), 200, 60, 1),
+    # satellite pressure profiles that are NOT strictly monotone, which scipy's interp1d
+    # (assume_sorted=False, amf_recal.py:103-107) argsorts: exact ties and level swaps over
+    # whole blocks of scan lines (so the GRIDDED profile has them too), NaN pressures and NaN
+    # scattering weights at scattered pixels -- the slow path of the vertical kernels
+    "omi_no2_kinked": ("OMI_NO2", 0.25, 0.0, (17, 18), 260, 60, 1),
 }
+KINKED = ("omi_no2_kinked",)
+
+
+def kink_profiles(granules):
+    """Deterministic damage to the pressure / scattering-weight profiles (in place)."""
+    for gi, g in enumerate(granules):
+        rng = np.random.default_rng(100 + gi)
+        p = g.pressure_mid
+        sw = g.scattering_weights
+        L, nt, nxt = p.shape
+        k0, k1 = 5 + gi, 12 + 2 * gi
+        p[k0 + 1, 40:70, :] = p[k0, 40:70, :]                       # ties
+        a = p[k1, 110:140, :].copy()                                  # a swap two levels apart
+        p[k1, 110:140, :] = p[k1 + 2, 110:140, :]
+        p[k1 + 2, 110:140, :] = a
+        p[L - 1, 180:200, :] = p[L - 2, 180:200, :] * np.float16(1.5)   # top level out of order
+        for arr, frac in ((p, 0.004), (sw, 0.004)):                   # scattered NaNs
+            idx = rng.choice(nt * nxt, size=max(1, int(frac * nt * nxt)), replace=False)
+            lev = rng.integers(0, L, size=idx.size)
+            arr[lev, idx // nxt, idx % nxt] = np.nan
+    return granules
+
+
 REGION_FINE = (36.0, 46.0, -98.0, -84.0)
 FINE_MODEL_SPACING = {"omi_no2_fine_model": 0.125}   # degrees, both directions
 
@@ -64,8 +92,11 @@ def amf_case(name):
         return dict(product=product, grid_size=gs, flag_thresh=thr, kind=kind,
                     granules=amf_granules(product, seeds, nt, nxt, region=REGION_FINE), coords=c,
                     ctm=model, sensor=product.split("_")[0], gas=product.split("_")[1])
+    granules = amf_granules(product, seeds, nt, nxt)
+    if name in KINKED:
+        kink_profiles(granules)
     return dict(product=product, grid_size=gs, flag_thresh=thr, kind=kind,
-                granules=amf_granules(product, seeds, nt, nxt), coords=coords(), ctm=ctm(),
+                granules=granules, coords=coords(), ctm=ctm(),
                 sensor=product.split("_")[0], gas=product.split("_")[1])
 
 

@@ -140,7 +140,8 @@ def test_no_kernel_writes_outside_its_buffers(name, monkeypatch):
         assert_field(res2[k], res[k], k, rtol=1e-12)
 
 
-@pytest.mark.parametrize("name", ["omi_hcho", "omi_no2", "tropomi_no2", "tropomi_nearest"])
+@pytest.mark.parametrize("name", ["omi_hcho", "omi_no2", "tropomi_no2", "tropomi_nearest",
+                                  "omi_no2_kinked"])
 def test_tile_form_is_bit_identical_to_split_form(name, monkeypatch):
     """oisat_fused_amf_tile (one launch, gridded columns in shared memory, bisection) and
     oisat_fused_amf_split (two launches, row buffer, merge walk) evaluate the same
@@ -162,7 +163,7 @@ def test_tile_form_is_bit_identical_to_split_form(name, monkeypatch):
             assert np.array_equal(res_t[k], res_s[k], equal_nan=True), k
 
 
-@pytest.mark.parametrize("name", ["omi_hcho", "omi_no2", "tropomi_no2"])
+@pytest.mark.parametrize("name", ["omi_hcho", "omi_no2", "tropomi_no2", "omi_no2_kinked"])
 def test_tile_form_generic_build_equals_specialised_build(name, monkeypatch):
     """The BASELINE products run a build of the tile kernel with their level counts and
     stencil size as compile-time constants; OISAT_TILE_GENERIC=1 forces the run-time build
