@@ -114,7 +114,16 @@ int64_t oisat_h_delaunay_swath_adj(const double* h_x, const double* h_y, int64_t
  * pixel coordinates (f32 or f64, widened exactly); *n_ties: device counter (zeroed here). */
 int oisat_near_ties(const int32_t* tri, const int32_t* half, int64_t n_tri, const void* px,
                     const void* py, int32_t coord_dtype, double max_abs_coord, uint64_t* n_ties,
-                    void* stream);
+                    uint8_t* tri_flag, void* stream);
+
+/* tri_flag (may be NULL; n_tri bytes, zeroed by the caller) receives 1 for both triangles of
+ * every tied edge: Qhull's triangulation can differ from the exact one only inside those
+ * quadrilaterals (it merges them into one facet and re-splits it its own way).
+ * oisat_flagged_nodes counts the mesh nodes oisat_locate placed in a flagged triangle
+ * (node_tri[f] != INT32_MAX and tri_flag[node_tri[f]]): when there is none, the stencils do
+ * not depend on how the tied quadrilaterals are split and the exact triangulation serves. */
+int oisat_flagged_nodes(const int32_t* node_tri, int64_t n_nodes, const uint8_t* tri_flag,
+                        uint64_t* n_flagged, void* stream);
 
 /* node_tri[f] (caller pre-fills with INT32_MAX) <- lowest index of a triangle that
  * contains mesh node f by scipy's rule (barycentric coordinates within

@@ -59,7 +59,8 @@ PROTOTYPES = {
     "oisat_h_delaunay": (i64, [vp, vp, i64, vp, i64, C.POINTER(i64)]),
     "oisat_h_delaunay_swath": (i64, [vp, vp, i64, i64, vp, i64, C.POINTER(i64), C.POINTER(i32)]),
     "oisat_h_delaunay_swath_adj": (i64, [vp, vp, i64, i64, vp, i64, vp, C.POINTER(i64), C.POINTER(i32)]),
-    "oisat_near_ties": (C.c_int, [vp, vp, i64, vp, vp, i32, f64, vp, vp]),
+    "oisat_near_ties": (C.c_int, [vp, vp, i64, vp, vp, i32, f64, vp, vp, vp]),
+    "oisat_flagged_nodes": (C.c_int, [vp, i64, vp, vp, vp]),
     "oisat_locate": (C.c_int, [vp, i64, vp, vp, i32, vp, i64, vp, i64, vp, vp, vp, vp]),
     "oisat_plan_cells": (C.c_int, [vp, i32, vp, i64, vp, vp, vp]),
     "oisat_plan_fill": (C.c_int, [vp, i64, vp, i32, vp, vp, vp, vp, i32, vp, i64, vp, i32, vp, vp,

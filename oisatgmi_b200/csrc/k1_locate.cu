@@ -226,7 +226,8 @@ plan_fill_kernel(const int32_t* __restrict__ cells, int64_t n_cells,
 template <typename T>
 __global__ void __launch_bounds__(256)
 near_ties_kernel(const int32_t* __restrict__ tri, const int32_t* __restrict__ half, int64_t n_half,
-                 Coords<T> P, double tol, unsigned long long* __restrict__ ties) {
+                 Coords<T> P, double tol, unsigned long long* __restrict__ ties,
+                 uint8_t* __restrict__ tri_flag) {
   const int64_t a64 = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (a64 >= n_half) return;
   const int32_t a = (int32_t)a64;
@@ -243,16 +244,46 @@ near_ties_kernel(const int32_t* __restrict__ tri, const int32_t* __restrict__ ha
                      (bdx * bdx + bdy * bdy) * (cdx * ady - adx * cdy) +
                      (cdx * cdx + cdy * cdy) * (adx * bdy - bdx * ady);
   const double area2 = fabs((x0 - xr) * (yl - yr) - (y0 - yr) * (xl - xr));
-  if (fabs(det) <= tol * area2) atomicAdd(ties, 1ull);
+  if (fabs(det) <= tol * area2) {
+    atomicAdd(ties, 1ull);
+    if (tri_flag) {   // both triangles of the quadrilateral: Qhull may split it the other way
+      tri_flag[a / 3] = 1;
+      tri_flag[b / 3] = 1;
+    }
+  }
+}
+
+// mesh nodes that K1 placed in a triangle next to a (near-)tied edge: the only nodes whose
+// stencil could differ from the one Qhull's triangulation gives
+__global__ void __launch_bounds__(256)
+flagged_nodes_kernel(const int32_t* __restrict__ node_tri, int64_t n_nodes,
+                     const uint8_t* __restrict__ tri_flag, unsigned long long* __restrict__ count) {
+  const int64_t f = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (f >= n_nodes) return;
+  const int32_t t = node_tri[f];
+  if (t != INT_MAX && tri_flag[t]) atomicAdd(count, 1ull);
 }
 
 }  // namespace oisat
 
 using namespace oisat;
 
+extern "C" int oisat_flagged_nodes(const int32_t* node_tri, int64_t n_nodes, const uint8_t* tri_flag,
+                                   uint64_t* n_flagged, void* stream) {
+  OISAT_CHECK_ARG(n_flagged != nullptr, "null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  OISAT_CHECK_CUDA(cudaMemsetAsync(n_flagged, 0, sizeof(uint64_t), s));
+  if (n_nodes <= 0) return OISAT_OK;
+  OISAT_CHECK_ARG(node_tri && tri_flag, "null pointer");
+  flagged_nodes_kernel<<<(unsigned)ceil_div(n_nodes, 256), 256, 0, s>>>(
+      node_tri, n_nodes, tri_flag, (unsigned long long*)n_flagged);
+  OISAT_CHECK_LAUNCH();
+  return OISAT_OK;
+}
+
 extern "C" int oisat_near_ties(const int32_t* tri, const int32_t* half, int64_t n_tri, const void* px,
                                const void* py, int32_t coord_dtype, double max_abs_coord,
-                               uint64_t* n_ties, void* stream) {
+                               uint64_t* n_ties, uint8_t* tri_flag, void* stream) {
   OISAT_CHECK_ARG(n_ties != nullptr, "null pointer");
   cudaStream_t s = (cudaStream_t)stream;
   OISAT_CHECK_CUDA(cudaMemsetAsync(n_ties, 0, sizeof(uint64_t), s));
@@ -266,11 +297,11 @@ extern "C" int oisat_near_ties(const int32_t* tri, const int32_t* half, int64_t 
   if (coord_dtype == OISAT_F32)
     near_ties_kernel<float><<<blocks, 256, 0, s>>>(tri, half, 3 * n_tri,
                                                    Coords<float>{(const float*)px, (const float*)py},
-                                                   tol, (unsigned long long*)n_ties);
+                                                   tol, (unsigned long long*)n_ties, tri_flag);
   else
     near_ties_kernel<double><<<blocks, 256, 0, s>>>(tri, half, 3 * n_tri,
                                                     Coords<double>{(const double*)px, (const double*)py},
-                                                    tol, (unsigned long long*)n_ties);
+                                                    tol, (unsigned long long*)n_ties, tri_flag);
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
 }

@@ -401,19 +401,23 @@ def _plan_v1_enqueue(tri_host, lonlat_dev, gplan, keep_dev, half_host=None, maxa
     window, nn_ok = gplan.dev_tables()
     s = _dev.stream()
     tri = t.from_numpy(tri_host).to(dev, non_blocking=True)    # asynchronous when pinned
-    ties_dev = None
+    ties_dev = tri_flag = None
     if half_host is not None:
         half = t.from_numpy(half_host).to(dev, non_blocking=True)
-        ties_dev = _dev.empty((1,), "int64")
+        ties_dev = _dev.empty((2,), "int64")     # [near ties, kept nodes inside tied quadrilaterals]
+        tri_flag = _dev.zeros((tri.shape[0],), "uint8")
         _lib.check(L.oisat_near_ties(tri.data_ptr(), half.data_ptr(), tri.shape[0], lo.data_ptr(),
                                      la.data_ptr(), _dev.dtype_code(lo), float(maxabs),
-                                     ties_dev.data_ptr(), s))
+                                     ties_dev.data_ptr(), tri_flag.data_ptr(), s))
     node_tri = _dev.full((gplan.H * gplan.W,), 2 ** 31 - 1, "int32")
     code = _dev.dtype_code(lo)
     work = _dev.empty((2 * tri.shape[0] + 2,), "int32")
     _lib.check(L.oisat_locate(tri.data_ptr(), tri.shape[0], lo.data_ptr(), la.data_ptr(), code,
                               xs.data_ptr(), gplan.W, ys.data_ptr(), gplan.H, keep_dev.data_ptr(),
                               node_tri.data_ptr(), work.data_ptr(), s))
+    if tri_flag is not None:
+        _lib.check(L.oisat_flagged_nodes(node_tri.data_ptr(), gplan.H * gplan.W, tri_flag.data_ptr(),
+                                         ties_dev[1:].data_ptr(), s))
     n_cell = int(np.prod(gplan.out_shape))
     ok = _dev.empty((n_cell,), "uint8")
     _lib.check(L.oisat_plan_cells(window.data_ptr(), gplan.nwin, nn_ok.data_ptr(), n_cell,
@@ -422,12 +426,12 @@ def _plan_v1_enqueue(tri_host, lonlat_dev, gplan, keep_dev, half_host=None, maxa
     ok_host.copy_(ok, non_blocking=True)
     ties_host = None
     if ties_dev is not None:
-        ties_host = t.empty((1,), dtype=t.int64, pin_memory=True)
+        ties_host = t.empty((2,), dtype=t.int64, pin_memory=True)
         ties_host.copy_(ties_dev, non_blocking=True)
     done = t.cuda.Event()
     done.record()
     return dict(tri=tri, node_tri=node_tri, ok_host=ok_host, ties_host=ties_host, done=done,
-                lonlat=lonlat_dev, code=code, keep=(tri_host, half_host, work, ok, ties_dev))
+                lonlat=lonlat_dev, code=code, keep=(tri_host, half_host, work, ok, ties_dev, tri_flag))
 
 
 def _plan_v1_finish(st, gplan):
@@ -435,8 +439,15 @@ def _plan_v1_finish(st, gplan):
     the stencil fill.  None when the near-tie scan found a tie (the caller takes v0)."""
     L = _lib.lib()
     st["done"].synchronize()
-    if st["ties_host"] is not None and int(st["ties_host"][0]) != 0 and _plan_mode() != "v1":
-        return None   # not unique (or inside Qhull's tolerance): Qhull's own answer is needed
+    near_ties = affected = 0
+    if st["ties_host"] is not None:
+        near_ties, affected = int(st["ties_host"][0]), int(st["ties_host"][1])
+    if affected != 0 and _plan_mode() != "v1":
+        # a kept mesh node lies in a quadrilateral that is not uniquely split (or is inside
+        # Qhull's tolerance): Qhull's own answer is needed.  Ties whose quadrilaterals hold no
+        # kept node (the usual case for an isolated near-tie: a pixel quadrilateral is smaller
+        # than the mesh spacing) cannot change any stencil and are accepted.
+        return None
     cells = np.flatnonzero(st["ok_host"].numpy().view(np.bool_))   # flags are 0 / 1
     lo, la = st["lonlat"]
     xs, ys = gplan.dev_axes()
@@ -451,7 +462,9 @@ def _plan_v1_finish(st, gplan):
                                      st["node_tri"].data_ptr(), st["tri"].data_ptr(), lo.data_ptr(),
                                      la.data_ptr(), st["code"], xs.data_ptr(), gplan.W, ys.data_ptr(), 1,
                                      vert.data_ptr(), w.data_ptr(), _dev.stream()))
-    return GranulePlan(gplan, cells, keep=None, dev_pairs=(vert, w), builder="v1")
+    plan = GranulePlan(gplan, cells, keep=None, dev_pairs=(vert, w), builder="v1")
+    plan.near_ties = near_ties
+    return plan
 
 
 def _plan_v1_device(tri_host, lonlat_dev, gplan, keep_dev, half_host=None, maxabs=0.0):

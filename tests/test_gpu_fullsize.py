@@ -97,3 +97,30 @@ def test_tropomi_scale_plan_builders_agree(monkeypatch):
     v0 = np.sort(p0.vert.reshape(S // 3, 3, n), axis=1)
     v1 = np.sort(p1.vert.reshape(S // 3, 3, n), axis=1)
     assert np.array_equal(v0, v1)
+
+
+def test_tropomi_scale_isolated_near_tie_does_not_need_qhull(monkeypatch):
+    """One edge of this 5.6 M-edge triangulation is inside Qhull's tolerance of a
+    co-circular quadrilateral.  No kept mesh node lies in that quadrilateral (a pixel
+    quadrilateral is smaller than the mesh spacing), so no stencil depends on how it is
+    split: builder v1 keeps the exact triangulation (before, the whole granule went back to
+    Qhull + scipy's walk, ~20 s) -- and the plan equals the one built on Qhull's answer."""
+    from oisatgmi_b200 import plan as _plan
+    rng = np.random.default_rng(501)
+    lat, lon = synth.swath_geolocation(4172, 450, rng=rng, node_lon_deg=150.0 - 360.0 / 14.6,
+                                       alt_km=824.0, half_fov_deg=54.0)
+    _, ties, path = _plan.native_delaunay_path(lon, lat)
+    assert path == 1 and ties >= 1          # the host's complete report sees the tie
+    gpl = _plan.grid_plan(synth.ctm_coordinates(None), 0.10)
+    monkeypatch.setenv("OISAT_PLAN", "auto")
+    p1 = _plan.granule_plan(lon, lat, gpl, 0.2, cache=False)
+    assert p1.builder == "v1" and p1.near_ties == ties
+    monkeypatch.setenv("OISAT_PLAN", "v0")
+    p0 = _plan.granule_plan(lon, lat, gpl, 0.2, cache=False)
+    assert p0.builder == "v0"
+    assert np.array_equal(p0.cells, p1.cells)
+    S, n = p0.vert.shape
+    assert np.array_equal(np.sort(p0.vert.reshape(S // 3, 3, n), axis=1),
+                          np.sort(p1.vert.reshape(S // 3, 3, n), axis=1))
+    assert np.allclose(np.sort(p0.w.reshape(S // 3, 3, n), axis=1),
+                       np.sort(p1.w.reshape(S // 3, 3, n), axis=1), rtol=0, atol=1e-9)

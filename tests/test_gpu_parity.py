@@ -283,7 +283,18 @@ def test_near_tie_scan_on_the_device_equals_the_host_scan():
             d_tri, d_half = _dev.to_device(tri), _dev.to_device(half)
             d_lo, d_la = _dev.to_device(lo.ravel()), _dev.to_device(la.ravel())
             out = _dev.empty((1,), "int64")
+            flag = _dev.zeros((tri.shape[0],), "uint8")
             _lib.check(L.oisat_near_ties(d_tri.data_ptr(), d_half.data_ptr(), tri.shape[0],
                                          d_lo.data_ptr(), d_la.data_ptr(), _dev.dtype_code(d_lo),
-                                         float(maxabs), out.data_ptr(), _dev.stream()))
+                                         float(maxabs), out.data_ptr(), flag.data_ptr(), _dev.stream()))
             assert hull_ties + int(out.item()) == total, (name, dt)
+            n_flag = int(flag.sum().item())
+            assert (n_flag == 0) == (int(out.item()) == 0) and n_flag <= 2 * int(out.item())
+            # nodes "located" in flagged triangles are counted; INT32_MAX = not located
+            node_tri = _dev.full((tri.shape[0] + 5,), 2 ** 31 - 1, "int32")
+            node_tri[:tri.shape[0]] = _dev.torch().arange(tri.shape[0], dtype=_dev.torch().int32,
+                                                          device=node_tri.device)
+            cnt = _dev.empty((1,), "int64")
+            _lib.check(L.oisat_flagged_nodes(node_tri.data_ptr(), node_tri.numel(), flag.data_ptr(),
+                                             cnt.data_ptr(), _dev.stream()))
+            assert int(cnt.item()) == n_flag
