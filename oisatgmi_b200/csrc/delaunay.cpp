@@ -147,7 +147,7 @@ int orient_exact(double ax, double ay, double bx, double by, double cx, double c
 }
 
 // > 0 when a, b, c are in counter-clockwise order
-int orient2d(double ax, double ay, double bx, double by, double cx, double cy) {
+__attribute__((always_inline)) inline int orient2d(double ax, double ay, double bx, double by, double cx, double cy) {
   const double l = (ax - cx) * (by - cy);
   const double r = (ay - cy) * (bx - cx);
   const double det = l - r;
@@ -156,7 +156,7 @@ int orient2d(double ax, double ay, double bx, double by, double cx, double cy) {
   return orient_exact(ax, ay, bx, by, cx, cy);
 }
 
-int incircle_exact(double ax, double ay, double bx, double by, double cx, double cy, double dx,
+__attribute__((noinline)) int incircle_exact(double ax, double ay, double bx, double by, double cx, double cy, double dx,
                    double dy) {
   static thread_local Expansion adx, ady, bdx, bdy, cdx, cdy, t0, t1, t2, al, bl, cl, ab, bc, ca,
       s0, s1, det;
@@ -190,7 +190,7 @@ int incircle_exact(double ax, double ay, double bx, double by, double cx, double
 }
 
 // > 0 when d lies inside the circle through a, b, c (a, b, c counter-clockwise)
-int incircle(double ax, double ay, double bx, double by, double cx, double cy, double dx,
+__attribute__((always_inline)) inline int incircle(double ax, double ay, double bx, double by, double cx, double cy, double dx,
              double dy) {
   const double adx = ax - dx, ady = ay - dy, bdx = bx - dx, bdy = by - dy, cdx = cx - dx,
                cdy = cy - dy;
