@@ -313,6 +313,18 @@ int oisat_oi_apply(const double* xa, const double* y, const double* Sa, const do
                    int64_t n, double factor, double* xb, double* ak, double* inc, double* err,
                    void* stream);
 
+/* The knee of the (factor, mean AK) curve on the device (Kneedle as the reference uses it,
+ * optimal_interpolation.py:37-41: concave, increasing, S = 1, first knee; index 0 when there
+ * is none) from the sums / counts of oisat_oi_sweep: *pick (int32) and *factor (the chosen
+ * factor) are device outputs, means (may be NULL) receives the n_factors nanmeans.
+ * oisat_oi_apply_dev is oisat_oi_apply with the factor read from device memory, so that
+ * sweep -> knee -> update needs no host round trip. */
+int oisat_oi_knee(const double* h_factors, int32_t n_factors, const double* sums,
+                  const double* counts, int32_t* pick, double* factor, double* means, void* stream);
+int oisat_oi_apply_dev(const double* xa, const double* y, const double* Sa, const double* So,
+                       int64_t n, const double* factor, double* xb, double* ak, double* inc,
+                       double* err, void* stream);
+
 /* ---- K8: the data side of driver.write_to_nc (driver.py:156-227) ------------------
  * out: float32 [9][n] in the order the reference stores its variables: sat_averaged_vcd,
  * ctm_averaged_vcd_prior, ctm_averaged_vcd_posterior, sat_averaged_error, ak_OI, error_OI,

@@ -89,6 +89,8 @@ PROTOTYPES = {
     "oisat_oi_sweep_workspace": (i64, [i64, i32]),
     "oisat_oi_sweep": (C.c_int, [vp, vp, i64, C.POINTER(f64), i32, vp, vp, vp, i64, vp]),
     "oisat_oi_apply": (C.c_int, [vp, vp, vp, vp, i64, f64, vp, vp, vp, vp, vp]),
+    "oisat_oi_knee": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp]),
+    "oisat_oi_apply_dev": (C.c_int, [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]),
     "oisat_output_fields": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "oisat_pack_record_halfs": (i64, [i32, i32]),
     "oisat_pack_granule": (C.c_int, [vp, vp, i32, vp, vp, vp, i64, vp, vp]),

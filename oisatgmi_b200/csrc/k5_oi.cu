@@ -270,6 +270,140 @@ extern "C" int oisat_oi_sweep(const double* Sa, const double* So, int64_t n,
   return OISAT_OK;
 }
 
+// ---------------------------------------------------------------- knee ----
+// The knee of the (factor, nanmean(AK_r)) curve on the device: the Kneedle algorithm
+// (Satopaa et al., 2011) for the one configuration the reference uses -- concave,
+// increasing, S = 1, first knee (optimal_interpolation.py:37-41; kneed 0.8.x, restated in
+// oisatgmi_b200/kneedle.py, whose every numpy expression is repeated here in the same
+// order: normalisation by min/max, difference curve, argrelextrema with clipped ends, the
+// threshold from np.diff(xn).mean() -- numpy's pairwise sum for n < 128 -- and the scan).
+// One thread, ~100 points: this is control flow, moved here so that the month step has no
+// host round trip between the sweep and the update.
+namespace oisat {
+struct FactorList {
+  double f[kMaxFactors];
+};
+
+__device__ double np_mean_small(const double* v, int n) {   // np.mean of n <= 128 values
+  double s;
+  if (n < 8) {
+    s = 0.0;
+    for (int i = 0; i < n; ++i) s += v[i];
+  } else {
+    double q[8];
+    for (int j = 0; j < 8; ++j) q[j] = v[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8)
+      for (int j = 0; j < 8; ++j) q[j] += v[i + j];
+    s = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+    for (; i < n; ++i) s += v[i];
+  }
+  return s / (double)n;
+}
+
+__global__ void oi_knee_kernel(FactorList X, int n, const double* __restrict__ sums,
+                               const double* __restrict__ counts, int32_t* __restrict__ pick,
+                               double* __restrict__ factor, double* __restrict__ means) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double y[kMaxFactors], xn[kMaxFactors], yd[kMaxFactors], d[kMaxFactors];
+  bool any_nan = false;
+  for (int i = 0; i < n; ++i) {
+    y[i] = sums[i] / counts[i];            // np.nanmean = sum of finite / count of finite
+    if (means) means[i] = y[i];
+    any_nan = any_nan || y[i] != y[i];
+  }
+  int best = 0;                            // "no knee": the reference falls back to index 0
+  if (!any_nan && n >= 2) {                // a NaN poisons min/max, every comparison is false
+    double xmin = X.f[0], xmax = X.f[0], ymin = y[0], ymax = y[0];
+    for (int i = 1; i < n; ++i) {
+      xmin = X.f[i] < xmin ? X.f[i] : xmin;
+      xmax = X.f[i] > xmax ? X.f[i] : xmax;
+      ymin = y[i] < ymin ? y[i] : ymin;
+      ymax = y[i] > ymax ? y[i] : ymax;
+    }
+    const double xr = xmax - xmin, yr = ymax - ymin;
+    for (int i = 0; i < n; ++i) {
+      xn[i] = (X.f[i] - xmin) / xr;
+      yd[i] = (y[i] - ymin) / yr - xn[i];
+    }
+    for (int i = 0; i + 1 < n; ++i) d[i] = xn[i + 1] - xn[i];
+    const double drop = fabs(np_mean_small(d, n - 1));   // S = 1
+    auto is_max = [&](int i) {
+      const double l = yd[i > 0 ? i - 1 : 0], r = yd[i + 1 < n ? i + 1 : n - 1];
+      return yd[i] >= l && yd[i] >= r;
+    };
+    auto is_min = [&](int i) {
+      const double l = yd[i > 0 ? i - 1 : 0], r = yd[i + 1 < n ? i + 1 : n - 1];
+      return yd[i] <= l && yd[i] <= r;
+    };
+    int first = -1;
+    for (int i = 0; i < n && first < 0; ++i)
+      if (is_max(i)) first = i;
+    if (first >= 0) {
+      double threshold = 0.0;
+      int threshold_index = 0;
+      for (int i = first; i < n; ++i) {
+        if (xn[i] == 1.0) break;
+        if (is_max(i)) {
+          threshold = yd[i] - drop;
+          threshold_index = i;
+        }
+        if (is_min(i)) threshold = 0.0;
+        if (i + 1 < n && yd[i + 1] < threshold) {
+          // np.argwhere(x == knee)[0]: the first factor equal to the knee abscissa
+          best = threshold_index;
+          for (int k = 0; k < n; ++k)
+            if (X.f[k] == X.f[threshold_index]) { best = k; break; }
+          break;
+        }
+      }
+    }
+  }
+  *pick = best;
+  *factor = X.f[best];
+}
+
+__global__ void __launch_bounds__(256)
+oi_apply_dev_kernel(const double* __restrict__ xa, const double* __restrict__ y,
+                    const double* __restrict__ Sa, const double* __restrict__ So, int64_t n,
+                    const double* __restrict__ factor, double* __restrict__ xb,
+                    double* __restrict__ ak, double* __restrict__ inc, double* __restrict__ err) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const double r = *factor;
+  double K, Sb, AK;
+  oi_terms(Sa[c], So[c], r, &K, &Sb, &AK);
+  const double d = __dmul_rn(K, __dsub_rn(y[c], xa[c]));  // optimal_interpolation.py:49
+  inc[c] = d;
+  xb[c] = __dadd_rn(xa[c], d);
+  ak[c] = AK;
+  err[c] = sqrt(Sb);
+}
+}  // namespace oisat
+
+extern "C" int oisat_oi_knee(const double* h_factors, int32_t n_factors, const double* sums,
+                             const double* counts, int32_t* pick, double* factor, double* means,
+                             void* stream) {
+  OISAT_CHECK_ARG(h_factors && sums && counts && pick && factor, "null pointer");
+  OISAT_CHECK_ARG(n_factors >= 1 && n_factors <= kMaxFactors, "bad extent");
+  FactorList X;
+  for (int i = 0; i < kMaxFactors; ++i) X.f[i] = i < n_factors ? h_factors[i] : 0.0;
+  oi_knee_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(X, n_factors, sums, counts, pick, factor, means);
+  OISAT_CHECK_LAUNCH();
+  return OISAT_OK;
+}
+
+extern "C" int oisat_oi_apply_dev(const double* xa, const double* y, const double* Sa,
+                                  const double* So, int64_t n, const double* factor, double* xb,
+                                  double* ak, double* inc, double* err, void* stream) {
+  if (n == 0) return OISAT_OK;
+  OISAT_CHECK_ARG(xa && y && Sa && So && factor && xb && ak && inc && err && n > 0, "null pointer");
+  oi_apply_dev_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      xa, y, Sa, So, n, factor, xb, ak, inc, err);
+  OISAT_CHECK_LAUNCH();
+  return OISAT_OK;
+}
+
 extern "C" int oisat_oi_apply(const double* xa, const double* y, const double* Sa,
                               const double* So, int64_t n, double factor, double* xb, double* ak,
                               double* inc, double* err, void* stream) {

@@ -39,6 +39,50 @@ def sweep_device(Sa_d, So_d, factors):
         return _dev.to_host(sums) / _dev.to_host(cnts)
 
 
+_KNEED = None
+
+
+def kneed_available() -> bool:
+    """The reference's own third-party dependency decides when it is importable
+    (kneedle.knee_index); otherwise the restated Kneedle runs, on the device."""
+    global _KNEED
+    if _KNEED is None:
+        _KNEED = _kneed_importable()
+    return _KNEED
+
+
+def _kneed_importable() -> bool:
+    try:
+        import kneed  # noqa: F401
+        return True
+    except ImportError:
+        return False
+
+
+def sweep_knee_apply_device(xa_d, y_d, Sa_d, So_d, factors):
+    """Sweep, knee and update queued back to back with no host round trip: returns
+    (xb, ak, inc, err, pick, factor, means) as device tensors (pick: int32 scalar)."""
+    L = _lib.lib()
+    n = Sa_d.numel()
+    nf = len(factors)
+    sums, cnts, means = _dev.empty((nf,)), _dev.empty((nf,)), _dev.empty((nf,))
+    wbytes = int(L.oisat_oi_sweep_workspace(n, nf))
+    work = _dev.empty(((wbytes + 7) // 8,))
+    fac = (C.c_double * nf)(*[float(f) for f in factors])
+    s = _dev.stream()
+    _lib.check(L.oisat_oi_sweep(Sa_d.data_ptr(), So_d.data_ptr(), n, fac, nf, sums.data_ptr(),
+                                cnts.data_ptr(), work.data_ptr(), wbytes, s))
+    pick = _dev.empty((1,), "int32")
+    factor = _dev.empty((1,))
+    _lib.check(L.oisat_oi_knee(fac, nf, sums.data_ptr(), cnts.data_ptr(), pick.data_ptr(),
+                               factor.data_ptr(), means.data_ptr(), s))
+    outs = [_dev.empty((n,)) for _ in range(4)]
+    _lib.check(L.oisat_oi_apply_dev(xa_d.data_ptr(), y_d.data_ptr(), Sa_d.data_ptr(), So_d.data_ptr(),
+                                    n, factor.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(),
+                                    outs[2].data_ptr(), outs[3].data_ptr(), s))
+    return outs + [pick, factor, means]
+
+
 def apply_device(xa_d, y_d, Sa_d, So_d, factor):
     L = _lib.lib()
     n = xa_d.numel()

@@ -9,7 +9,8 @@ materialising a gridded granule.
     oisat_fused_amf_split     gather-interpolate, then AMF recalculation per (granule, cell)
     oisat_accum_pairs         ordered segmented reduction -> [10][n_cell] sums / counts
     (torch.distributed all_reduce of the accumulator block when sharded, section 8e)
-    oisat_accum_finalize, oisat_oi_prepare, oisat_oi_sweep, knee (host), oisat_oi_apply
+    oisat_accum_finalize, oisat_oi_prepare, oisat_oi_sweep, oisat_oi_knee, oisat_oi_apply_dev
+    (knee on the host, through the reference's own `kneed`, when that package is importable)
 
 It computes exactly what `interpolator` -> `amf_recal` -> `averaging` ->
 `bias_correct` -> `oi` compute through the drop-in modules (same device
@@ -24,7 +25,46 @@ import numpy as np
 from . import _dev, _lib, _vertical as _v, plan as _plan
 from .driver import BIAS_CORRECTION
 from .kneedle import knee_index
-from .optimal_interpolation import apply_device, regularisation_factors, sweep_device
+from .optimal_interpolation import (apply_device, kneed_available, regularisation_factors,
+                                    sweep_device, sweep_knee_apply_device)
+
+
+class _DeviceScalar:
+    """A one-element device tensor that reads as a host number when asked (int(), float(),
+    ==): the month step itself never waits for it."""
+
+    def __init__(self, t, kind):
+        self.t, self.kind = t, kind
+
+    def value(self):
+        return self.kind(self.t.item())
+
+    def __int__(self):
+        return int(self.value())
+
+    def __index__(self):
+        return int(self.value())
+
+    def __float__(self):
+        return float(self.value())
+
+    def __eq__(self, other):
+        return self.value() == other
+
+    def __repr__(self):
+        return repr(self.value())
+
+
+class _DeviceVector:
+    def __init__(self, t):
+        self.t = t
+
+    def value(self):
+        return _dev.to_host(self.t)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.value()
+        return a if dtype is None else a.astype(dtype)
 
 
 class _Granule:
@@ -442,13 +482,20 @@ class MonthPipeline:
                                       a, b, self.error_ctm, Sa.data_ptr(), So.data_ptr(),
                                       _dev.stream()))
         factors = regularisation_factors(True)
-        ak_means = sweep_device(Sa, So, factors)   # one small D2H: 99 sums + 99 counts
-        pick = knee_index(factors, ak_means)
-        xb, ak, inc, err = apply_device(ctm_vcd, sat_vcd, Sa, So, float(factors[pick]))
+        if kneed_available() or os.environ.get("OISAT_KNEE") == "host":
+            ak_means = sweep_device(Sa, So, factors)   # one small D2H: 99 sums + 99 counts
+            pick = knee_index(factors, ak_means)       # the reference's own kneed when importable
+            xb, ak, inc, err = apply_device(ctm_vcd, sat_vcd, Sa, So, float(factors[pick]))
+            extra = dict(knee_index=pick, ak_means=ak_means, factor=float(factors[pick]))
+        else:
+            # sweep -> knee -> update on the device, no host round trip inside the step
+            xb, ak, inc, err, pick, factor, ak_means = sweep_knee_apply_device(
+                ctm_vcd, sat_vcd, Sa, So, factors)
+            extra = dict(knee_index=_DeviceScalar(pick, int), ak_means=_DeviceVector(ak_means),
+                         factor=_DeviceScalar(factor, float))
         return dict(sat_averaged_vcd=sat_vcd, sat_averaged_error=sat_err, ctm_averaged_vcd=ctm_vcd,
                     aux1=aux1, aux2=aux2, ctm_averaged_vcd_corrected=xb, ak_OI=ak,
-                    increment_OI=inc, error_OI=err, knee_index=pick, ak_means=ak_means,
-                    factor=float(factors[pick]))
+                    increment_OI=inc, error_OI=err, **extra)
 
     def run(self, marks=None):
         """pack -> fused -> accumulate -> OI on the current stream.  `marks`
@@ -479,7 +526,10 @@ class MonthPipeline:
         shape = self.gplan.out_shape
         out = {}
         for k, v in res.items():
-            out[k] = _dev.to_host(v).reshape(shape) if hasattr(v, "data_ptr") else v
+            if isinstance(v, (_DeviceScalar, _DeviceVector)):
+                out[k] = v.value()
+            else:
+                out[k] = _dev.to_host(v).reshape(shape) if hasattr(v, "data_ptr") else v
         return out
 
     def output_fields(self, res):

@@ -298,3 +298,53 @@ def test_near_tie_scan_on_the_device_equals_the_host_scan():
             _lib.check(L.oisat_flagged_nodes(node_tri.data_ptr(), node_tri.numel(), flag.data_ptr(),
                                              cnt.data_ptr(), _dev.stream()))
             assert int(cnt.item()) == n_flag
+
+
+def test_knee_on_the_device_equals_the_host_kneedle():
+    """oisat_oi_knee (one thread on the device) against kneedle.knee_index on saturating
+    curves with and without wiggles (several local maxima of the difference curve), curves
+    without a knee, NaNs; and the pipeline gives the same index either way."""
+    import ctypes as C
+    from oisatgmi_b200 import _dev, _lib, kneedle
+    L = _lib.lib()
+    rng = np.random.default_rng(11)
+    x = np.arange(0.1, 10, 0.1)
+    fac = (C.c_double * len(x))(*[float(v) for v in x])
+    curves = []
+    for trial in range(300):
+        a = rng.uniform(0.05, 5.0)
+        y = x / (x + a) * rng.uniform(0.2, 1.0) + rng.uniform(0, 0.2)
+        if trial % 3 == 0:
+            y = y + rng.normal(0, 1e-3, y.shape)
+        if trial % 7 == 0:
+            y = y + rng.normal(0, 3e-2, y.shape)
+        curves.append(y)
+    curves += [np.full_like(x, np.nan), np.linspace(0, 1, len(x)), x ** 2, np.sqrt(x), -x,
+               np.where(np.arange(len(x)) == 40, np.nan, np.sqrt(x))]
+    picks = set()
+    for y in curves:
+        cnt = rng.integers(1, 50, size=len(x)).astype(np.float64)
+        sums = y * cnt
+        with np.errstate(invalid="ignore"):
+            means_host = sums / cnt
+        want = kneedle.knee_index(x, means_host)
+        pick, factor, means = _dev.empty((1,), "int32"), _dev.empty((1,)), _dev.empty((len(x),))
+        d_sums, d_cnt = _dev.to_device(sums), _dev.to_device(cnt)
+        _lib.check(L.oisat_oi_knee(fac, len(x), d_sums.data_ptr(), d_cnt.data_ptr(), pick.data_ptr(),
+                                   factor.data_ptr(), means.data_ptr(), _dev.stream()))
+        assert int(pick.item()) == want
+        assert float(factor.item()) == x[want]
+        assert np.array_equal(_dev.to_host(means), means_host, equal_nan=True)
+        picks.add(want)
+    assert len(picks) > 10 and 0 in picks
+
+
+def test_pipeline_knee_on_device_equals_knee_on_host(monkeypatch):
+    from test_gpu_fused import run_pipeline
+    _, dev = run_pipeline("omi_hcho")
+    monkeypatch.setenv("OISAT_KNEE", "host")
+    _, host = run_pipeline("omi_hcho")
+    assert dev["knee_index"] == host["knee_index"] and dev["factor"] == host["factor"]
+    assert np.array_equal(np.asarray(dev["ak_means"]), np.asarray(host["ak_means"]), equal_nan=True)
+    for k in ("ctm_averaged_vcd_corrected", "ak_OI", "increment_OI", "error_OI"):
+        assert np.array_equal(dev[k], host[k], equal_nan=True), k
