@@ -371,6 +371,13 @@ int oisat_pack_batch(const oisat_pack_item* items, int32_t n_items, int64_t tota
                      int32_t n_sat_lev, int32_t has_trop, int32_t qflag_dtype,
                      double flag_thresh, int32_t amf_dtype, void* records, double* amf_masked,
                      void* stream);
+/* The same with the granule of every block given by the caller (block_item[b] = index of
+ * the item whose tile block b packs, [total_blocks] device int32; NULL = found by
+ * bisection over items[].block0, ~9 dependent loads per block). */
+int oisat_pack_batch_indexed(const oisat_pack_item* items, int32_t n_items, int64_t total_blocks,
+                             const int32_t* block_item, int32_t n_sat_lev, int32_t has_trop,
+                             int32_t qflag_dtype, double flag_thresh, int32_t amf_dtype,
+                             void* records, double* amf_masked, void* stream);
 
 /* derived model fields, once per month instead of once per granule
  * (amf_recal.py:151-152): logp = float32 log(p_mid) (:108), pcol = float32 partial

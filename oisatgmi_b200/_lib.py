@@ -96,6 +96,7 @@ PROTOTYPES = {
     "oisat_pack_granule": (C.c_int, [vp, vp, i32, vp, vp, vp, i64, vp, vp]),
     "oisat_pack_blocks": (i64, [i64]),
     "oisat_pack_batch": (C.c_int, [vp, i32, i64, i32, i32, i32, f64, i32, vp, vp, vp]),
+    "oisat_pack_batch_indexed": (C.c_int, [vp, i32, i64, vp, i32, i32, i32, f64, i32, vp, vp, vp]),
     "oisat_ctm_prepare": (C.c_int, [vp, vp, vp, i64, vp, vp, vp]),
     "oisat_fused_amf": (C.c_int, [C.POINTER(FusedArgs), vp]),
     "oisat_rows_per_pair": (i64, [i32, i32]),

@@ -209,35 +209,46 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __global__ void __launch_bounds__(256, 4)
 pack_batch_kernel(const oisat_pack_item* __restrict__ items, int n_items, int L, int has_trop,
                   int qflag_dtype, double thresh, int amf_dtype, __half* __restrict__ records,
-                  double* __restrict__ amf_masked, int use_bulk) {
+                  double* __restrict__ amf_masked, int use_bulk,
+                  const int32_t* __restrict__ block_item) {
   extern __shared__ __align__(128) __half tile[];
   __shared__ unsigned char bad[kPackPixels];
   __shared__ __align__(8) unsigned long long mbar;
-  // granule of this block: last item with block0 <= blockIdx.x
-  int lo = 0, hi = n_items - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (items[mid].block0 <= (int64_t)blockIdx.x) lo = mid; else hi = mid - 1;
+  // granule of this block: from the caller's table, else the last item with block0 <= blockIdx.x
+  // (a bisection is ~9 DEPENDENT global loads before the block can request a single byte)
+  int lo = 0;
+  if (block_item) {
+    lo = block_item[blockIdx.x];
+  } else {
+    int hi = n_items - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (items[mid].block0 <= (int64_t)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
   }
   const oisat_pack_item it = items[lo];
   PackSrc s{(const __half*)it.sw, (const __half*)it.p_mid, (const __half*)it.vcd,
             (const __half*)it.sigma, (const __half*)it.trop, it.n_px};
   const int64_t p0 = ((int64_t)blockIdx.x - it.block0) * kPackPixels;
-  if (threadIdx.x < kPackPixels) {
-    const int64_t p = p0 + threadIdx.x;
-    bool is_bad = true;
-    if (p < it.n_px) {
-      is_bad = !(load_as_double(it.qflag, qflag_dtype, p) > thresh);
-      amf_masked[it.px0 + p] = is_bad ? qnan() : load_as_double(it.amf, amf_dtype, p);
+  // quality mask of the tile's pixels + masked AMF (interpolator.py:126-128)
+  auto mask_pixels = [&]() {
+    if (threadIdx.x < kPackPixels) {
+      const int64_t p = p0 + threadIdx.x;
+      bool is_bad = true;
+      if (p < it.n_px) {
+        is_bad = !(load_as_double(it.qflag, qflag_dtype, p) > thresh);
+        amf_masked[it.px0 + p] = is_bad ? qnan() : load_as_double(it.amf, amf_dtype, p);
+      }
+      bad[threadIdx.x] = is_bad ? 1 : 0;
     }
-    bad[threadIdx.x] = is_bad ? 1 : 0;
-  }
+  };
   const int nrow = record_rows(L, has_trop);
   const int nchunk = record_chunks(L, has_trop);
   const int R = 8 * nchunk;
   uintptr_t align = (uintptr_t)it.sw | (uintptr_t)it.p_mid | (uintptr_t)it.vcd | (uintptr_t)it.sigma;
   if (has_trop) align |= (uintptr_t)it.trop;
   if (!use_bulk || (align & 15) != 0 || (it.n_px & 7) != 0) {
+    mask_pixels();
     // (pack_block starts with a __syncthreads that also publishes `bad`)
     pack_block(s, L, has_trop, p0, records + it.px0 * R, tile, bad);
     return;
@@ -250,7 +261,10 @@ pack_batch_kernel(const oisat_pack_item* __restrict__ items, int n_items, int L,
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();  // barrier initialised, `bad` published
+  __syncthreads();  // barrier initialised
+  // the row copies are requested FIRST; the mask (its own loads and stores) is worked out
+  // while they are in flight and published by the barrier before the store phase
+  if (threadIdx.x >= 32) mask_pixels();
   if (threadIdx.x < 32) {
     if (threadIdx.x == 0)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
@@ -267,6 +281,7 @@ pack_batch_kernel(const oisat_pack_item* __restrict__ items, int n_items, int L,
           ::"r"(smem_u32(tile + row * kTmaPitch)), "l"(src + p0), "r"(row_bytes), "r"(bar)
           : "memory");
     }
+    mask_pixels();
   }
   // rows nrow..R-1 are the zero padding of the record
   for (int i = threadIdx.x; i < (R - nrow) * kPackPixels; i += blockDim.x)
@@ -558,10 +573,25 @@ extern "C" int oisat_pack_granule(const void* sw, const void* p_mid, int32_t n_s
 
 extern "C" int64_t oisat_pack_blocks(int64_t n_px) { return ceil_div(n_px, kPackPixels); }
 
+extern "C" int oisat_pack_batch_indexed(const oisat_pack_item* items, int32_t n_items,
+                                        int64_t total_blocks, const int32_t* block_item,
+                                        int32_t n_sat_lev, int32_t has_trop, int32_t qflag_dtype,
+                                        double flag_thresh, int32_t amf_dtype, void* records,
+                                        double* amf_masked, void* stream);
+
 extern "C" int oisat_pack_batch(const oisat_pack_item* items, int32_t n_items,
                                 int64_t total_blocks, int32_t n_sat_lev, int32_t has_trop,
                                 int32_t qflag_dtype, double flag_thresh, int32_t amf_dtype,
                                 void* records, double* amf_masked, void* stream) {
+  return oisat_pack_batch_indexed(items, n_items, total_blocks, nullptr, n_sat_lev, has_trop,
+                                  qflag_dtype, flag_thresh, amf_dtype, records, amf_masked, stream);
+}
+
+extern "C" int oisat_pack_batch_indexed(const oisat_pack_item* items, int32_t n_items,
+                                        int64_t total_blocks, const int32_t* block_item,
+                                        int32_t n_sat_lev, int32_t has_trop, int32_t qflag_dtype,
+                                        double flag_thresh, int32_t amf_dtype, void* records,
+                                        double* amf_masked, void* stream) {
   if (n_items <= 0 || total_blocks <= 0) return OISAT_OK;
   OISAT_CHECK_ARG(items && records && amf_masked, "null pointer");
   OISAT_CHECK_ARG(amf_dtype == OISAT_F16 || amf_dtype == OISAT_F32 || amf_dtype == OISAT_F64,
@@ -579,7 +609,7 @@ extern "C" int oisat_pack_batch(const oisat_pack_item* items, int32_t n_items,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pack_batch_kernel<<<(unsigned)total_blocks, 256, smem, (cudaStream_t)stream>>>(
       items, n_items, n_sat_lev, has_trop, qflag_dtype, flag_thresh, amf_dtype, (__half*)records,
-      amf_masked, use_bulk);
+      amf_masked, use_bulk, block_item);
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
 }

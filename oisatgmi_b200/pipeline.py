@@ -268,29 +268,39 @@ class MonthPipeline:
         vert = t.cat([p[0] for p in pairs]) if len(pairs) > 1 else pairs[0][0]   # (n_pairs, S)
         w = t.cat([p[1] for p in pairs]) if len(pairs) > 1 else pairs[0][1]
         n_pairs = cells.size
-        # tiles: runs of pairs of one granule inside one 32-aligned cell segment
-        tid = gran.astype(np.int64) * ((self.n_cell + 31) // 32 + 1) + cells // 32
-        starts = np.concatenate(([0], np.flatnonzero(np.diff(tid)) + 1))
-        tile_pair0 = starts.astype(np.int64)
-        tile_gran = gran[starts].astype(np.int32)
-        tile_cell0 = ((cells[starts] // 32) * 32).astype(np.int32)
-        bits = (np.uint32(1) << (cells % 32).astype(np.uint32))
-        tile_mask = np.bitwise_or.reduceat(bits, starts).astype(np.uint32)
-        # segments: pairs of each model cell in granule order (stable sort by cell)
-        order = np.argsort(cells, kind="stable").astype(np.int64)
-        seg_start = np.zeros(self.n_cell + 1, np.int64)
-        np.cumsum(np.bincount(cells, minlength=self.n_cell), out=seg_start[1:])
         px0 = np.concatenate(([0], np.cumsum([g.n_px for g in G])[:-1])).astype(np.int64)
-        host = dict(n_pairs=n_pairs, n_tiles=len(starts), S=S, px0=px0,
-                    total_px=int(sum(g.n_px for g in G)))
+        host = dict(n_pairs=n_pairs, n_tiles=0, S=S, px0=px0,
+                    total_px=int(sum(g.n_px for g in G)), cells=cells, gran=gran)
         d = _dev.to_device
-        dev = dict(vert=vert, w=w, tile_pair0=d(tile_pair0), tile_gran=d(tile_gran), tile_cell0=d(tile_cell0),
-                   tile_mask=d(tile_mask.view(np.int32)), seg_start=d(seg_start),
-                   seg_pair=d(order), gran_px0=d(px0), pair_gran=d(gran),
-                   pair_cell=d(cells.astype(np.int32)),
+        pair_cell = d(cells.astype(np.int32))
+        # segments: pairs of each model cell in granule order (stable sort by cell), built on
+        # the device -- the host only concatenated the cell lists
+        pc64 = pair_cell.to(t.int64)
+        order = t.sort(pc64, stable=True).indices
+        seg_start = t.zeros(self.n_cell + 1, dtype=t.int64, device=pair_cell.device)
+        t.cumsum(t.bincount(pc64, minlength=self.n_cell), 0, out=seg_start[1:])
+        dev = dict(vert=vert, w=w, seg_start=seg_start, seg_pair=order, gran_px0=d(px0),
+                   pair_gran=d(gran), pair_cell=pair_cell,
                    gran_slot=d(np.array([g.slot for g in G], np.int32)))
         self._tables = (host, dev)
         return self._tables
+
+    def _tile_tables(self):
+        """Tile table of the single-kernel form (oisat_fused_amf): runs of pairs of one
+        granule inside one 32-aligned cell segment.  The tile and split forms do not read it."""
+        host, dev = self.build_tables()
+        if "tile_pair0" in dev:
+            return
+        cells, gran = host["cells"], host["gran"]
+        tid = gran.astype(np.int64) * ((self.n_cell + 31) // 32 + 1) + cells // 32
+        starts = np.concatenate(([0], np.flatnonzero(np.diff(tid)) + 1))
+        bits = (np.uint32(1) << (cells % 32).astype(np.uint32))
+        tile_mask = np.bitwise_or.reduceat(bits, starts).astype(np.uint32)
+        d = _dev.to_device
+        dev.update(tile_pair0=d(starts.astype(np.int64)), tile_gran=d(gran[starts].astype(np.int32)),
+                   tile_cell0=d(((cells[starts] // 32) * 32).astype(np.int32)),
+                   tile_mask=d(tile_mask.view(np.int32)))
+        host["n_tiles"] = len(starts)
 
     def plan_bytes(self):
         _, dev = self.build_tables()
@@ -307,6 +317,7 @@ class MonthPipeline:
         # device table of the batch pack launch
         items = (_lib.PackItem * len(self.granules))()
         block0 = 0
+        blocks_of = []
         for i, (g, p0) in enumerate(zip(self.granules, host["px0"])):
             d = g.dev
             items[i].sw, items[i].p_mid = d["sw"].data_ptr(), d["pmid"].data_ptr()
@@ -315,7 +326,8 @@ class MonthPipeline:
             items[i].qflag = d["qflag"].data_ptr()
             items[i].amf = d["amf"].data_ptr()
             items[i].n_px, items[i].px0, items[i].block0 = g.n_px, int(p0), block0
-            block0 += int(L.oisat_pack_blocks(g.n_px))
+            blocks_of.append(int(L.oisat_pack_blocks(g.n_px)))
+            block0 += blocks_of[-1]
         raw = np.frombuffer(bytes(items), dtype=np.uint8).copy()
         # OISAT_GUARD=1 (tests): every output buffer sits between two canary zones that
         # check_guards() inspects after a run -- the out-of-bounds-write check of this path
@@ -344,6 +356,8 @@ class MonthPipeline:
                        int(L.oisat_rows_per_pair(g0.nlev, int(g0.has_trop))), 16))
                   if self.split else None),
             pack_items=_dev.to_device(raw), pack_blocks=block0,
+            pack_block_item=_dev.to_device(np.repeat(np.arange(len(blocks_of), dtype=np.int32),
+                                                     blocks_of)),
         )
         return self._buf
 
@@ -369,11 +383,11 @@ class MonthPipeline:
         L = _lib.lib()
         buf = self._buf
         g0 = self.granules[0]
-        _lib.check(L.oisat_pack_batch(buf["pack_items"].data_ptr(), len(self.granules),
-                                      buf["pack_blocks"], g0.nlev, int(g0.has_trop),
-                                      _dev.dtype_code(g0.dev["qflag"]), self.flag_thresh,
-                                      _dev.dtype_code(g0.dev["amf"]), buf["records"].data_ptr(),
-                                      buf["amf_masked"].data_ptr(), _dev.stream()))
+        _lib.check(L.oisat_pack_batch_indexed(
+            buf["pack_items"].data_ptr(), len(self.granules), buf["pack_blocks"],
+            buf["pack_block_item"].data_ptr(), g0.nlev, int(g0.has_trop),
+            _dev.dtype_code(g0.dev["qflag"]), self.flag_thresh, _dev.dtype_code(g0.dev["amf"]),
+            buf["records"].data_ptr(), buf["amf_masked"].data_ptr(), _dev.stream()))
 
     def fused_args(self):
         host, dev = self.build_tables()
@@ -382,11 +396,13 @@ class MonthPipeline:
         g0 = self.granules[0]
         nwin = self.gplan.nwin
         a = _lib.FusedArgs()
-        a.n_tiles = host["n_tiles"]
-        a.tile_granule = dev["tile_gran"].data_ptr()
-        a.tile_cell0 = dev["tile_cell0"].data_ptr()
-        a.tile_pair0 = dev["tile_pair0"].data_ptr()
-        a.tile_mask = dev["tile_mask"].data_ptr()
+        if self.fused_form == "single":
+            self._tile_tables()
+            a.n_tiles = host["n_tiles"]
+            a.tile_granule = dev["tile_gran"].data_ptr()
+            a.tile_cell0 = dev["tile_cell0"].data_ptr()
+            a.tile_pair0 = dev["tile_pair0"].data_ptr()
+            a.tile_mask = dev["tile_mask"].data_ptr()
         a.n_pairs = host["n_pairs"]
         a.nwin = nwin
         a.vert = dev["vert"].data_ptr()
