@@ -540,11 +540,19 @@ __device__ __noinline__ double amf_slow_path_tile(const RowViewP<kTP>& r, int L,
 
 struct TileSmem {   // static part
   double2 tab[128];   // (r_i, -log r_i)
-  double part_a[8 * 16];
-  double tail_a[8 * 16];
+  union {
+    struct {          // vertical phase
+      double part_a[8 * 16];
+      double tail_a[8 * 16];
+      float part_b[8 * 16];
+      float tail_b[8 * 16];
+    };
+    struct {          // packed gather: weight and first chunk of every (pair, entry) of a sweep
+      double gw[16 * 15];
+      uint32_t gcix[16 * 15];
+    };
+  };
   double old_amf[16];
-  float part_b[8 * 16];
-  float tail_b[8 * 16];
   int unsorted[16];
 };
 
@@ -553,7 +561,7 @@ struct TileSmem {   // static part
 // (the BASELINE products), 0 = read from the arguments: with constants the record and
 // tile geometry fold into immediates and the loops unroll (the generic build spends more
 // than half of its instructions outside the arithmetic).
-template <bool HAS_TROP, int H, int CL, int CS, int CN, int SW, int MINB>
+template <bool HAS_TROP, int H, int CL, int CS, int CN, int SW, int MINB, bool PACKED>
 __global__ void __launch_bounds__(kTileThreads, MINB)
 fused_tile_kernel(const __grid_constant__ SplitParams P) {
   const oisat_fused_args& A = P.a;
@@ -602,6 +610,106 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
   const int i0 = t < 8 ? 0 : half;
   const int cnt = t < 8 ? half : nb - half;
   // ------------------------------------------------------------ gather phase
+  if constexpr (PACKED) {
+    // Packed lanes: a record of nchunk < 16 chunks leaves 16 - nchunk lanes of every half warp
+    // idle in the loops below (4 of 16 for OMI HCHO, 6 for OMI NO2, 7 for TROPOMI).  Here the
+    // 16 * nchunk (pair, chunk) work items of the tile are dealt to consecutive threads, so
+    // the loops run on 6 / 5 / 4.5 warps instead of 8; weights and chunk indices of a sweep
+    // come from a small shared table (filled in the half-warp layout, which also keeps the
+    // AMF term's summation tree) instead of shuffles.  Same arithmetic, same order.
+    const int64_t pair_raw = (int64_t)blockIdx.x * 16 + col;
+    const bool mine = pair_raw < A.n_pairs;
+    const int64_t pair = mine ? pair_raw : A.n_pairs - 1;
+    int64_t rec0, px0;
+    if (A.pair_record0) {
+      rec0 = px0 = A.pair_record0[pair];
+    } else {
+      const int g = A.pair_granule[pair];
+      rec0 = A.gran_record0[g];
+      px0 = A.gran_px0[g];
+    }
+    const uint4* records = reinterpret_cast<const uint4*>(A.records);
+    const int tid = threadIdx.x;
+    const bool active = tid < 16 * nchunk;
+    const int pp = active ? tid / nchunk : 0;          // pair of the tile
+    const int ch = active ? tid - pp * nchunk : 0;     // chunk of its records
+    double acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.0;
+    double acc_amf = 0.0;
+    uint4* slot = stage + (pp * sweep) * nchunk + ch;                  // [pair][entry][chunk]
+#pragma unroll 1
+    for (int base = 0; base < S; base += SW) {
+      const int nk = (S - base) < SW ? (S - base) : SW;
+      int32_t v = 0;
+      double wt = 0.0;
+      if (base > 0) __syncthreads();                   // the previous sweep is done with the table
+      if (gl < nk) {
+        v = A.vert[pair * S + base + gl];
+        wt = A.w[pair * S + base + gl];
+        sm.gcix[col * SW + gl] = (uint32_t)((rec0 + v) * nchunk);
+        sm.gw[col * SW + gl] = wt;
+      }
+      __syncthreads();
+      if (active) {
+#pragma unroll
+        for (int e = 0; e < SW; ++e) {
+          if (e < nk) {
+            const uint32_t ck = sm.gcix[pp * SW + e] + (uint32_t)ch;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + e * nchunk);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(records + ck)
+                         : "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      double za = 0.0;
+      if (gl < nk) za = wt * A.amf_masked[px0 + v];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) za += __shfl_xor_sync(0xffffffffu, za, o, 16);
+      acc_amf += za;
+      if (base == 0 && live) {
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+          if (i < cnt) {
+            const uint32_t at = off + (uint32_t)(j8 + 8 * (i0 + i)) * stride;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + at));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + at));
+            if (HAS_TROP) asm volatile("prefetch.global.L2 [%0];" ::"l"(pm + at));
+          }
+        }
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (active) {
+#pragma unroll
+        for (int e = 0; e < SW; ++e) {
+          if (e < nk) {
+            const double wk = sm.gw[pp * SW + e];
+            double z[8];
+            h8_to_f64(slot[e * nchunk], z);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = fma(wk, z[k], acc[k]);
+          }
+        }
+      }
+    }
+    const int sig_row = 2 * L + 1;
+    if (active) {
+      double sig = 0.0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int row = ch + nchunk * e;
+        if (row == sig_row) sig = acc[e];
+        const int orow = row <= 2 * L ? row : row - 1;                 // tropopause follows vcd
+        if (row < nrow && row != sig_row) tile[orow * kTP + pp] = acc[e] * A.box_weight;
+      }
+      const int64_t my_pair = (int64_t)blockIdx.x * 16 + pp;
+      if (my_pair < A.n_pairs && ch == sig_row % nchunk)
+        A.staged[1 * A.n_pairs + my_pair] = sqrt(sig * A.box_weight_err);   // interpolator.py:188
+    }
+    if (gl == 0) sm.old_amf[col] = acc_amf * A.box_weight;
+    if (mine && gl == 0) A.staged[4 * A.n_pairs + pair] = acc_amf * A.box_weight;
+  } else
   {
     const int64_t pair_raw = (int64_t)blockIdx.x * 16 + col;
     const bool mine = pair_raw < A.n_pairs;
@@ -909,7 +1017,7 @@ extern "C" int oisat_fused_amf_split(const oisat_fused_args* h_args, double* row
   return OISAT_OK;
 }
 
-template <bool HAS_TROP, int H, int CL, int CS, int CN, int SW = 15, int MINB = 4>
+template <bool HAS_TROP, int H, int CL, int CS, int CN, bool PACKED = false, int SW = 15, int MINB = 4>
 static int launch_tile(const SplitParams& P, cudaStream_t s) {
   const oisat_fused_args& a = P.a;
   const int sweep = 3 * a.nwin < SW ? 3 * a.nwin : SW;
@@ -917,9 +1025,9 @@ static int launch_tile(const SplitParams& P, cudaStream_t s) {
   const size_t stage_bytes = (size_t)16 * sweep * P.nchunk * sizeof(uint4);
   const size_t vert_bytes = (size_t)(kSearchRows + a.n_sat_lev) * kXP * sizeof(double);
   const size_t smem = tile_bytes + (stage_bytes > vert_bytes ? stage_bytes : vert_bytes);
-  OISAT_CHECK_CUDA(cudaFuncSetAttribute(fused_tile_kernel<HAS_TROP, H, CL, CS, CN, SW, MINB>,
+  OISAT_CHECK_CUDA(cudaFuncSetAttribute(fused_tile_kernel<HAS_TROP, H, CL, CS, CN, SW, MINB, PACKED>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fused_tile_kernel<HAS_TROP, H, CL, CS, CN, SW, MINB>
+  fused_tile_kernel<HAS_TROP, H, CL, CS, CN, SW, MINB, PACKED>
       <<<(unsigned)ceil_div(P.a.n_pairs, 16), kTileThreads, smem, s>>>(P);
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
@@ -953,10 +1061,16 @@ extern "C" int oisat_fused_amf_tile(const oisat_fused_args* h_args, void* stream
   // forces the run-time build: the tests compare the two)
   const char* gen = getenv("OISAT_TILE_GENERIC");
   const bool generic = gen && gen[0] == '1';
+  const char* pk = getenv("OISAT_TILE_PACKED");   // "0": half-warp-per-pair gather lanes (A/B runs, tests)
+  const bool packed = !(pk && pk[0] == '0');
   if (generic) {
-  } else if (!a.has_trop && L == 47 && S == 12 && N == 72) return launch_tile<false, 5, 47, 12, 72>(P, s);
-  else if (a.has_trop && L == 35 && S == 12 && N == 72) return launch_tile<true, 5, 35, 12, 72>(P, s);
-  else if (a.has_trop && L == 34 && S == 90 && N == 72) return launch_tile<true, 5, 34, 90, 72>(P, s);
+  } else if (!a.has_trop && L == 47 && S == 12 && N == 72) {
+    return packed ? launch_tile<false, 5, 47, 12, 72, true>(P, s) : launch_tile<false, 5, 47, 12, 72>(P, s);
+  } else if (a.has_trop && L == 35 && S == 12 && N == 72) {
+    return packed ? launch_tile<true, 5, 35, 12, 72, true>(P, s) : launch_tile<true, 5, 35, 12, 72>(P, s);
+  } else if (a.has_trop && L == 34 && S == 90 && N == 72) {
+    return packed ? launch_tile<true, 5, 34, 90, 72, true>(P, s) : launch_tile<true, 5, 34, 90, 72>(P, s);
+  }
   const int half = ((N / 8) + 1) / 2;
   if (half <= 5)
     return a.has_trop ? launch_tile<true, 5, 0, 0, 0>(P, s) : launch_tile<false, 5, 0, 0, 0>(P, s);

@@ -175,3 +175,20 @@ def test_tile_form_generic_build_equals_specialised_build(name, monkeypatch):
     pipe_b, _ = run_pipeline(name)
     b = pipe_b._buf["staged"].cpu().numpy()
     assert a.size > 0 and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+@pytest.mark.parametrize("name", ["omi_hcho", "omi_no2", "tropomi_no2", "omi_no2_kinked"])
+def test_tile_form_packed_lanes_equal_half_warp_lanes(name, monkeypatch):
+    """OISAT_TILE_PACKED=1 deals the (pair, chunk) work of the gather to consecutive threads
+    (no idle lanes for records of fewer than 16 chunks); the half-warp-per-pair layout is the
+    other build.  Same staged values bit for bit."""
+    monkeypatch.setenv("OISAT_FUSED", "tile")
+    monkeypatch.setenv("OISAT_TILE_PACKED", "0")
+    pipe_a, _ = run_pipeline(name)
+    a = pipe_a._buf["staged"].cpu().numpy()
+    monkeypatch.setenv("OISAT_TILE_PACKED", "1")
+    monkeypatch.setenv("OISAT_GUARD", "1")
+    pipe_b, _ = run_pipeline(name)
+    assert pipe_b.check_guards()
+    b = pipe_b._buf["staged"].cpu().numpy()
+    assert a.size > 0 and np.array_equal(a.view(np.uint64), b.view(np.uint64))
