@@ -128,8 +128,35 @@ struct LatticeBuilder {
     // the whole footprint; L descending, boustrophedon inside a level.  That behaves
     // like a randomised order (a few flips per point) yet keeps consecutive points
     // close, so the location walk from the previous point stays short.
+    // The levels refine the lattice ISOTROPICALLY IN THE PLANE, not in index space: OMI pixels
+    // are 13 km apart along the track and 24-150 km across it (4.7 : 1 in lon/lat), so a level
+    // steps 4 x further in the row index than in the column index (ai = 2); TROPOMI's 1.7 : 1
+    // gives ai = 1.  With square-ish cells at every level the intermediate triangulations look
+    // like the final one and a new point costs 2.7 flips instead of 5.1 (measured on an OMI
+    // granule: 502 k -> 267 k flips, insertion 56 -> 34 ms).
+    int ai = 0, aj = 0;
+    {
+      std::vector<double> dr, dc;
+      const int64_t sr = std::max<int64_t>(1, rows / 64), sc = std::max<int64_t>(1, cols / 64);
+      for (int64_t i = 0; i + 1 < rows; i += sr)
+        for (int64_t j = 0; j + 1 < cols; j += sc) {
+          const int64_t v = i * cols + j;
+          dr.push_back(std::hypot(x[v + cols] - x[v], y[v + cols] - y[v]));
+          dc.push_back(std::hypot(x[v + 1] - x[v], y[v + 1] - y[v]));
+        }
+      if (!dr.empty()) {
+        std::nth_element(dr.begin(), dr.begin() + dr.size() / 2, dr.end());
+        std::nth_element(dc.begin(), dc.begin() + dc.size() / 2, dc.end());
+        const double a = dr[dr.size() / 2], b = dc[dc.size() / 2];   // medians: row / column spacing
+        if (a > 0.0 && b > 0.0) {
+          const int k = (int)std::lround(std::log2(b / a));
+          ai = std::min(std::max(k, 0), 3);
+          aj = std::min(std::max(-k, 0), 3);
+        }
+      }
+    }
     std::vector<int32_t> ord;
-    std::vector<uint8_t> lev;             // level (log2 of the lattice step) each point enters at
+    std::vector<uint8_t> lev;             // level index (0 = finest) each point enters at
     ord.reserve(n);
     lev.reserve(n);
     {
@@ -142,14 +169,16 @@ struct LatticeBuilder {
       int top = 0;
       while ((int64_t(2) << top) < std::max(rows, cols)) ++top;
       std::vector<int64_t> ri, cj;
-      for (int L = top; L >= 0; --L) {
-        cur_level = L;
-        const int64_t step = int64_t(1) << L;
+      const int lowest = -std::max(ai, aj);
+      for (int L = top; L >= lowest; --L) {
+        cur_level = L - lowest;
+        const int64_t step = int64_t(1) << std::max(L + ai, 0);
+        const int64_t stepj = int64_t(1) << std::max(L + aj, 0);
         ri.clear();
         cj.clear();
         for (int64_t i = 0; i < rows; i += step) ri.push_back(i);
         if (ri.back() != rows - 1) ri.push_back(rows - 1);
-        for (int64_t j = 0; j < cols; j += step) cj.push_back(j);
+        for (int64_t j = 0; j < cols; j += stepj) cj.push_back(j);
         if (cj.back() != cols - 1) cj.push_back(cols - 1);
         bool backward = false;
         for (int64_t i : ri) {
@@ -198,10 +227,11 @@ struct LatticeBuilder {
       {
         const double px = x[p], py = y[p];
         double best = (x[prev_pt] - px) * (x[prev_pt] - px) + (y[prev_pt] - py) * (y[prev_pt] - py);
-        const int64_t s2 = int64_t(2) << lev[k];
+        const int Lr = (int)lev[k] - std::max(ai, aj);
+        const int64_t s2 = int64_t(2) << std::max(Lr + ai, 0), s2j = int64_t(2) << std::max(Lr + aj, 0);
         const int64_t i = p / cols, j = p % cols;
-        const int64_t i0 = (i / s2) * s2, j0 = (j / s2) * s2;
-        const int64_t i1 = std::min(i0 + s2, rows - 1), j1 = std::min(j0 + s2, cols - 1);
+        const int64_t i0 = (i / s2) * s2, j0 = (j / s2j) * s2j;
+        const int64_t i1 = std::min(i0 + s2, rows - 1), j1 = std::min(j0 + s2j, cols - 1);
         const int64_t cand[4] = {i0 * cols + j0, i0 * cols + j1, i1 * cols + j0, i1 * cols + j1};
         for (int c = 0; c < 4; ++c) {
           const int32_t h = hint[cand[c]];
