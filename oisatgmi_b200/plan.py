@@ -296,7 +296,7 @@ def native_delaunay_path(lon, lat):
     return tri[:nt], int(ties.value), int(path.value)
 
 
-def native_delaunay_adj(lon, lat, pinned=False):
+def native_delaunay_adj(lon, lat, pinned=False, device_index=None):
     """Triangulation for builder v1 with the near-tie scan left to the device:
     (tri, half, n_ties, max_abs_coord).  `half` (twin half-edge of every triangle edge) is
     None when the general builder ran -- then n_ties is already the complete report."""
@@ -313,8 +313,11 @@ def native_delaunay_adj(lon, lat, pinned=False):
     n = x.size
     if pinned:   # page-locked outputs: their upload does not block the calling thread
         t = _dev.torch()
-        tri = t.empty((2 * n, 3), dtype=t.int32, pin_memory=True).numpy()
-        half = t.empty((2 * n, 3), dtype=t.int32, pin_memory=True).numpy()
+        # (a pool thread's current device is 0 whatever the rank's device is: pin through the
+        # caller's device so that a rank does not open a context on somebody else's GPU)
+        with t.cuda.device(device_index if device_index is not None else t.cuda.current_device()):
+            tri = t.empty((2 * n, 3), dtype=t.int32, pin_memory=True).numpy()
+            half = t.empty((2 * n, 3), dtype=t.int32, pin_memory=True).numpy()
     else:
         tri = np.empty((2 * n, 3), dtype=np.int32)
         half = np.empty((2 * n, 3), dtype=np.int32)
@@ -623,7 +626,8 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
     import time as _time
     trace = [] if os.environ.get("OISAT_PLAN_TRACE") == "1" else None
     t_start = _time.perf_counter()
-    futures = {ex.submit(native_delaunay_adj, lons[i], lats[i], True): i for i in range(n)}
+    dev_index = _dev.device().index
+    futures = {ex.submit(native_delaunay_adj, lons[i], lats[i], True, dev_index): i for i in range(n)}
     for fut in as_completed(futures):
         i = futures[fut]
         tri, half, ties, maxabs = fut.result()
