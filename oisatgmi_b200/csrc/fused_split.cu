@@ -1,3 +1,15 @@
+// Two forms of the fused month step for records of fewer than 16 chunks (every BASELINE
+// product); oisat_fused_amf (fused_amf.cu, half warp per pair end to end) serves wider records.
+//
+//   oisat_fused_amf_tile   THE DEFAULT (second half of this file): one launch, a block owns 16
+//                          consecutive pairs, gathers their gridded columns into shared memory
+//                          and runs the vertical operator there on all of its threads -- no row
+//                          buffer, no data-dependent control flow; builds with the BASELINE
+//                          products' level counts and stencil size as compile-time constants.
+//   oisat_fused_amf_split  the two-launch form it grew out of (below), kept as the fallback for
+//                          more than 62 satellite levels and as the bit-for-bit cross-check of
+//                          the tile form (tests/test_gpu_fused.py).
+//
 // Split form of the fused month kernel (round-1 profile: oisat_fused_amf spends
 // ~2400 warp instructions per two pairs, two thirds of them overhead of running
 // the vertical operator co-operatively on 16 lanes).  Same arithmetic, two launches:
