@@ -383,3 +383,46 @@ def test_delaunay_adjacency_output_is_the_twin_map_and_carries_the_tie_report():
         assert maxabs == max(np.abs(lon).max(), np.abs(lat).max())
         assert hull_ties + _near_ties_numpy(lon, lat, tri, half) == ties_ref, name
     assert ties_ref > 0   # the last case does have ties
+
+
+def test_granule_plans_routes_ties_and_failures(monkeypatch):
+    """Control flow of plan.granule_plans without a GPU (device steps stubbed): a granule with
+    exact hull ties goes to builder v0, one whose device scan finds an affected near-tie too,
+    an untriangulable one stays None, the rest take the two-phase v1 path; the thread pool is
+    the persistent one."""
+    import types
+    calls = []
+
+    class FakeDev:
+        @staticmethod
+        def to_device(a, *k, **kw):
+            return a
+
+        @staticmethod
+        def to_host(a):
+            return np.asarray(a)
+
+        @staticmethod
+        def device():
+            return types.SimpleNamespace(index=0)
+
+    def fake_adj(lon, lat, pinned=False, device_index=None):
+        kind = int(lon[0, 0])
+        if kind == 3:
+            return None, None, 0, 0.0
+        return np.zeros((1, 3), np.int32), np.zeros((1, 3), np.int32), (2 if kind == 1 else 0), 1.0
+
+    monkeypatch.setattr(plan, "_dev", FakeDev)
+    monkeypatch.setattr(plan, "distance_mask", lambda lo, la, g, r: np.ones(4, np.uint8))
+    monkeypatch.setattr(plan, "native_delaunay_adj", fake_adj)
+    monkeypatch.setattr(plan, "_plan_v1_enqueue", lambda tri, ll, g, keep, half, m: dict(kind=int(np.ravel(ll[0])[0])))
+    monkeypatch.setattr(plan, "_plan_v1_finish", lambda st, g: None if st["kind"] == 2 else ("v1", st["kind"]))
+    monkeypatch.setattr(plan, "_plan_v0", lambda lon, lat, g, keep: calls.append(int(lon[0, 0])) or ("v0", int(lon[0, 0])))
+    monkeypatch.setenv("OISAT_PLAN", "auto")
+    gplan = types.SimpleNamespace(upscale=True)
+    kinds = [0, 1, 2, 3, 0, 0]
+    lons = [np.full((2, 2), float(k)) for k in kinds]
+    out = plan.granule_plans(lons, lons, gplan, 0.5, workers=3)
+    assert out == [("v1", 0), ("v0", 1), ("v0", 2), None, ("v1", 0), ("v1", 0)]
+    assert sorted(calls) == [1, 2]
+    assert plan._plan_pool(3) is plan._plan_pool(3)
