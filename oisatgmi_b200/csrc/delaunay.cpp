@@ -538,7 +538,10 @@ extern "C" int64_t oisat_h_delaunay_swath_adj(const double* h_x, const double* h
   if (!h_x || !h_y || !h_tri || !h_half || n_rows < 1 || n_cols < 1 ||
       n_rows * n_cols > (int64_t)0x3fffffff)
     return OISAT_E_ARG;
-  LatticeBuilder g;
+  // one builder per thread, reused: the plan pool's threads live as long as the process, and a
+  // builder that keeps its 5 MB of work arrays does not map and page-fault them again for every
+  // granule (2.7 of 37 ms on the build host)
+  static thread_local LatticeBuilder g;
   g.x = h_x;
   g.y = h_y;
   g.rows = n_rows;
@@ -549,7 +552,7 @@ extern "C" int64_t oisat_h_delaunay_swath_adj(const double* h_x, const double* h
     int64_t m = 0;
     for (int64_t t = 0; t < g.ntri; ++t)
       if (g.tri[3 * t] >= 0) slot[(size_t)t] = (int32_t)m++;
-    if (m > tri_capacity) return OISAT_E_ARG;
+    if (m > tri_capacity) { g.release_if_large(); return OISAT_E_ARG; }
     for (int64_t t = 0; t < g.ntri; ++t) {
       const int32_t u = slot[(size_t)t];
       if (u < 0) continue;
@@ -561,8 +564,10 @@ extern "C" int64_t oisat_h_delaunay_swath_adj(const double* h_x, const double* h
     }
     if (n_ties) *n_ties = g.ties;
     if (path) *path = 1;
+    g.release_if_large();
     return m;
   }
+  g.release_if_large();
   if (path) *path = 0;
   return oisat_h_delaunay(h_x, h_y, n_rows * n_cols, h_tri, tri_capacity, n_ties);
 }

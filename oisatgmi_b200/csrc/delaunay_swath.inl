@@ -26,6 +26,8 @@ struct LatticeBuilder {
   int32_t G = 0;                          // ghost vertex id (= n)
   std::vector<int32_t> tri, half, stack;  // every half-edge has a twin while ghosts exist
   std::vector<int32_t> vtri;              // per vertex: a triangle that has it (ghost or real), -1 before insertion
+  std::vector<int32_t> ord, hull_next;    // work arrays kept as members: a builder that is reused
+  std::vector<uint8_t> lev, seen;         // (one per thread, see delaunay.cpp) keeps their pages
   int64_t ntri = 0, flips = 0, ties = 0;
 
   static int32_t next(int32_t e) { return e % 3 == 2 ? e - 2 : e + 1; }
@@ -140,6 +142,8 @@ struct LatticeBuilder {
     if (rows < 2 || cols < 2) return -1;
     n = rows * cols;
     if (n > (int64_t)0x1fffffff) return -1;
+    ntri = flips = ties = 0;
+    stack.clear();
     for (int64_t i = 0; i < n; ++i)
       if (!(std::fabs(x[i]) <= 1e300) || !(std::fabs(y[i]) <= 1e300)) return -1;
     G = (int32_t)n;
@@ -184,12 +188,12 @@ struct LatticeBuilder {
         }
       }
     }
-    std::vector<int32_t> ord;
-    std::vector<uint8_t> lev;             // level index (0 = finest) each point enters at
+    ord.clear();                          // insertion order
+    lev.clear();                          // level index (0 = finest) each point enters at
     ord.reserve(n);
     lev.reserve(n);
     {
-      std::vector<uint8_t> seen(n, 0);
+      seen.assign(n, 0);
       int cur_level = 0;
       auto push = [&](int64_t i, int64_t j) {
         const int64_t v = i * cols + j;
@@ -306,7 +310,7 @@ struct LatticeBuilder {
     }
     // hull: collinear triples make Qhull's answer non-unique; then drop the ghosts
     {
-      std::vector<int32_t> hull_next(n, -1);
+      hull_next.assign(n, -1);
       int32_t start = -1;
       for (int64_t t = 0; t < ntri; ++t) {
         const int32_t s = (int32_t)(3 * t);
@@ -335,6 +339,20 @@ struct LatticeBuilder {
       }
     }
     return 0;
+  }
+
+  // a reused builder keeps its arrays between calls unless they are large (TROPOMI-scale
+  // granules: 130 MB per thread would stay resident)
+  void release_if_large() {
+    if (tri.capacity() > (size_t)8 << 20) {
+      std::vector<int32_t>().swap(tri);
+      std::vector<int32_t>().swap(half);
+      std::vector<int32_t>().swap(vtri);
+      std::vector<int32_t>().swap(ord);
+      std::vector<int32_t>().swap(hull_next);
+      std::vector<uint8_t>().swap(lev);
+      std::vector<uint8_t>().swap(seen);
+    }
   }
 
   int64_t emit(int32_t* out, int64_t capacity) const {
