@@ -91,30 +91,47 @@ class MonthPipeline:
         self.granules = []
         self._stamps, self._fracs = _v.ctm_clock(ctm_data)
         self._ctm_dev = None
+        self._ctm_slots = []
         self._tables = None
         self._buf = None
         self.timings = {}
 
     # ------------------------------------------------------------------ inputs
     def upload_ctm(self):
-        """Model fields as [n_slots][n_lev][n_cell] float32 device tensors."""
-        if self._ctm_dev is not None:
+        """Model fields as [n_used_slots][n_lev][n_cell] float32 device tensors.  Only the
+        time slots the granules of THIS pipeline (this rank's share) refer to are uploaded
+        and `gran_slot` indexes the compact block: a non-averaged month (8 slots a day, 44 GB
+        for the three fields) never has to be resident as a whole (amf_recal.py:39-49 picks
+        one slot per granule)."""
+        used = sorted({g.slot for g in self.granules}) or [0]
+        if self._ctm_dev is not None and set(used) <= set(self._ctm_slots):
             return self._ctm_dev
         t = _dev.torch()
+        free = self.ctm_data[0].ctmtype == "FREE"
+        per = 1 if free else int(np.asarray(self.ctm_data[0].pressure_mid).shape[0])
+
+        def slab(name, slot):
+            c = self.ctm_data[slot // per] if not free else self.ctm_data[slot]
+            a = np.asarray(getattr(c, name))
+            if a.dtype != np.float32:
+                raise _lib.OisatError("model fields must be float32 as delivered by the readers")
+            if a.ndim == 4:
+                a = a[slot % per]
+            return _dev.to_device(np.ascontiguousarray(a).reshape(1, a.shape[0], -1))
 
         def stack(name):
-            parts = []
-            for c in self.ctm_data:
-                a = np.asarray(getattr(c, name))
-                if a.dtype != np.float32:
-                    raise _lib.OisatError("model fields must be float32 as delivered by the readers")
-                if a.ndim == 3:
-                    a = a[None]
-                parts.append(_dev.to_device(a.reshape(a.shape[0], a.shape[1], -1)))
+            parts = [slab(name, s) for s in used]
             return parts[0] if len(parts) == 1 else t.cat(parts, dim=0)
 
         self._ctm_dev = (stack("pressure_mid"), stack("gas_profile"), stack("delta_p"))
+        self._ctm_slots = list(used)
+        self._tables = None            # gran_slot indexes the compact block
+        self._buf = None
         return self._ctm_dev
+
+    def share_ctm(self, other):
+        """Use the model block `other` already uploaded (one upload per month)."""
+        self._ctm_dev, self._ctm_slots = other._ctm_dev, list(other._ctm_slots)
 
     def _slot_of(self, t_sat):
         k, day, hour = _v.closest_slot(self.ctm_data, self._stamps, self._fracs, t_sat)
@@ -255,6 +272,8 @@ class MonthPipeline:
         G = self.granules
         if not G:
             raise _lib.OisatError("no granule on the grid")
+        self.upload_ctm()
+        slot_index = {s: i for i, s in enumerate(self._ctm_slots)}
         nlev = {g.nlev for g in G}
         trop = {g.has_trop for g in G}
         if len(nlev) != 1 or len(trop) != 1:
@@ -281,7 +300,7 @@ class MonthPipeline:
         t.cumsum(t.bincount(pc64, minlength=self.n_cell), 0, out=seg_start[1:])
         dev = dict(vert=vert, w=w, seg_start=seg_start, seg_pair=order, gran_px0=d(px0),
                    pair_gran=d(gran), pair_cell=pair_cell,
-                   gran_slot=d(np.array([g.slot for g in G], np.int32)))
+                   gran_slot=d(np.array([slot_index[g.slot] for g in G], np.int32)))
         self._tables = (host, dev)
         return self._tables
 
@@ -502,13 +521,14 @@ class MonthPipeline:
             ak_means = sweep_device(Sa, So, factors)   # one small D2H: 99 sums + 99 counts
             pick = knee_index(factors, ak_means)       # the reference's own kneed when importable
             xb, ak, inc, err = apply_device(ctm_vcd, sat_vcd, Sa, So, float(factors[pick]))
-            extra = dict(knee_index=pick, ak_means=ak_means, factor=float(factors[pick]))
+            extra = dict(knee_index=pick, ak_means=ak_means, factor=float(factors[pick]),
+                         knee_source="kneed" if kneed_available() else "restated-host")
         else:
             # sweep -> knee -> update on the device, no host round trip inside the step
             xb, ak, inc, err, pick, factor, ak_means = sweep_knee_apply_device(
                 ctm_vcd, sat_vcd, Sa, So, factors)
             extra = dict(knee_index=_DeviceScalar(pick, int), ak_means=_DeviceVector(ak_means),
-                         factor=_DeviceScalar(factor, float))
+                         factor=_DeviceScalar(factor, float), knee_source="restated-device")
         return dict(sat_averaged_vcd=sat_vcd, sat_averaged_error=sat_err, ctm_averaged_vcd=ctm_vcd,
                     aux1=aux1, aux2=aux2, ctm_averaged_vcd_corrected=xb, ak_OI=ak,
                     increment_OI=inc, error_OI=err, **extra)
@@ -516,6 +536,15 @@ class MonthPipeline:
     def run(self, marks=None):
         """pack -> fused -> accumulate -> OI on the current stream.  `marks`
         (a list) receives (phase, cuda event) pairs recorded on that stream."""
+        if not self.granules:
+            # a rank whose share of the month is empty (fewer days than ranks, or every granule
+            # skipped): nothing to grid, but it still owns a zero accumulator block and MUST
+            # join the all-reduce, or the other ranks wait for it forever
+            self._buf = dict(acc=_dev.zeros((10, self.n_cell)))
+            if self.pg is not None:
+                from .sharding import merge_accumulators
+                merge_accumulators(self._buf["acc"], self.pg)
+            return self.run_oi()
         if getattr(self, "_buf", None) is None:
             self.allocate()
 

@@ -7,7 +7,8 @@ cases of tests/cases.py.  Run in the build container only:
 The reference cannot travel to the GPU box; these fixtures (and this script)
 do.  Each file holds the reference's outputs plus a checksum of the generated
 inputs, so a test can tell "inputs drifted" from "outputs differ".
-3-D fields are stored for the levels in cases.LEVEL_SUBSET to keep fixtures small.
+3-D fields are stored for the levels in cases.LEVEL_SUBSET to keep fixtures small, except
+in the cases of cases.ALL_LEVELS, which keep every level.
 """
 from __future__ import annotations
 
@@ -44,89 +45,36 @@ def quiet(fn, *a, **k):
         return fn(*a, **k)
 
 
-def put(store, prefix, obj, names):
-    for n in names:
-        v = getattr(obj, n)
-        if isinstance(v, np.ndarray) and v.size > 1:
-            store["%s.%s" % (prefix, n)] = cases.subset_levels(v)
+def _with_checksum(store, granules):
+    out = {"input_sha256": np.array(checksum(granules))}
+    out.update(store)
+    return out
 
 
 def amf_chain(ref, name):
-    c = cases.amf_case(name)
-    store = {"input_sha256": np.array(checksum(c["granules"]))}
-    rcls = ref.config.satellite_amf
-    grids = []
-    for i, g in enumerate(c["granules"]):
-        r = quiet(ref.interpolator, c["kind"], c["grid_size"], config.convert(cases.clone(g), rcls),
-                  c["coords"], flag_thresh=c["flag_thresh"])
-        assert r is not None
-        put(store, "interp%d" % i, r, ["vcd", "amf", "tropopause", "uncertainty", "pressure_mid",
-                                        "scattering_weights"])
-        grids.append(r)
-    rctm = [config.convert(m, ref.config.ctm_model) for m in c["ctm"]]
-    grids = quiet(ref.amf_recal, rctm, grids)
-    for i, r in enumerate(grids):
-        put(store, "amf%d" % i, r, ["vcd", "ctm_vcd", "new_amf", "old_amf"])
-    avg = quiet(ref.averaging, "2005-06-01", "2005-07-01", cases.reader_ns(grids))
-    for n, v in zip(["sat_vcd", "sat_err", "ctm_vcd", "aux1", "aux2"], avg[:5]):
-        store["avg." + n] = v
-    d = ref.driver.oisatgmi()
-    d.sat_averaged_vcd, d.sat_averaged_error, d.ctm_averaged_vcd, d.aux1, d.aux2 = \
-        [np.array(v) for v in avg[:5]]
-    quiet(d.bias_correct, c["sensor"], c["gas"])
-    quiet(d.oi, c["sensor"], 50.0)
-    store["oi.y"] = d.sat_averaged_vcd
-    for n in ["ctm_averaged_vcd_corrected", "ak_OI", "increment_OI", "error_OI"]:
-        store["oi." + n] = getattr(d, n)
-    # knee-free variant pins everything in OI except the third-party knee
-    y2 = np.array(avg[0])
-    r2 = quiet(ref.OI, np.array(avg[2]), y2, (np.array(avg[2]) * 0.5) ** 2, np.array(avg[1]) ** 2,
-               regularization_on=False)
-    for n, v in zip(["xb", "ak", "inc", "err"], r2):
-        store["oi_noreg." + n] = v
-    return store
+    """tests/chains.py drives the reference's own functions (chains.reference_impl): the
+    fixtures hold exactly the keys the tests compare."""
+    import chains
+    return _with_checksum(chains.amf_chain(chains.reference_impl(), name)[0],
+                          cases.amf_case(name)["granules"])
 
 
 def mopitt_chain(ref):
-    c = cases.mopitt_case()
-    store = {"input_sha256": np.array(checksum(c["granules"]))}
-    grids = []
-    for i, g in enumerate(c["granules"]):
-        r = quiet(ref.interpolator, 1, c["grid_size"],
-                  config.convert(cases.clone(g), ref.config.satellite_opt), c["coords"],
-                  flag_thresh=c["flag_thresh"])
-        assert r is not None and r.ctm_upscaled_needed
-        put(store, "interp%d" % i, r, ["vcd", "uncertainty", "x_col", "aprior_column",
-                                        "surface_pressure", "apriori_surface", "pressure_mid",
-                                        "averaging_kernels", "apriori_profile"])
-        grids.append(r)
-    rctm = [config.convert(m, ref.config.ctm_model) for m in c["ctm"]]
-    grids = quiet(ref.ak_conv_mopitt, rctm, grids)
-    for i, r in enumerate(grids):
-        put(store, "ak%d" % i, r, ["ctm_vcd", "ctm_xcol"])
-    return store
+    import chains
+    return _with_checksum(chains.mopitt_chain(chains.reference_impl())[0],
+                          cases.mopitt_case()["granules"])
 
 
 def gosat_chain(ref):
-    c = cases.gosat_case()
-    store = {"input_sha256": np.array(checksum(c["granules"]))}
-    grids = []
-    for i, g in enumerate(c["granules"]):
-        f = quiet(ref.filler_gosatxch4, 1.0, config.convert(cases.clone(g), ref.config.satellite_opt),
-                  flag_thresh=0.0)
-        assert f is not None
-        put(store, "fill%d" % i, f, ["vcd", "x_col", "uncertainty", "quality_flag", "pressure_mid",
-                                      "averaging_kernels", "apriori_profile", "pressure_weight"])
-        r = quiet(ref.interpolator, 1, c["grid_size"], f, c["coords"], flag_thresh=0.0)
-        assert r is not None and r.ctm_upscaled_needed
-        put(store, "interp%d" % i, r, ["vcd", "uncertainty", "x_col", "pressure_mid",
-                                        "averaging_kernels", "apriori_profile", "pressure_weight"])
-        grids.append(r)
-    rctm = [config.convert(m, ref.config.ctm_model) for m in c["ctm"]]
-    grids = quiet(ref.ak_conv_gosat, rctm, grids)
-    for i, r in enumerate(grids):
-        put(store, "ak%d" % i, r, ["ctm_xcol"])
-    return store
+    import chains
+    return _with_checksum(chains.gosat_chain(chains.reference_impl())[0],
+                          cases.gosat_case()["granules"])
+
+
+def o3_chain(ref):
+    import chains
+    return _with_checksum(chains.o3_chain(chains.reference_impl())[0],
+                          cases.o3_case()["granules"])
 
 
 READER_CALLS = [("omi_no2", (True,)), ("omi_no2", (False,)), ("omi_hcho", ()),
@@ -168,6 +116,7 @@ def main():
     jobs = {name: (lambda n=name: amf_chain(ref, n)) for name in cases.CASES}
     jobs["mopitt_co"] = lambda: mopitt_chain(ref)
     jobs["gosat_xch4"] = lambda: gosat_chain(ref)
+    jobs["omi_o3"] = lambda: o3_chain(ref)
     for product in cases.READER_PRODUCTS:
         jobs["reader_" + product] = lambda p=product: reader_chain(ref, p)
     only = sys.argv[1:]

@@ -12,7 +12,8 @@ from oisatgmi_b200 import synth
 
 REGION = (30.0, 50.0, -105.0, -75.0)        # 41 x 49 model cells
 REGION_AK = (10.0, 60.0, -130.0, -60.0)     # MOPITT / GOSAT: 1 degree lattice needs room
-LEVEL_SUBSET = (0, 5, -1)                    # 3-D fields are stored for these levels only
+LEVEL_SUBSET = (0, 5, -1)                    # 3-D fields are stored for these levels only ...
+ALL_LEVELS = ("omi_hcho",)                   # ... except in these cases: every level is compared
 
 
 def coords(region=REGION):
@@ -116,6 +117,17 @@ def gosat_case():
     grans = [synth.make_gosat_soundings(41 + i, n=1500, region=(15.0, 55.0, -125.0, -65.0),
                                         time=datetime.datetime(2005, 6, 6 + i, 3)) for i in range(2)]
     return dict(granules=grans, coords=c, ctm=model, grid_size=1.0, flag_thresh=0.0)
+
+
+def o3_case():
+    """OMI total O3 as omi_reader_o3 hands it over (reader.py:1037-1042): no scattering
+    weights, no tropopause, `amf` = the column itself, `pressure_mid` an empty list."""
+    granules = amf_granules("OMI_O3", (23, 24), 220, 60)
+    for g in granules:
+        g.amf = g.vcd
+        g.pressure_mid = []
+    return dict(granules=granules, coords=coords(), ctm=ctm(gas_scale=30.0), grid_size=0.25,
+                flag_thresh=0.0, sensor="OMI", gas="O3")
 
 
 def reader_ns(sat_data, ctm_data=None):

@@ -6,11 +6,11 @@ import numpy as np
 import cases
 
 
-def put(store, prefix, obj, names):
+def put(store, prefix, obj, names, all_levels=False):
     for n in names:
         v = getattr(obj, n)
         if isinstance(v, np.ndarray) and v.size > 1:
-            store["%s.%s" % (prefix, n)] = cases.subset_levels(v)
+            store["%s.%s" % (prefix, n)] = v if all_levels else cases.subset_levels(v)
 
 
 def amf_chain(impl, name, stop_after=None):
@@ -23,7 +23,7 @@ def amf_chain(impl, name, stop_after=None):
                               flag_thresh=c["flag_thresh"])
         assert r is not None
         put(store, "interp%d" % i, r, ["vcd", "amf", "tropopause", "uncertainty", "pressure_mid",
-                                        "scattering_weights"])
+                                        "scattering_weights"], all_levels=name in cases.ALL_LEVELS)
         grids.append(r)
     if stop_after == "interp":
         return store, grids
@@ -50,6 +50,36 @@ def amf_chain(impl, name, stop_after=None):
     return store, grids
 
 
+def month_tail(impl, store, sensor, gas, ctm, grids, per_granule, skip_aux=False):
+    """The rest of the month exactly as run/job.py:61-84 drives it, through the `oisatgmi`
+    class of the implementation (driver.py:36-114): conv_ak / recal_amf -> average ->
+    bias_correct -> oi.  `per_granule`: names stored after the vertical stage.
+    skip_aux: granules without scattering weights carry np.empty(1) air-mass factors
+    (amf_recal.py:169-170), so aux1 / aux2 are uninitialised memory."""
+    d = impl.driver(ctm, grids)
+    if sensor in ("MOPITT", "GOSAT"):
+        d.conv_ak(sensor)
+    else:
+        d.recal_amf()
+    grids = d.reader_obj.sat_data
+    tag = "ak" if sensor in ("MOPITT", "GOSAT") else "amf"
+    for i, r in enumerate(grids):
+        put(store, "%s%d" % (tag, i), r, per_granule)
+    d.average("2005-06-01", "2005-07-01", gasname=gas)
+    names = ["sat_vcd", "sat_err", "ctm_vcd"] + ([] if skip_aux else ["aux1", "aux2"])
+    for n, a in zip(names, ["sat_averaged_vcd", "sat_averaged_error", "ctm_averaged_vcd",
+                            "aux1", "aux2"]):
+        store["avg." + n] = np.array(getattr(d, a))
+    d.bias_correct(sensor, gas)
+    d.oi(sensor, error_ctm=50.0)
+    # OI clips its Y argument in place (optimal_interpolation.py:14): the satellite mean for
+    # every sensor but GOSAT, whose Y is aux1 (driver.py:113-114)
+    store["oi.y"] = np.array(d.aux1 if sensor == "GOSAT" else d.sat_averaged_vcd)
+    for n in ["ctm_averaged_vcd_corrected", "ak_OI", "increment_OI", "error_OI"]:
+        store["oi." + n] = np.array(getattr(d, n))
+    return grids
+
+
 def mopitt_chain(impl):
     c = cases.mopitt_case()
     store = {}
@@ -62,9 +92,7 @@ def mopitt_chain(impl):
                                         "surface_pressure", "apriori_surface", "pressure_mid",
                                         "averaging_kernels", "apriori_profile"])
         grids.append(r)
-    grids = impl.ak_conv_mopitt(c["ctm"], grids)
-    for i, r in enumerate(grids):
-        put(store, "ak%d" % i, r, ["ctm_vcd", "ctm_xcol"])
+    grids = month_tail(impl, store, "MOPITT", "CO", c["ctm"], grids, ["ctm_vcd", "ctm_xcol"])
     return store, grids
 
 
@@ -82,19 +110,85 @@ def gosat_chain(impl):
         put(store, "interp%d" % i, r, ["vcd", "uncertainty", "x_col", "pressure_mid",
                                         "averaging_kernels", "apriori_profile", "pressure_weight"])
         grids.append(r)
-    grids = impl.ak_conv_gosat(c["ctm"], grids)
-    for i, r in enumerate(grids):
-        put(store, "ak%d" % i, r, ["ctm_xcol"])
+    grids = month_tail(impl, store, "GOSAT", "CH4", c["ctm"], grids, ["ctm_xcol"])
     return store, grids
+
+
+def o3_chain(impl):
+    """OMI total O3: no scattering weights, so amf_recal only grabs the model column
+    (amf_recal.py:160-171) and average() converts it to Dobson units (driver.py:62-63)."""
+    c = cases.o3_case()
+    store = {}
+    grids = []
+    for i, g in enumerate(c["granules"]):
+        r = impl.interpolator(1, c["grid_size"], cases.clone(g), c["coords"],
+                              flag_thresh=c["flag_thresh"])
+        assert r is not None
+        put(store, "interp%d" % i, r, ["vcd", "amf", "uncertainty"])
+        assert np.size(r.scattering_weights) == 1 and np.size(r.tropopause) == 1
+        grids.append(r)
+    grids = month_tail(impl, store, "OMI", "O3", c["ctm"], grids, ["vcd", "ctm_vcd"],
+                       skip_aux=True)
+    return store, grids
+
+
+def _attached(d, ctm, grids):
+    d.reader_obj = cases.reader_ns(grids, ctm)
+    return d
 
 
 def oracle_impl():
     import types
-    from oracle import averaging as oavg, interp as ointerp, oi as ooi, vertical as overt
+    from oracle import averaging as oavg, driver as odriver, interp as ointerp, oi as ooi, vertical as overt
     return types.SimpleNamespace(
         interpolator=ointerp.interpolator, filler_gosatxch4=ointerp.filler_gosatxch4,
         amf_recal=overt.amf_recal, ak_conv_mopitt=overt.ak_conv_mopitt,
-        ak_conv_gosat=overt.ak_conv_gosat, averaging=oavg.averaging, OI=ooi.OI, bias=ooi.BIAS)
+        ak_conv_gosat=overt.ak_conv_gosat, averaging=oavg.averaging, OI=ooi.OI, bias=ooi.BIAS,
+        driver=lambda ctm, grids: _attached(odriver.oisatgmi(), ctm, grids))
+
+
+def reference_impl():
+    """The LIVE unmodified reference (build container only, through oracle/ref_shim.py):
+    what oracle/make_golden.py records and tests/test_oracle_vs_reference.py compares with."""
+    import contextlib
+    import io
+    import types
+    from oisatgmi_b200 import config
+    from oracle import ref_shim
+    ref = ref_shim.load_reference()
+
+    def quiet(fn):
+        def run(*a, **k):
+            with contextlib.redirect_stdout(io.StringIO()):
+                return fn(*a, **k)
+        return run
+
+    def conv(g):
+        cls = ref.config.satellite_amf if config.kind_of(g) == "amf" else ref.config.satellite_opt
+        return g if isinstance(g, cls) else config.convert(g, cls)
+
+    def ctm(models):
+        return [m if isinstance(m, ref.config.ctm_model) else config.convert(m, ref.config.ctm_model)
+                for m in models]
+
+    class QuietDriver(ref.driver.oisatgmi):
+        pass
+
+    for meth in ("recal_amf", "conv_ak", "average", "bias_correct", "oi"):
+        setattr(QuietDriver, meth, quiet(getattr(ref.driver.oisatgmi, meth)))
+
+    return types.SimpleNamespace(
+        interpolator=quiet(lambda k, gs, g, c, flag_thresh=0.75: ref.interpolator(
+            k, gs, conv(g), c, flag_thresh=flag_thresh)),
+        filler_gosatxch4=quiet(lambda gs, g, flag_thresh=0.75: ref.filler_gosatxch4(
+            gs, conv(g), flag_thresh=flag_thresh)),
+        amf_recal=quiet(lambda m, s: ref.amf_recal(ctm(m), s)),
+        ak_conv_mopitt=quiet(lambda m, s: ref.ak_conv_mopitt(ctm(m), s)),
+        ak_conv_gosat=quiet(lambda m, s: ref.ak_conv_gosat(ctm(m), s)),
+        averaging=quiet(ref.averaging), OI=quiet(ref.OI),
+        bias={("TROPOMI", "NO2"): (0.32, 0.66), ("TROPOMI", "HCHO"): (0.90, 0.59),
+              ("OMI", "NO2"): (0.32, 0.63), ("OMI", "HCHO"): (0.821, 0.79)},
+        driver=lambda models, grids: _attached(QuietDriver(), ctm(models), grids))
 
 
 def cuda_impl():
@@ -105,7 +199,8 @@ def cuda_impl():
         interpolator=interpolator.interpolator, filler_gosatxch4=filler_gosat.filler_gosatxch4,
         amf_recal=amf_recal.amf_recal, ak_conv_mopitt=ak_conv_mopitt.ak_conv_mopitt,
         ak_conv_gosat=ak_conv_gosat.ak_conv_gosat, averaging=averaging.averaging,
-        OI=optimal_interpolation.OI, bias=driver.BIAS_CORRECTION)
+        OI=optimal_interpolation.OI, bias=driver.BIAS_CORRECTION,
+        driver=lambda ctm, grids: _attached(driver.oisatgmi(), ctm, grids))
 
 
 READER_CALLS = [("omi_no2", (True,)), ("omi_no2", (False,)), ("omi_hcho", ()),

@@ -11,7 +11,7 @@ from util import assert_field
 # fields that pass through numpy's float32 log (amf_recal.py:108) can move in the
 # last float32 ulp between CPUs with different SIMD dispatch; everything else is
 # float64 arithmetic in a fixed order
-LOOSE = ("amf", "avg.", "oi")
+LOOSE = ("amf", "ak", "avg.", "oi")
 
 
 def _compare(store, gold):
@@ -36,6 +36,11 @@ def test_mopitt_chain_matches_reference_fixture(golden):
 def test_gosat_chain_matches_reference_fixture(golden):
     store, _ = chains.gosat_chain(chains.oracle_impl())
     _compare(store, golden("gosat_xch4"))
+
+
+def test_o3_chain_matches_reference_fixture(golden):
+    store, _ = chains.o3_chain(chains.oracle_impl())
+    _compare(store, golden("omi_o3"))
 
 
 def test_inputs_did_not_drift(golden):

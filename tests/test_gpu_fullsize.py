@@ -124,3 +124,40 @@ def test_tropomi_scale_isolated_near_tie_does_not_need_qhull(monkeypatch):
                           np.sort(p1.vert.reshape(S // 3, 3, n), axis=1))
     assert np.allclose(np.sort(p0.w.reshape(S // 3, 3, n), axis=1),
                        np.sort(p1.w.reshape(S // 3, 3, n), axis=1), rtol=0, atol=1e-9)
+
+
+def test_full_omi_hcho_granule_on_global_grid_vs_oracle():
+    """One full-size OMI HCHO granule (1644 x 60 px, 47 levels) whose orbit runs across the
+    date line, on the global 361 x 576 GMI grid: VALUES of the CUDA path against the oracle
+    (about a minute of CPU), not properties -- through the drop-in functions
+    (interpolator -> amf_recal, every gridded field and level) and through the fused month
+    pipeline (a one-granule month: the means are the granule's own grids)."""
+    import types
+    from oisatgmi_b200 import amf_recal as _amf, interpolator as _interp
+    from oisatgmi_b200.pipeline import MonthPipeline
+    from oracle import interp as ointerp, vertical as overt
+    from util import assert_field
+    coords = synth.ctm_coordinates(None)
+    model = [synth.make_ctm(11, coords, averaged=True)]
+    g = synth.make_amf_granule(77, "OMI_HCHO", geo=dict(node_lon_deg=172.0), bad_fraction=0.2,
+                               time=datetime.datetime(2005, 6, 9, 1, 40, 0))
+    lon = np.asarray(g.longitude_center)
+    assert lon.shape == (1644, 60) and lon.max() > 179.0 and lon.min() < -179.0   # both sides
+    want = ointerp.interpolator(1, 0.25, copy.deepcopy(g), coords, flag_thresh=0.0)
+    got = _interp.interpolator(1, 0.25, copy.deepcopy(g), coords, flag_thresh=0.0)
+    assert want is not None and got is not None
+    for name in ("vcd", "amf", "uncertainty", "pressure_mid", "scattering_weights"):
+        assert_field(getattr(got, name), getattr(want, name), "interp." + name, rtol=1e-12)
+    assert np.isfinite(want.vcd).sum() > 10_000
+    overt.amf_recal(model, [want])
+    _amf.amf_recal(model, [got])
+    for name in ("vcd", "ctm_vcd", "new_amf", "old_amf"):
+        assert_field(getattr(got, name), getattr(want, name), "amf." + name)
+    pipe = MonthPipeline(model, 0.25, 0.0, sensor="OMI", gas="HCHO")
+    assert pipe.add_granule(copy.deepcopy(g))
+    res = pipe.results_to_host(pipe.run())
+    assert_field(res["sat_averaged_vcd"], want.vcd, "fused.vcd")
+    assert_field(res["sat_averaged_error"], want.uncertainty, "fused.sigma")
+    assert_field(res["ctm_averaged_vcd"], want.ctm_vcd, "fused.ctm_vcd")
+    assert_field(res["aux1"], want.new_amf, "fused.new_amf")
+    assert_field(res["aux2"], want.old_amf, "fused.old_amf")

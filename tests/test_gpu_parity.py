@@ -52,6 +52,15 @@ def test_gosat_chain_vs_oracle_and_golden(golden):
     _compare(got, golden("gosat_xch4"), tight=("interp", "fill"))
 
 
+def test_o3_chain_vs_oracle_and_golden(golden):
+    """Granules without scattering weights: oisat_vertical_column (amf_recal.py:160-171), the
+    Dobson-unit conversion of average() and OI on the result, through the oisatgmi class."""
+    got, _ = chains.o3_chain(chains.cuda_impl())
+    want, _ = chains.o3_chain(chains.oracle_impl())
+    print("o3", _compare(got, want, tight=("interp",)))
+    _compare(got, golden("omi_o3"), tight=("interp",))
+
+
 def test_distance_predicate_is_bit_exact():
     """K0 against scipy's cKDTree distances, including nodes that sit within one
     ulp of the threshold."""

@@ -18,34 +18,7 @@ pytestmark = pytest.mark.skipif(not ref_shim.reference_available(),
                                 reason="reference tree not present on this machine")
 
 
-def reference_impl():
-    ref = ref_shim.load_reference()
-
-    def quiet(fn):
-        def run(*a, **k):
-            with contextlib.redirect_stdout(io.StringIO()):
-                return fn(*a, **k)
-        return run
-
-    def conv(g):
-        cls = ref.config.satellite_amf if config.kind_of(g) == "amf" else ref.config.satellite_opt
-        return g if isinstance(g, cls) else config.convert(g, cls)
-
-    def ctm(models):
-        return [m if isinstance(m, ref.config.ctm_model) else config.convert(m, ref.config.ctm_model)
-                for m in models]
-
-    return types.SimpleNamespace(
-        interpolator=quiet(lambda k, gs, g, c, flag_thresh=0.75: ref.interpolator(
-            k, gs, conv(g), c, flag_thresh=flag_thresh)),
-        filler_gosatxch4=quiet(lambda gs, g, flag_thresh=0.75: ref.filler_gosatxch4(
-            gs, conv(g), flag_thresh=flag_thresh)),
-        amf_recal=quiet(lambda m, s: ref.amf_recal(ctm(m), s)),
-        ak_conv_mopitt=quiet(lambda m, s: ref.ak_conv_mopitt(ctm(m), s)),
-        ak_conv_gosat=quiet(lambda m, s: ref.ak_conv_gosat(ctm(m), s)),
-        averaging=quiet(ref.averaging), OI=quiet(ref.OI),
-        bias={("TROPOMI", "NO2"): (0.32, 0.66), ("TROPOMI", "HCHO"): (0.90, 0.59),
-              ("OMI", "NO2"): (0.32, 0.63), ("OMI", "HCHO"): (0.821, 0.79)})
+reference_impl = chains.reference_impl
 
 
 def _same(a, b):
@@ -65,6 +38,10 @@ def test_mopitt_chain_is_bit_identical_to_reference():
 
 def test_gosat_chain_is_bit_identical_to_reference():
     _same(chains.gosat_chain(chains.oracle_impl())[0], chains.gosat_chain(reference_impl())[0])
+
+
+def test_o3_chain_is_bit_identical_to_reference():
+    _same(chains.o3_chain(chains.oracle_impl())[0], chains.o3_chain(reference_impl())[0])
 
 
 def test_bias_table_matches_driver():

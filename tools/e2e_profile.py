@@ -35,7 +35,7 @@ def main():
         t0 = time.perf_counter()
         p = new_pipe()
         if ctm_dev is not None:
-            p._ctm_dev = ctm_dev
+            p._ctm_dev, p._ctm_slots = ctm_dev
         pra = cProfile.Profile()
         if os.environ.get("OISAT_PLAN_TRACE") != "1":
             pra.enable()
@@ -55,14 +55,14 @@ def main():
         out = p.results_to_host(p.run())
         torch.cuda.synchronize()
         t3 = time.perf_counter()
-        ctm_dev = p._ctm_dev
+        ctm_dev = (p._ctm_dev, list(p._ctm_slots))
         print("iter %d: add_day %.1f ms, allocate %.1f ms, run+d2h %.1f ms" %
               (it, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3), flush=True)
         if it == 2:
             pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
             pr2 = cProfile.Profile()
             p = new_pipe()
-            p._ctm_dev = ctm_dev
+            p._ctm_dev, p._ctm_slots = ctm_dev
             p.add_day(day, hosts=hosts)
             p.allocate()
             torch.cuda.synchronize()
