@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OISAT_ABI_VERSION 1
+#define OISAT_ABI_VERSION 2
 
 enum {
   OISAT_OK = 0,
@@ -378,6 +378,13 @@ int oisat_pack_batch_indexed(const oisat_pack_item* items, int32_t n_items, int6
                              const int32_t* block_item, int32_t n_sat_lev, int32_t has_trop,
                              int32_t qflag_dtype, double flag_thresh, int32_t amf_dtype,
                              void* records, double* amf_masked, void* stream);
+/* The same, also writing the mask itself: px_bad[px0 + p] = 1 where NOT(qflag > flag_thresh)
+ * (interpolator.py:126), [total pixels] device bytes, NULL = not wanted.  oisat_pair_alive
+ * reads it. */
+int oisat_pack_batch_masked(const oisat_pack_item* items, int32_t n_items, int64_t total_blocks,
+                            const int32_t* block_item, int32_t n_sat_lev, int32_t has_trop,
+                            int32_t qflag_dtype, double flag_thresh, int32_t amf_dtype,
+                            void* records, double* amf_masked, uint8_t* px_bad, void* stream);
 
 /* derived model fields, once per month instead of once per granule
  * (amf_recal.py:151-152): logp = float32 log(p_mid) (:108), pcol = float32 partial
@@ -436,7 +443,27 @@ typedef struct oisat_fused_args {
    * pair_ctm_off[p] = gran_slot[pair_granule[p]] * n_ctm_lev * n_cell + pair_cell[p] */
   const int64_t* pair_record0;
   const uint32_t* pair_ctm_off;
+  /* optional, tile form only (NULL = every pair): the pairs without a masked stencil pixel,
+   * alive_pairs[0 .. *n_alive), both device memory written by oisat_pair_alive, which has
+   * then already staged row 4 (old AMF) of the live pairs and all five NaNs of the others;
+   * the kernel covers the listed pairs and leaves the rest alone. */
+  const int32_t* alive_pairs;
+  const int64_t* n_alive;
 } oisat_fused_args;
+
+/* Pairs that can hold a value: a masked pixel is a NaN vertex for every field
+ * (interpolator.py:126-128,163) and a NaN vertex makes the gridded cell NaN whatever its
+ * weight, so a pair with one masked pixel among its 3*nwin stencil vertices is NaN in all
+ * five staged rows.  One pass over the stencil tables and the mask bytes of
+ * oisat_pack_batch_masked: dead pairs get their NaNs, live pairs their gridded old AMF
+ * (staged row 4; same products and summation tree as the gather kernels, same bits) and a
+ * place in alive_pairs ([n_pairs] int32; *n_alive = how many; neighbours stay neighbours).
+ * pair_record0 may be NULL when pair_granule and gran_px0 are given. */
+int oisat_pair_alive(int64_t n_pairs, int32_t nwin, const int32_t* vert, const double* w,
+                     const int64_t* pair_record0, const int32_t* pair_granule,
+                     const int64_t* gran_px0, const uint8_t* px_bad, const double* amf_masked,
+                     double box_weight, double* staged, int32_t* alive_pairs, int64_t* n_alive,
+                     void* stream);
 
 int oisat_fused_amf(const oisat_fused_args* h_args, void* stream);
 

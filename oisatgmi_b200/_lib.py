@@ -40,7 +40,7 @@ class FusedArgs(C.Structure):
         ("has_trop", i32),
         ("ctm_pmid", vp), ("ctm_logp", vp), ("ctm_pcol", vp), ("n_ctm_lev", i32), ("n_cell", i64),
         ("staged", vp), ("pair_granule", vp), ("pair_cell", vp),
-        ("pair_record0", vp), ("pair_ctm_off", vp),
+        ("pair_record0", vp), ("pair_ctm_off", vp), ("alive_pairs", vp), ("n_alive", vp),
     ]
 
 
@@ -97,6 +97,8 @@ PROTOTYPES = {
     "oisat_pack_blocks": (i64, [i64]),
     "oisat_pack_batch": (C.c_int, [vp, i32, i64, i32, i32, i32, f64, i32, vp, vp, vp]),
     "oisat_pack_batch_indexed": (C.c_int, [vp, i32, i64, vp, i32, i32, i32, f64, i32, vp, vp, vp]),
+    "oisat_pack_batch_masked": (C.c_int, [vp, i32, i64, vp, i32, i32, i32, f64, i32, vp, vp, vp, vp]),
+    "oisat_pair_alive": (C.c_int, [i64, i32, vp, vp, vp, vp, vp, vp, vp, f64, vp, vp, vp, vp]),
     "oisat_ctm_prepare": (C.c_int, [vp, vp, vp, i64, vp, vp, vp]),
     "oisat_fused_amf": (C.c_int, [C.POINTER(FusedArgs), vp]),
     "oisat_rows_per_pair": (i64, [i32, i32]),

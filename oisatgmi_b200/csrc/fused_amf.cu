@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256, 4)
 pack_batch_kernel(const oisat_pack_item* __restrict__ items, int n_items, int L, int has_trop,
                   int qflag_dtype, double thresh, int amf_dtype, __half* __restrict__ records,
                   double* __restrict__ amf_masked, int use_bulk,
-                  const int32_t* __restrict__ block_item) {
+                  const int32_t* __restrict__ block_item, uint8_t* __restrict__ px_bad) {
   extern __shared__ __align__(128) __half tile[];
   __shared__ unsigned char bad[kPackPixels];
   __shared__ __align__(8) unsigned long long mbar;
@@ -238,6 +238,7 @@ pack_batch_kernel(const oisat_pack_item* __restrict__ items, int n_items, int L,
       if (p < it.n_px) {
         is_bad = !(load_as_double(it.qflag, qflag_dtype, p) > thresh);
         amf_masked[it.px0 + p] = is_bad ? qnan() : load_as_double(it.amf, amf_dtype, p);
+        if (px_bad) px_bad[it.px0 + p] = is_bad ? 1 : 0;
       }
       bad[threadIdx.x] = is_bad ? 1 : 0;
     }
@@ -592,6 +593,16 @@ extern "C" int oisat_pack_batch_indexed(const oisat_pack_item* items, int32_t n_
                                         int32_t n_sat_lev, int32_t has_trop, int32_t qflag_dtype,
                                         double flag_thresh, int32_t amf_dtype, void* records,
                                         double* amf_masked, void* stream) {
+  return oisat_pack_batch_masked(items, n_items, total_blocks, block_item, n_sat_lev, has_trop,
+                                 qflag_dtype, flag_thresh, amf_dtype, records, amf_masked, nullptr,
+                                 stream);
+}
+
+extern "C" int oisat_pack_batch_masked(const oisat_pack_item* items, int32_t n_items,
+                                       int64_t total_blocks, const int32_t* block_item,
+                                       int32_t n_sat_lev, int32_t has_trop, int32_t qflag_dtype,
+                                       double flag_thresh, int32_t amf_dtype, void* records,
+                                       double* amf_masked, uint8_t* px_bad, void* stream) {
   if (n_items <= 0 || total_blocks <= 0) return OISAT_OK;
   OISAT_CHECK_ARG(items && records && amf_masked, "null pointer");
   OISAT_CHECK_ARG(amf_dtype == OISAT_F16 || amf_dtype == OISAT_F32 || amf_dtype == OISAT_F64,
@@ -609,7 +620,7 @@ extern "C" int oisat_pack_batch_indexed(const oisat_pack_item* items, int32_t n_
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pack_batch_kernel<<<(unsigned)total_blocks, 256, smem, (cudaStream_t)stream>>>(
       items, n_items, n_sat_lev, has_trop, qflag_dtype, flag_thresh, amf_dtype, (__half*)records,
-      amf_masked, use_bulk, block_item);
+      amf_masked, use_bulk, block_item, px_bad);
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
 }

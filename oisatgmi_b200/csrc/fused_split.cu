@@ -566,6 +566,7 @@ struct TileSmem {   // static part
   };
   double old_amf[16];
   int unsorted[16];
+  int pair_id[16];    // pair of tile slot p (alive_pairs[16 * tile + p])
 };
 
 // H = levels per thread and half (ceil(ceil(n_ctm / 8) / 2) <= H).  CL / CS / CN: the
@@ -603,8 +604,13 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
   // known now, so the model column's offset is loaded early and the column itself is
   // prefetched into L2 while the records are in flight
   const int p = threadIdx.x & 15, t = threadIdx.x >> 4;
-  const int64_t vpair = (int64_t)blockIdx.x * 16 + p;
-  const bool live = vpair < A.n_pairs;
+  // the tile's pairs come from the compact list of pairs without a masked pixel
+  // (oisat_pair_alive); blocks beyond the list have nothing to do
+  const int64_t n_act = *A.n_alive;
+  if ((int64_t)blockIdx.x * 16 >= n_act) return;
+  const int64_t vslot = (int64_t)blockIdx.x * 16 + p;
+  const bool live = vslot < n_act;
+  const int64_t vpair = A.alive_pairs[live ? vslot : n_act - 1];
   const uint32_t stride = (uint32_t)A.n_cell;
   uint32_t off = 0;
   if (live)
@@ -630,15 +636,17 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
     // come from a small shared table (filled in the half-warp layout, which also keeps the
     // AMF term's summation tree) instead of shuffles.  Same arithmetic, same order.
     const int64_t pair_raw = (int64_t)blockIdx.x * 16 + col;
-    const bool mine = pair_raw < A.n_pairs;
-    const int64_t pair = mine ? pair_raw : A.n_pairs - 1;
-    int64_t rec0, px0;
+    const bool mine = pair_raw < n_act;
+    const int64_t pair = A.alive_pairs[mine ? pair_raw : n_act - 1];
+    if (gl == 0) {
+      sm.pair_id[col] = (int)pair;
+      sm.old_amf[col] = A.staged[4 * A.n_pairs + pair];   // gridded by oisat_pair_alive
+    }
+    int64_t rec0;
     if (A.pair_record0) {
-      rec0 = px0 = A.pair_record0[pair];
+      rec0 = A.pair_record0[pair];
     } else {
-      const int g = A.pair_granule[pair];
-      rec0 = A.gran_record0[g];
-      px0 = A.gran_px0[g];
+      rec0 = A.gran_record0[A.pair_granule[pair]];
     }
     const uint4* records = reinterpret_cast<const uint4*>(A.records);
     const int tid = threadIdx.x;
@@ -648,7 +656,6 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
     double acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.0;
-    double acc_amf = 0.0;
     uint4* slot = stage + (pp * sweep) * nchunk + ch;                  // [pair][entry][chunk]
 #pragma unroll 1
     for (int base = 0; base < S; base += SW) {
@@ -675,11 +682,6 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      double za = 0.0;
-      if (gl < nk) za = wt * A.amf_masked[px0 + v];
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) za += __shfl_xor_sync(0xffffffffu, za, o, 16);
-      acc_amf += za;
       if (base == 0 && live) {
 #pragma unroll
         for (int i = 0; i < H; ++i) {
@@ -715,30 +717,25 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
         const int orow = row <= 2 * L ? row : row - 1;                 // tropopause follows vcd
         if (row < nrow && row != sig_row) tile[orow * kTP + pp] = acc[e] * A.box_weight;
       }
-      const int64_t my_pair = (int64_t)blockIdx.x * 16 + pp;
-      if (my_pair < A.n_pairs && ch == sig_row % nchunk)
-        A.staged[1 * A.n_pairs + my_pair] = sqrt(sig * A.box_weight_err);   // interpolator.py:188
+      if ((int64_t)blockIdx.x * 16 + pp < n_act && ch == sig_row % nchunk)
+        A.staged[1 * A.n_pairs + sm.pair_id[pp]] = sqrt(sig * A.box_weight_err);   // interpolator.py:188
     }
-    if (gl == 0) sm.old_amf[col] = acc_amf * A.box_weight;
-    if (mine && gl == 0) A.staged[4 * A.n_pairs + pair] = acc_amf * A.box_weight;
   } else
   {
     const int64_t pair_raw = (int64_t)blockIdx.x * 16 + col;
-    const bool mine = pair_raw < A.n_pairs;
-    const int64_t pair = mine ? pair_raw : A.n_pairs - 1;  // shadow work keeps the warp converged
-    int64_t rec0, px0;
+    const bool mine = pair_raw < n_act;
+    const int64_t pair = A.alive_pairs[mine ? pair_raw : n_act - 1];  // shadow work keeps the warp converged
+    if (gl == 0) sm.old_amf[col] = A.staged[4 * A.n_pairs + pair];    // gridded by oisat_pair_alive
+    int64_t rec0;
     if (A.pair_record0) {
-      rec0 = px0 = A.pair_record0[pair];
+      rec0 = A.pair_record0[pair];
     } else {
-      const int g = A.pair_granule[pair];
-      rec0 = A.gran_record0[g];
-      px0 = A.gran_px0[g];
+      rec0 = A.gran_record0[A.pair_granule[pair]];
     }
     const uint4* records = reinterpret_cast<const uint4*>(A.records);
     double acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.0;
-    double acc_amf = 0.0;
     uint4* slot = stage + (col * sweep) * nchunk + gl;                 // [pair][entry][chunk]
     const bool has_chunk = gl < nchunk;
 #pragma unroll 1
@@ -766,13 +763,8 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      // ... and while they are: the AMF term (a dependent load of its own) and, once, the
-      // prefetch of the model levels this thread evaluates in phase B
-      double za = 0.0;
-      if (gl < nk) za = wt * A.amf_masked[px0 + v];
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) za += __shfl_xor_sync(0xffffffffu, za, o, 16);
-      acc_amf += za;
+      // ... and while they are, once, the prefetch of the model levels this thread evaluates
+      // in phase B
       if (base == 0 && live) {
 #pragma unroll
         for (int i = 0; i < H; ++i) {
@@ -812,8 +804,6 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
     }
     if (mine && gl == sig_row % nchunk)
       A.staged[1 * A.n_pairs + pair] = sqrt(sig * A.box_weight_err);   // interpolator.py:188
-    if (gl == 0) sm.old_amf[col] = acc_amf * A.box_weight;
-    if (mine && gl == 0) A.staged[4 * A.n_pairs + pair] = acc_amf * A.box_weight;
   }
   __syncthreads();   // tile complete; the stage area is free
   // ---------------------------------------------------------- vertical phase
@@ -1050,8 +1040,10 @@ extern "C" int oisat_fused_amf_tile(const oisat_fused_args* h_args, void* stream
   const oisat_fused_args& a = *h_args;
   if (a.n_pairs == 0) return OISAT_OK;
   OISAT_CHECK_ARG(a.vert && a.w && a.gran_record0 && a.gran_px0 && a.gran_slot && a.records &&
-                      a.amf_masked && a.ctm_logp && a.ctm_pcol && a.staged && a.pair_cell &&
+                      a.ctm_logp && a.ctm_pcol && a.staged && a.pair_cell &&
                       a.pair_granule, "null pointer");
+  OISAT_CHECK_ARG(a.alive_pairs && a.n_alive,
+                  "the tile form runs over the live pairs: call oisat_pair_alive first");
   OISAT_CHECK_ARG(!a.has_trop || a.ctm_pmid, "tropopause masking needs the model p_mid");
   OISAT_CHECK_ARG(a.nwin >= 1 && a.n_sat_lev >= 2 && a.n_sat_lev <= kSearchRows - 1, "bad stencil");
   OISAT_CHECK_ARG(a.n_ctm_lev >= 2 && a.n_ctm_lev <= kMaxCtmLev, "bad model level count");

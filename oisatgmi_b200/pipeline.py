@@ -368,6 +368,8 @@ class MonthPipeline:
         self._buf = dict(
             records=out((host["total_px"], R), "float16"),
             amf_masked=out((host["total_px"],)),
+            px_bad=out((host["total_px"],), "uint8"),
+            alive_pairs=out((host["n_pairs"],), "int32"), n_alive=out((1,), "int64"),
             staged=out((5, host["n_pairs"])),
             acc=out((10, self.n_cell), zero=True),
             ctm_logp=out(tuple(pm.shape), "float32"), ctm_pcol=out(tuple(pm.shape), "float32"),
@@ -402,11 +404,12 @@ class MonthPipeline:
         L = _lib.lib()
         buf = self._buf
         g0 = self.granules[0]
-        _lib.check(L.oisat_pack_batch_indexed(
+        _lib.check(L.oisat_pack_batch_masked(
             buf["pack_items"].data_ptr(), len(self.granules), buf["pack_blocks"],
             buf["pack_block_item"].data_ptr(), g0.nlev, int(g0.has_trop),
             _dev.dtype_code(g0.dev["qflag"]), self.flag_thresh, _dev.dtype_code(g0.dev["amf"]),
-            buf["records"].data_ptr(), buf["amf_masked"].data_ptr(), _dev.stream()))
+            buf["records"].data_ptr(), buf["amf_masked"].data_ptr(), buf["px_bad"].data_ptr(),
+            _dev.stream()))
 
     def fused_args(self):
         host, dev = self.build_tables()
@@ -454,6 +457,9 @@ class MonthPipeline:
             dev["pair_ctm_off"] = off.to(t.int32).contiguous()
         a.pair_record0 = dev["pair_rec0"].data_ptr()
         a.pair_ctm_off = dev["pair_ctm_off"].data_ptr()
+        if self.fused_form == "tile":
+            a.alive_pairs = buf["alive_pairs"].data_ptr()
+            a.n_alive = buf["n_alive"].data_ptr()
         return a
 
     @property
@@ -483,6 +489,12 @@ class MonthPipeline:
         a = self.fused_args()
         form = self.fused_form
         if form == "tile":
+            # pairs with a masked stencil pixel are NaN in every field (interpolator.py:126-128):
+            # they get their NaNs here, the kernel runs over the compact list of the others
+            _lib.check(L.oisat_pair_alive(
+                a.n_pairs, a.nwin, a.vert, a.w, a.pair_record0, a.pair_granule, a.gran_px0,
+                self._buf["px_bad"].data_ptr(), a.amf_masked, a.box_weight, a.staged,
+                a.alive_pairs, a.n_alive, _dev.stream()))
             _lib.check(L.oisat_fused_amf_tile(C.byref(a), _dev.stream()))
         elif form == "split":
             _lib.check(L.oisat_fused_amf_split(C.byref(a), self._buf["rows"].data_ptr(),

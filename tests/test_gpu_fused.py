@@ -16,6 +16,15 @@ KEYS = {"avg.sat_vcd": None, "avg.sat_err": "sat_averaged_error", "avg.ctm_vcd":
         "oi.increment_OI": "increment_OI", "oi.error_OI": "error_OI"}
 
 
+def same_bits_where_defined(a, b):
+    """NaN at the same places, identical bits everywhere else.  (The NaNs of a pair with a
+    masked pixel are written by oisat_pair_alive in the tile form and produced by arithmetic in
+    the other forms: their payload bits are not part of the contract.)"""
+    na, nb = np.isnan(a), np.isnan(b)
+    return a.shape == b.shape and np.array_equal(na, nb) and \
+        np.array_equal(a[~na].view(np.uint64), b[~nb].view(np.uint64))
+
+
 def run_pipeline(name):
     from oisatgmi_b200.pipeline import MonthPipeline
     c = cases.amf_case(name)
@@ -157,7 +166,9 @@ def test_tile_form_is_bit_identical_to_split_form(name, monkeypatch):
     assert pipe_s.fused_form == "split" and pipe_s.check_guards()
     staged_s = pipe_s._buf["staged"].cpu().numpy()
     assert staged_t.shape == staged_s.shape and staged_t.size > 0
-    assert np.array_equal(staged_t.view(np.uint64), staged_s.view(np.uint64))
+    assert same_bits_where_defined(staged_t, staged_s)
+    n_alive = int(pipe_t._buf["n_alive"].item())
+    assert 0 < n_alive < staged_t.shape[1]            # the case does have masked pixels
     for k in res_s:
         if isinstance(res_s[k], np.ndarray):
             assert np.array_equal(res_t[k], res_s[k], equal_nan=True), k
@@ -174,7 +185,7 @@ def test_tile_form_generic_build_equals_specialised_build(name, monkeypatch):
     monkeypatch.setenv("OISAT_TILE_GENERIC", "1")
     pipe_b, _ = run_pipeline(name)
     b = pipe_b._buf["staged"].cpu().numpy()
-    assert a.size > 0 and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    assert a.size > 0 and same_bits_where_defined(a, b)
 
 
 @pytest.mark.parametrize("name", ["omi_hcho", "omi_no2", "tropomi_no2", "omi_no2_kinked"])
@@ -191,4 +202,35 @@ def test_tile_form_packed_lanes_equal_half_warp_lanes(name, monkeypatch):
     pipe_b, _ = run_pipeline(name)
     assert pipe_b.check_guards()
     b = pipe_b._buf["staged"].cpu().numpy()
-    assert a.size > 0 and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    assert a.size > 0 and same_bits_where_defined(a, b)
+
+
+def test_live_pair_list_is_exactly_the_unmasked_pairs():
+    """oisat_pair_alive against numpy: a pair is live iff none of its 3*nwin stencil pixels is
+    masked (interpolator.py:126-128); the list holds every live pair once."""
+    from oisatgmi_b200 import _dev
+    pipe, _ = run_pipeline("omi_no2")
+    host, dev = pipe.build_tables()
+    vert = _dev.to_host(dev["vert"]).astype(np.int64)            # (n_pairs, S)
+    bad = np.concatenate([~(np.asarray(g.host["qflag"].numpy(), dtype=np.float64) > pipe.flag_thresh)
+                          for g in pipe.granules])
+    px0 = host["px0"][host["gran"]]
+    want = ~bad[vert + px0[:, None]].any(axis=1)
+    n = int(pipe._buf["n_alive"].item())
+    got = np.sort(_dev.to_host(pipe._buf["alive_pairs"])[:n])
+    assert np.array_equal(got, np.flatnonzero(want))
+    staged = _dev.to_host(pipe._buf["staged"])
+    assert np.all(np.isnan(staged[:, ~want]))
+
+
+def test_month_without_granules_still_finishes():
+    """A rank whose share of the month is empty must not raise before the all-reduce (the other
+    ranks would wait for it forever): it contributes a zero accumulator block and the month
+    finalises to empty fields."""
+    from oisatgmi_b200.pipeline import MonthPipeline
+    c = cases.amf_case("omi_no2")
+    pipe = MonthPipeline(c["ctm"], c["grid_size"], c["flag_thresh"], sensor="OMI", gas="NO2")
+    res = pipe.results_to_host(pipe.run())
+    for k in ("ctm_averaged_vcd", "sat_averaged_vcd", "sat_averaged_error",
+              "ctm_averaged_vcd_corrected"):
+        assert res[k].shape == tuple(pipe.gplan.out_shape) and np.all(np.isnan(res[k])), k

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
     assert set(names) == set(_lib.PROTOTYPES), sorted(set(names) ^ set(_lib.PROTOTYPES))
     L = _lib.lib()   # loading and the calls below need no GPU
-    assert L.oisat_abi_version() == 1
+    assert L.oisat_abi_version() == 2
     assert L.oisat_pack_record_halfs(47, 0) == 96
     assert L.oisat_pack_record_halfs(35, 1) == 80
     assert L.oisat_oi_sweep_workspace(207936, 99) > 0
