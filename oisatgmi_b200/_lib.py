@@ -133,7 +133,7 @@ def lib():
             fn = getattr(h, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if h.oisat_abi_version() != 1:
+        if h.oisat_abi_version() != 2:
             raise OisatError("liboisat ABI mismatch")
         _lib = h
         return _lib

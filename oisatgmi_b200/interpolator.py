@@ -56,11 +56,13 @@ def apply_plan(gp: "_plan.GranulePlan", specs, good_dev, n_px, n_out):
         farr = (_lib.Field * len(chunk))()
         chunk_row0 = row0
         for i, s in enumerate(chunk):
-            host = _flat_levels(s.array, s.nlev, n_px)
-            d = _dev.to_device(host)
+            if hasattr(s.array, "data_ptr"):     # already on the device ([nlev * n_px], native dtype)
+                d = s.array
+            else:
+                d = _dev.to_device(_flat_levels(s.array, s.nlev, n_px))
             keep_alive.append(d)
             farr[i].data = d.data_ptr()
-            farr[i].dtype = _dev.dtype_code(host)
+            farr[i].dtype = _dev.dtype_code(d)
             farr[i].op = _lib.OP_SQUARE_NATIVE if s.error else _lib.OP_NONE
             farr[i].post = _lib.POST_SQRT if s.error else _lib.POST_NONE
             farr[i].nlev = s.nlev

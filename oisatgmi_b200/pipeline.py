@@ -71,6 +71,40 @@ class _Granule:
     __slots__ = ("n_px", "nlev", "has_trop", "dev", "plan", "slot", "time", "host")
 
 
+def finalize_and_oi(acc, n_cell, sensor, gas, error_ctm):
+    """[10][n_cell] accumulator block -> monthly means (averaging.py:97-108), bias correction
+    (driver.py:65-106), the 99-factor OI sweep, the knee and the update (driver.py:108-114,
+    optimal_interpolation.py:6-52).  GOSAT runs OI on (aux2, aux1) = (mean model XCH4, mean
+    satellite XCH4) instead of the columns (driver.py:113-114).  Returns device tensors."""
+    L = _lib.lib()
+    n = int(n_cell)
+    means = [_dev.empty((n,)) for _ in range(5)]
+    _lib.check(L.oisat_accum_finalize(acc.data_ptr(), n, *[m.data_ptr() for m in means],
+                                      _dev.stream()))
+    sat_vcd, sat_err, ctm_vcd, aux1, aux2 = means
+    a, b = BIAS_CORRECTION.get((sensor, gas), (0.0, 1.0))
+    xa, y = (aux2, aux1) if sensor == "GOSAT" else (ctm_vcd, sat_vcd)
+    Sa, So = _dev.empty((n,)), _dev.empty((n,))
+    _lib.check(L.oisat_oi_prepare(xa.data_ptr(), y.data_ptr(), sat_err.data_ptr(), n,
+                                  a, b, float(error_ctm), Sa.data_ptr(), So.data_ptr(),
+                                  _dev.stream()))
+    factors = regularisation_factors(True)
+    if kneed_available() or os.environ.get("OISAT_KNEE") == "host":
+        ak_means = sweep_device(Sa, So, factors)   # one small D2H: 99 sums + 99 counts
+        pick = knee_index(factors, ak_means)       # the reference's own kneed when importable
+        xb, ak, inc, err = apply_device(xa, y, Sa, So, float(factors[pick]))
+        extra = dict(knee_index=pick, ak_means=ak_means, factor=float(factors[pick]),
+                     knee_source="kneed" if kneed_available() else "restated-host")
+    else:
+        # sweep -> knee -> update on the device, no host round trip inside the step
+        xb, ak, inc, err, pick, factor, ak_means = sweep_knee_apply_device(xa, y, Sa, So, factors)
+        extra = dict(knee_index=_DeviceScalar(pick, int), ak_means=_DeviceVector(ak_means),
+                     factor=_DeviceScalar(factor, float), knee_source="restated-device")
+    return dict(sat_averaged_vcd=sat_vcd, sat_averaged_error=sat_err, ctm_averaged_vcd=ctm_vcd,
+                aux1=aux1, aux2=aux2, ctm_averaged_vcd_corrected=xb, ak_OI=ak,
+                increment_OI=inc, error_OI=err, **extra)
+
+
 class MonthPipeline:
     def __init__(self, ctm_data, grid_size, flag_thresh, sensor="OMI", gas="NO2", error_ctm=50.0,
                  process_group=None, interpolator_type=1):
@@ -484,17 +518,23 @@ class MonthPipeline:
     def split(self):
         return self.fused_form == "split"
 
+    def run_alive(self):
+        """Tile form only: pairs with a masked stencil pixel are NaN in every field
+        (interpolator.py:126-128); they get their NaNs here and the fused kernel runs over the
+        compact list of the others."""
+        if self.fused_form != "tile":
+            return
+        a = self.fused_args()
+        _lib.check(_lib.lib().oisat_pair_alive(
+            a.n_pairs, a.nwin, a.vert, a.w, a.pair_record0, a.pair_granule, a.gran_px0,
+            self._buf["px_bad"].data_ptr(), a.amf_masked, a.box_weight, a.staged,
+            a.alive_pairs, a.n_alive, _dev.stream()))
+
     def run_fused(self):
         L = _lib.lib()
         a = self.fused_args()
         form = self.fused_form
         if form == "tile":
-            # pairs with a masked stencil pixel are NaN in every field (interpolator.py:126-128):
-            # they get their NaNs here, the kernel runs over the compact list of the others
-            _lib.check(L.oisat_pair_alive(
-                a.n_pairs, a.nwin, a.vert, a.w, a.pair_record0, a.pair_granule, a.gran_px0,
-                self._buf["px_bad"].data_ptr(), a.amf_masked, a.box_weight, a.staged,
-                a.alive_pairs, a.n_alive, _dev.stream()))
             _lib.check(L.oisat_fused_amf_tile(C.byref(a), _dev.stream()))
         elif form == "split":
             _lib.check(L.oisat_fused_amf_split(C.byref(a), self._buf["rows"].data_ptr(),
@@ -516,34 +556,7 @@ class MonthPipeline:
 
     def run_oi(self):
         """Means, bias correction, OI sweep, knee, apply.  Returns device tensors."""
-        L = _lib.lib()
-        buf = self._buf
-        n = self.n_cell
-        means = [_dev.empty((n,)) for _ in range(5)]
-        _lib.check(L.oisat_accum_finalize(buf["acc"].data_ptr(), n,
-                                          *[m.data_ptr() for m in means], _dev.stream()))
-        sat_vcd, sat_err, ctm_vcd, aux1, aux2 = means
-        a, b = BIAS_CORRECTION.get((self.sensor, self.gas), (0.0, 1.0))
-        Sa, So = _dev.empty((n,)), _dev.empty((n,))
-        _lib.check(L.oisat_oi_prepare(ctm_vcd.data_ptr(), sat_vcd.data_ptr(), sat_err.data_ptr(), n,
-                                      a, b, self.error_ctm, Sa.data_ptr(), So.data_ptr(),
-                                      _dev.stream()))
-        factors = regularisation_factors(True)
-        if kneed_available() or os.environ.get("OISAT_KNEE") == "host":
-            ak_means = sweep_device(Sa, So, factors)   # one small D2H: 99 sums + 99 counts
-            pick = knee_index(factors, ak_means)       # the reference's own kneed when importable
-            xb, ak, inc, err = apply_device(ctm_vcd, sat_vcd, Sa, So, float(factors[pick]))
-            extra = dict(knee_index=pick, ak_means=ak_means, factor=float(factors[pick]),
-                         knee_source="kneed" if kneed_available() else "restated-host")
-        else:
-            # sweep -> knee -> update on the device, no host round trip inside the step
-            xb, ak, inc, err, pick, factor, ak_means = sweep_knee_apply_device(
-                ctm_vcd, sat_vcd, Sa, So, factors)
-            extra = dict(knee_index=_DeviceScalar(pick, int), ak_means=_DeviceVector(ak_means),
-                         factor=_DeviceScalar(factor, float), knee_source="restated-device")
-        return dict(sat_averaged_vcd=sat_vcd, sat_averaged_error=sat_err, ctm_averaged_vcd=ctm_vcd,
-                    aux1=aux1, aux2=aux2, ctm_averaged_vcd_corrected=xb, ak_OI=ak,
-                    increment_OI=inc, error_OI=err, **extra)
+        return finalize_and_oi(self._buf["acc"], self.n_cell, self.sensor, self.gas, self.error_ctm)
 
     def run(self, marks=None):
         """pack -> fused -> accumulate -> OI on the current stream.  `marks`
@@ -571,6 +584,8 @@ class MonthPipeline:
         mark("prepare")
         self.run_pack()
         mark("pack")
+        self.run_alive()
+        mark("alive")
         self.run_fused()
         mark("fused")
         self.run_accumulate()

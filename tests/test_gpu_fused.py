@@ -234,3 +234,43 @@ def test_month_without_granules_still_finishes():
     for k in ("ctm_averaged_vcd", "sat_averaged_vcd", "sat_averaged_error",
               "ctm_averaged_vcd_corrected"):
         assert res[k].shape == tuple(pipe.gplan.out_shape) and np.all(np.isnan(res[k])), k
+
+
+OPT_KEYS = {"avg.sat_err": "sat_averaged_error", "avg.ctm_vcd": "ctm_averaged_vcd",
+            "oi.ctm_averaged_vcd_corrected": "ctm_averaged_vcd_corrected", "oi.ak_OI": "ak_OI",
+            "oi.increment_OI": "increment_OI", "oi.error_OI": "error_OI"}
+
+
+@pytest.mark.parametrize("sensor", ["MOPITT", "GOSAT"])
+def test_opt_month_pipeline_matches_oracle_month(sensor, golden):
+    """The device-resident satellite_opt month (gap filling, gridding, model resampling, AK
+    convolution, accumulation, OI -- OI on aux2/aux1 for GOSAT) against the oracle's month
+    through the oisatgmi class and against the reference's golden month."""
+    from oisatgmi_b200.opt_pipeline import OptMonthPipeline
+    c = cases.mopitt_case() if sensor == "MOPITT" else cases.gosat_case()
+    pipe = OptMonthPipeline(c["ctm"], c["grid_size"], c["flag_thresh"], sensor)
+    for g in c["granules"]:
+        assert pipe.add_granule(cases.clone(g))
+    res = pipe.results_to_host(pipe.run())
+    chain = chains.mopitt_chain if sensor == "MOPITT" else chains.gosat_chain
+    want, _ = chain(chains.oracle_impl())
+    gold = golden("mopitt_co" if sensor == "MOPITT" else "gosat_xch4")
+    keys = dict(OPT_KEYS)
+    # OI clips its Y in place: the satellite mean, or aux1 for GOSAT (driver.py:113-114)
+    keys["oi.y"] = "aux1" if sensor == "GOSAT" else "sat_averaged_vcd"
+    if sensor == "GOSAT":
+        keys["avg.sat_vcd"] = "sat_averaged_vcd"
+    else:
+        keys["avg.aux1"] = "aux1"
+    keys["avg.aux2"] = "aux2"
+    prior = want["avg.aux2"] if sensor == "GOSAT" else want["avg.ctm_vcd"]
+    for key, attr in keys.items():
+        scale = prior if "increment" in key else None
+        assert_field(res[attr], want[key], key, rtol=RTOL_FP64, scale=scale)
+        assert_field(res[attr], gold[key], key + "(golden)", rtol=RTOL_FP64, scale=scale)
+    assert np.isfinite(res["ctm_averaged_vcd_corrected"]).sum() > 100
+    from oracle import oi as ooi
+    pick = ooi.oi_from_means(sensor, np.array(want["avg.ctm_vcd"]), np.array(want["avg.sat_vcd"]),
+                             np.array(want["avg.sat_err"]), np.array(want["avg.aux1"]),
+                             np.array(want["avg.aux2"]))[4]
+    assert res["knee_index"] == pick

@@ -20,7 +20,7 @@ def test_sharded_accumulators_equal_single_pipeline():
         for i in idx:
             assert p.add_granule(cases.clone(c["granules"][i]))
         p.allocate()
-        p.run_prepare(); p.run_pack(); p.run_fused(); p.run_accumulate()
+        p.run_prepare(); p.run_pack(); p.run_alive(); p.run_fused(); p.run_accumulate()
         return p
 
     times = [g.time for g in c["granules"]]

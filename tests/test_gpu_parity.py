@@ -22,7 +22,13 @@ def _compare(store, want, tight=()):
     worst = {}
     for k in keys:
         rtol = 1e-12 if k.startswith(tight) else RTOL_FP64
-        scale = want["avg.ctm_vcd"] if k.endswith(("increment_OI", ".inc")) else None
+        scale = None
+        if k.endswith(("increment_OI", ".inc")):
+            # the prior of the OI: the model column, or aux2 for GOSAT (driver.py:113-114),
+            # whose ctm_vcd is NaN by design (ak_conv_gosat.py:138)
+            scale = want["avg.ctm_vcd"]
+            if np.isnan(scale).all():
+                scale = want["avg.aux2"]
         assert_field(store[k], want[k], k, rtol=rtol, scale=scale)
         worst[k.split(".")[0]] = max(worst.get(k.split(".")[0], 0.0), max_rel(store[k], want[k]))
     return worst
