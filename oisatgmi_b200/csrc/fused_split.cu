@@ -945,6 +945,395 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
   A.staged[3 * A.n_pairs + pair] = new_amf;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised, persistent form of the tile kernel (the default)
+// ---------------------------------------------------------------------------------------------
+// The tile kernel above is latency bound (ncu, profiles/r02_*): a block starts with three
+// DEPENDENT global loads (live-pair list -> stencil -> record index) before it can request a
+// single record (18 % of its stall samples), then waits for the records, then all of its warps
+// stand at barriers between the gather and the phases of the vertical operator (15 %).  Here a
+// block lives for the whole launch (two per SM) and its warps have ONE job each:
+//
+//   7 producer warps   gather: stencil tables of the NEXT sweep / tile are requested while the
+//                      records of this one are in flight (the dependent chain is always one
+//                      step ahead, in registers, then in a double-buffered shared table), the
+//                      model columns of the next tile are prefetched into L2, records arrive by
+//                      cp.async into the producers' own stage, float16 -> float64, FMA in scipy's
+//                      order; the gridded tile goes to one of TWO tile buffers;
+//   8 consumer warps   the vertical operator of the previous tile on the other buffer, exactly
+//                      the phases A / B / C of the tile kernel (same code, same order, same
+//                      bits: tests/test_gpu_fused.py compares the two forms bit for bit).
+//
+// Hand-over with named barriers (bar.arrive / bar.sync, ids 2..5 = full / empty per buffer);
+// producers and consumers each have a private barrier for their internal steps.  While the
+// consumers run logarithms and bisections the producers keep ~80 KB of record requests per SM
+// in flight: the memory pipe and the FP64 / issue slots are busy at the same time.
+constexpr int kWsProd = 224;                 // 7 producer warps: 16 pairs x (<= 14) chunks
+constexpr int kWsCons = 256;                 // 8 consumer warps: 16 level lanes x 16 pairs
+constexpr int kWsThreads = kWsProd + kWsCons;
+constexpr int kWsSW = 15;                    // stencil entries per sweep
+enum { kBarProd = 1, kBarFull = 2, kBarEmpty = 4, kBarCons = 6 };
+
+__device__ __forceinline__ void bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int n) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+struct WsSmem {
+  double2 tab[128];                 // (r_i, -log r_i)
+  double part_a[8 * 16];
+  double tail_a[8 * 16];
+  float part_b[8 * 16];
+  float tail_b[8 * 16];
+  double gw[2][16 * kWsSW];         // weight of every (pair slot, entry) of a sweep, double-buffered
+  uint32_t gcix[2][16 * kWsSW];     // first chunk of its record
+  int pid[3][16];                   // pair ids of tiles it, it+1, it+2 (ring)
+  double c_old_amf[2][16];          // per tile buffer: what the consumers need to know
+  uint32_t c_off[2][16];
+  int c_pair[2][16];
+  int unsorted[16];
+};
+
+template <bool HAS_TROP, int H, int CL, int CS, int CN>
+__global__ void __launch_bounds__(kWsThreads, 2)
+fused_ws_kernel(const __grid_constant__ SplitParams P) {
+  const oisat_fused_args& A = P.a;
+  extern __shared__ __align__(16) unsigned char wsm[];
+  __shared__ WsSmem sm;
+  const int L = CL > 0 ? CL : A.n_sat_lev;
+  const int n_ctm = CN > 0 ? CN : A.n_ctm_lev;
+  const int S = CS > 0 ? CS : 3 * A.nwin;
+  const int nrow = CL > 0 ? rec_rows(CL, HAS_TROP) : P.nrow;
+  const int nchunk = CL > 0 ? rec_chunks(CL, HAS_TROP) : P.nchunk;
+  const int nrow_out = CL > 0 ? 2 * CL + 1 + (HAS_TROP ? 1 : 0) : P.nrow_out;
+  const int sweep = S < kWsSW ? S : kWsSW;
+  // dynamic shared memory: [tile 0 | tile 1 | stage | xs | rd]
+  const size_t tile_doubles = ((size_t)nrow_out * kTP + 1) & ~(size_t)1;
+  double* tile0 = reinterpret_cast<double*>(wsm);
+  uint4* stage = reinterpret_cast<uint4*>(tile0 + 2 * tile_doubles);   // [16][sweep][nchunk]
+  double* xs_s = reinterpret_cast<double*>(stage + (size_t)16 * sweep * nchunk);   // [kSearchRows][kXP]
+  double* rd_s = xs_s + kSearchRows * kXP;                             // [L][kXP]
+  const int64_t n_act = *A.n_alive;
+  const int64_t n_tiles = (n_act + 15) >> 4;
+  const int64_t G = gridDim.x;
+  if ((int64_t)blockIdx.x >= n_tiles) return;
+  const uint32_t stride = (uint32_t)A.n_cell;
+  const float* lp = A.ctm_logp;
+  const float* pc = A.ctm_pcol;
+  const float* pm = HAS_TROP ? A.ctm_pmid : A.ctm_logp;
+  for (int i = threadIdx.x; i < 128; i += kWsThreads)
+    sm.tab[i] = make_double2(g_log_table.r[i], g_log_table.neg_log_r[i]);
+  __syncthreads();
+
+  if (threadIdx.x < kWsProd) {
+    // ================================================================== producers
+    const int tid = threadIdx.x;
+    const bool active = tid < 16 * nchunk;
+    const int pp = active ? tid / nchunk : 0;          // pair slot of the tile
+    const int ch = active ? tid - pp * nchunk : 0;     // chunk of its records
+    const uint4* records = reinterpret_cast<const uint4*>(A.records);
+    uint4* slot = stage + (pp * sweep) * nchunk + ch;  // [pair][entry][chunk]
+    auto load_pid = [&](int64_t tile) -> int {         // tid < 16
+      if (tile >= n_tiles) return 0;
+      const int64_t s = tile * 16 + tid;
+      return A.alive_pairs[s < n_act ? s : n_act - 1];  // shadow slots repeat the last pair
+    };
+    // table items of this thread: i = tid and (tid < 16) tid + 224, i = 15 * slot + entry
+    const int c0 = tid / kWsSW, e0 = tid - c0 * kWsSW;
+    const int c1 = (tid + kWsProd) / kWsSW, e1 = tid + kWsProd - c1 * kWsSW;
+    const bool has1 = tid + kWsProd < 16 * kWsSW;
+    uint32_t ncix0 = 0, ncix1 = 0;
+    double nw0 = 0.0, nw1 = 0.0;
+    auto fetch_tab = [&](int ring, int base, int nk) {
+      if (e0 < nk) {
+        const int64_t pr = sm.pid[ring][c0];
+        const int32_t v = A.vert[pr * S + base + e0];
+        nw0 = A.w[pr * S + base + e0];
+        ncix0 = (uint32_t)((A.pair_record0[pr] + v) * nchunk);
+      }
+      if (has1 && e1 < nk) {
+        const int64_t pr = sm.pid[ring][c1];
+        const int32_t v = A.vert[pr * S + base + e1];
+        nw1 = A.w[pr * S + base + e1];
+        ncix1 = (uint32_t)((A.pair_record0[pr] + v) * nchunk);
+      }
+    };
+    auto store_tab = [&](int sb) {
+      sm.gcix[sb][tid] = ncix0;
+      sm.gw[sb][tid] = nw0;
+      if (has1) {
+        sm.gcix[sb][tid + kWsProd] = ncix1;
+        sm.gw[sb][tid + kWsProd] = nw1;
+      }
+    };
+    // model columns of a tile into L2: thread = (pair slot, level lane), 14 level lanes
+    auto prefetch_model = [&](int ring) {
+      const uint32_t off = A.pair_ctm_off[sm.pid[ring][tid & 15]];
+      for (int k = tid >> 4; k < n_ctm; k += kWsProd / 16) {
+        const uint32_t at = off + (uint32_t)k * stride;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + at));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + at));
+        if (HAS_TROP) asm volatile("prefetch.global.L2 [%0];" ::"l"(pm + at));
+      }
+    };
+    // prologue: pair ids of the first two tiles, tables of the first sweep
+    if (tid < 16) {
+      sm.pid[0][tid] = load_pid(blockIdx.x);
+      sm.pid[1][tid] = load_pid(blockIdx.x + G);
+    }
+    bar_sync(kBarProd, kWsProd);
+    fetch_tab(0, 0, sweep);
+    store_tab(0);
+    prefetch_model(0);
+    bar_sync(kBarProd, kWsProd);
+    int q = 0;                                         // sweeps done: parity = table buffer
+    int it = 0;
+    for (int64_t tile_i = blockIdx.x; tile_i < n_tiles; tile_i += G, ++it) {
+      const int b = it & 1, ring = it % 3, ring1 = (it + 1) % 3, ring2 = (it + 2) % 3;
+      const bool more = tile_i + G < n_tiles;
+      int pid2 = 0, f_pair = 0;
+      uint32_t f_off = 0;
+      double f_old = 0.0;
+      if (tid < 16) {
+        pid2 = load_pid(tile_i + 2 * G);
+        f_pair = sm.pid[ring][tid];
+        f_off = A.pair_ctm_off[f_pair];
+        f_old = A.staged[4 * A.n_pairs + f_pair];      // gridded by oisat_pair_alive
+      }
+      double acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.0;
+#pragma unroll 1
+      for (int base = 0; base < S; base += kWsSW, ++q) {
+        const int nk = (S - base) < kWsSW ? (S - base) : kWsSW;
+        const int sb = q & 1;
+        if (active) {
+#pragma unroll
+          for (int e = 0; e < kWsSW; ++e) {
+            if (e < nk) {
+              const uint32_t ck = sm.gcix[sb][pp * kWsSW + e] + (uint32_t)ch;
+              const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + e * nchunk);
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(records + ck)
+                           : "memory");
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        // while the records fly: the tables of the next sweep (of this tile or of the next one)
+        const bool last = base + kWsSW >= S;
+        if (!last) {
+          const int nbase = base + kWsSW;
+          fetch_tab(ring, nbase, (S - nbase) < kWsSW ? (S - nbase) : kWsSW);
+        } else if (more) {
+          fetch_tab(ring1, 0, sweep);
+          prefetch_model(ring1);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (active) {
+#pragma unroll
+          for (int e = 0; e < kWsSW; ++e) {
+            if (e < nk) {
+              const double wk = sm.gw[sb][pp * kWsSW + e];
+              double z[8];
+              h8_to_f64(slot[e * nchunk], z);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc[k] = fma(wk, z[k], acc[k]);
+            }
+          }
+        }
+        store_tab(sb ^ 1);
+        bar_sync(kBarProd, kWsProd);
+      }
+      // ring slot (it + 2) % 3 == (it - 1) % 3: every producer is past the epilogue of tile
+      // it - 1 (it has been through a barrier of this tile); read again only after the barrier below
+      if (tid < 16) sm.pid[ring2][tid] = pid2;
+      // the tile buffer is free once the consumers have finished tile it - 2
+      bar_sync(kBarEmpty + b, kWsThreads);
+      double* tile = tile0 + b * tile_doubles;
+      const int sig_row = 2 * L + 1;
+      if (active) {
+        double sig = 0.0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int row = ch + nchunk * e;
+          if (row == sig_row) sig = acc[e];
+          const int orow = row <= 2 * L ? row : row - 1;                 // tropopause follows vcd
+          if (row < nrow && row != sig_row) tile[orow * kTP + pp] = acc[e] * A.box_weight;
+        }
+        if (tile_i * 16 + pp < n_act && ch == sig_row % nchunk)
+          A.staged[1 * A.n_pairs + sm.pid[ring][pp]] = sqrt(sig * A.box_weight_err);   // interpolator.py:188
+      }
+      if (tid < 16) {
+        sm.c_pair[b][tid] = f_pair;
+        sm.c_off[b][tid] = f_off;
+        sm.c_old_amf[b][tid] = f_old;
+      }
+      __threadfence_block();
+      bar_arrive(kBarFull + b, kWsThreads);
+    }
+    return;
+  }
+
+  // ==================================================================== consumers
+  const int ct = threadIdx.x - kWsProd;
+  const int p = ct & 15, t = ct >> 4;
+  const int body = n_ctm - (n_ctm % 8);
+  const int nb = body >> 3;                 // terms per running sum
+  const int half = (nb + 1) >> 1;           // <= H
+  const int j8 = t & 7;
+  const int i0 = t < 8 ? 0 : half;
+  const int cnt = t < 8 ? half : nb - half;
+  bar_arrive(kBarEmpty + 0, kWsThreads);    // both tile buffers start empty
+  bar_arrive(kBarEmpty + 1, kWsThreads);
+  int it = 0;
+  for (int64_t tile_i = blockIdx.x; tile_i < n_tiles; tile_i += G, ++it) {
+    const int b = it & 1;
+    bar_sync(kBarFull + b, kWsThreads);
+    double* tile = tile0 + b * tile_doubles;
+    const bool live = tile_i * 16 + p < n_act;
+    const int64_t pair = sm.c_pair[b][p];
+    const uint32_t off = sm.c_off[b][p];
+    if (t == 0) sm.unsorted[p] = n_ctm >= 8 ? 0 : 1;
+    RowViewP<kTP> r{tile + p};
+    const double vcd = r.at(2 * L);
+    const bool work = live && vcd == vcd;  // amf_recal.py:99-100
+    const double trop = HAS_TROP ? r.at(2 * L + 1) : 0.0;
+    const bool descending = r.at(L) > r.at(2 * L - 1);
+    bar_sync(kBarCons, kWsCons);   // every thread has read the raw pressures before they turn into logs
+    // phase A: p -> log p in place + ascending copy; padding rows = +inf
+#pragma unroll
+    for (int row = t; row < kSearchRows; row += 16) {
+      if (row < L) {
+        if (work) {
+          const double lg = table_log2(r.at(L + row), sm.tab);
+          r.set(L + row, lg);
+          xs_s[(descending ? L - 1 - row : row) * kXP + p] = lg;
+        }
+      } else {
+        xs_s[row * kXP + p] = CUDART_INF;
+      }
+    }
+    bar_sync(kBarCons, kWsCons);
+    float lpv[H], pcv8[H], pmv[H];
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      const int ii = i < cnt ? i : (cnt > 0 ? cnt - 1 : 0);
+      const uint32_t at = off + (uint32_t)(j8 + 8 * (i0 + ii)) * stride;
+      const bool ok = work && cnt > 0;
+      lpv[i] = ok ? __ldg(lp + at) : 0.0f;
+      pcv8[i] = ok ? __ldg(pc + at) : 0.0f;
+      pmv[i] = (HAS_TROP && ok) ? __ldg(pm + at) : 0.0f;
+    }
+    if (work) {
+      bool bad = false;
+#pragma unroll
+      for (int j = t; j < L; j += 16) {
+        const double x = xs_s[j * kXP + p];
+        const double prev = j > 0 ? xs_s[(j - 1) * kXP + p] : -CUDART_INF;
+        bad = bad || !(prev < x);
+        if (j > 0) rd_s[j * kXP + p] = __drcp_rn(x - prev);              // = 1.0 / (x - prev) bit for bit
+      }
+      if (bad) sm.unsorted[p] = 1;
+    }
+    bar_sync(kBarCons, kWsCons);
+    const bool sorted = sm.unsorted[p] == 0;
+    const bool go = work && sorted;
+    const double* y0 = tile + (descending ? L - 1 : 0) * kTP + p;
+    const int ystep = descending ? -kTP : kTP;
+    auto term = [&](float lpf, float pcf, float pmf, double& ta, float& tb) {
+      const double v = (double)lpf;
+      double pcv = (double)pcf;
+      int idx = 0;
+#pragma unroll
+      for (int step = 32; step >= 1; step >>= 1)
+        idx += (xs_s[(idx + step - 1) * kXP + p] < v) ? step : 0;         // searchsorted(xs, v, 'left')
+      const int c = idx < 1 ? 1 : (idx > L - 1 ? L - 1 : idx);
+      const double x_hi = xs_s[c * kXP + p], x_lo = xs_s[(c - 1) * kXP + p];
+      const double rden = rd_s[c * kXP + p];
+      const double y_hi = y0[c * ystep], y_lo = y0[(c - 1) * ystep];
+      double sw = ((v - x_lo) * rden) * y_hi + ((x_hi - v) * rden) * y_lo;  // interp1d._call_linear
+      if (isinf(sw)) sw = 0.0;
+      if (HAS_TROP && (double)pmf < trop) { sw = qnan(); pcv = qnan(); }
+      const double prod = sw * pcv;
+      ta = prod != prod ? 0.0 : prod;        // nansum terms
+      tb = pcv != pcv ? 0.0f : (float)pcv;
+    };
+    double ta[H];
+    float tb[H];
+    if (go) {
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        ta[i] = 0.0;
+        tb[i] = 0.0f;
+        if (i < cnt) term(lpv[i], pcv8[i], pmv[i], ta[i], tb[i]);
+      }
+      if (t < 8 && body + t < n_ctm) {      // scalar tail of numpy's pairwise sum
+        const uint32_t at = off + (uint32_t)(body + t) * stride;
+        double a;
+        float bb;
+        term(__ldg(lp + at), __ldg(pc + at), HAS_TROP ? __ldg(pm + at) : 0.0f, a, bb);
+        sm.tail_a[t * 16 + p] = a;
+        sm.tail_b[t * 16 + p] = bb;
+      }
+      if (t < 8) {                            // running sum j8, first half
+        double qa = ta[0];
+        float qb = tb[0];
+#pragma unroll
+        for (int i = 1; i < H; ++i)
+          if (i < cnt) { qa = qa + ta[i]; qb = __fadd_rn(qb, tb[i]); }
+        sm.part_a[j8 * 16 + p] = qa;
+        sm.part_b[j8 * 16 + p] = qb;
+      }
+    }
+    bar_sync(kBarCons, kWsCons);
+    if (go && t >= 8) {                       // second half continues the same running sum
+      double qa = sm.part_a[j8 * 16 + p];
+      float qb = sm.part_b[j8 * 16 + p];
+#pragma unroll
+      for (int i = 0; i < H; ++i)
+        if (i < cnt) { qa = qa + ta[i]; qb = __fadd_rn(qb, tb[i]); }
+      sm.part_a[j8 * 16 + p] = qa;
+      sm.part_b[j8 * 16 + p] = qb;
+    }
+    bar_sync(kBarCons, kWsCons);
+    // phase C
+    if (t == 0 && live) {
+      const double old_amf = sm.c_old_amf[b][p];
+      double new_amf = qnan(), vnew = qnan(), colv = qnan();
+      if (work) {
+        double colsum = 0.0;
+        if (sorted) {
+          auto qa = [&](int j) { return sm.part_a[j * 16 + p]; };
+          auto qb = [&](int j) { return sm.part_b[j * 16 + p]; };
+          double scd = ((qa(0) + qa(1)) + (qa(2) + qa(3))) + ((qa(4) + qa(5)) + (qa(6) + qa(7)));
+          float cs = __fadd_rn(__fadd_rn(__fadd_rn(qb(0), qb(1)), __fadd_rn(qb(2), qb(3))),
+                               __fadd_rn(__fadd_rn(qb(4), qb(5)), __fadd_rn(qb(6), qb(7))));
+          for (int k = body; k < n_ctm; ++k) {   // scalar tail after the tree
+            scd = scd + sm.tail_a[(k - body) * 16 + p];
+            cs = __fadd_rn(cs, sm.tail_b[(k - body) * 16 + p]);
+          }
+          colsum = (double)cs;
+          new_amf = colsum != 0.0 ? scd / colsum : qnan();
+        } else {
+          new_amf = amf_slow_path_tile(r, L, n_ctm, HAS_TROP, trop, lp + off, pc + off, pm + off,
+                                       (int64_t)stride, &colsum);
+        }
+        vnew = (old_amf * vcd) / new_amf;                        // amf_recal.py:179
+        colv = (vnew != vnew || isinf(vnew)) ? qnan() : colsum;  // :180-181
+      }
+      A.staged[0 * A.n_pairs + pair] = vnew;
+      A.staged[2 * A.n_pairs + pair] = colv;
+      A.staged[3 * A.n_pairs + pair] = new_amf;
+    }
+    // phase C has read the partial sums and the tile: hand the buffer back, and keep the fast
+    // threads out of the next tile's shared arrays until it is through
+    bar_sync(kBarCons, kWsCons);
+    bar_arrive(kBarEmpty + b, kWsThreads);
+  }
+}
+
 }  // namespace oisat
 
 using namespace oisat;
@@ -1035,6 +1424,31 @@ static int launch_tile(const SplitParams& P, cudaStream_t s) {
   return OISAT_OK;
 }
 
+template <bool HAS_TROP, int H, int CL, int CS, int CN>
+static int launch_ws(const SplitParams& P, cudaStream_t s) {
+  const oisat_fused_args& a = P.a;
+  const int sweep = 3 * a.nwin < kWsSW ? 3 * a.nwin : kWsSW;
+  const size_t tile_doubles = ((size_t)P.nrow_out * kTP + 1) & ~(size_t)1;
+  const size_t smem = 2 * tile_doubles * sizeof(double) + (size_t)16 * sweep * P.nchunk * sizeof(uint4) +
+                      (size_t)(kSearchRows + a.n_sat_lev) * kXP * sizeof(double);
+  static int sms[64];
+  int dev = 0;
+  OISAT_CHECK_CUDA(cudaGetDevice(&dev));
+  if (sms[dev & 63] == 0)
+    OISAT_CHECK_CUDA(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+  auto kern = fused_ws_kernel<HAS_TROP, H, CL, CS, CN>;
+  OISAT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  OISAT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWsThreads, smem));
+  OISAT_CHECK_ARG(per_sm >= 1, "the warp-specialised tile kernel does not fit on this device");
+  int64_t grid = (int64_t)per_sm * sms[dev & 63];
+  const int64_t tiles = ceil_div(a.n_pairs, 16);
+  if (grid > tiles) grid = tiles;
+  kern<<<(unsigned)grid, kWsThreads, smem, s>>>(P);
+  OISAT_CHECK_LAUNCH();
+  return OISAT_OK;
+}
+
 extern "C" int oisat_fused_amf_tile(const oisat_fused_args* h_args, void* stream) {
   OISAT_CHECK_ARG(h_args != nullptr, "null args");
   const oisat_fused_args& a = *h_args;
@@ -1067,6 +1481,23 @@ extern "C" int oisat_fused_amf_tile(const oisat_fused_args* h_args, void* stream
   const bool generic = gen && gen[0] == '1';
   const char* pk = getenv("OISAT_TILE_PACKED");   // "0": half-warp-per-pair gather lanes (A/B runs, tests)
   const bool packed = !(pk && pk[0] == '0');
+  // the warp-specialised persistent form (default) needs the per-pair tables and records of at
+  // most 14 chunks; OISAT_TILE_WS=0 runs the one-tile-per-block form (A/B runs, tests)
+  const char* wsenv = getenv("OISAT_TILE_WS");
+  const bool ws = !(wsenv && wsenv[0] == '0') && a.pair_record0 && a.pair_ctm_off && P.nchunk <= 14;
+  if (ws) {
+    if (generic) {
+    } else if (!a.has_trop && L == 47 && S == 12 && N == 72) {
+      return launch_ws<false, 5, 47, 12, 72>(P, s);
+    } else if (a.has_trop && L == 35 && S == 12 && N == 72) {
+      return launch_ws<true, 5, 35, 12, 72>(P, s);
+    } else if (a.has_trop && L == 34 && S == 90 && N == 72) {
+      return launch_ws<true, 5, 34, 90, 72>(P, s);
+    }
+    if (((N / 8) + 1) / 2 <= 5)
+      return a.has_trop ? launch_ws<true, 5, 0, 0, 0>(P, s) : launch_ws<false, 5, 0, 0, 0>(P, s);
+    return a.has_trop ? launch_ws<true, 8, 0, 0, 0>(P, s) : launch_ws<false, 8, 0, 0, 0>(P, s);
+  }
   if (generic) {
   } else if (!a.has_trop && L == 47 && S == 12 && N == 72) {
     return packed ? launch_tile<false, 5, 47, 12, 72, true>(P, s) : launch_tile<false, 5, 47, 12, 72>(P, s);
