@@ -47,6 +47,7 @@ struct SplitParams {
   oisat_fused_args a;
   double* rows;              // [ceil(n_pairs/16)][nrow_out][16]
   int nrow, nchunk, nrow_out;
+  int probe;                 // timing experiments only (OISAT_WS_PROBE): 1 = consumers idle, 2 = producers idle
 };
 
 __device__ __forceinline__ void h8_to_f64(const uint4& u, double* z) {
@@ -1090,6 +1091,7 @@ fused_ws_kernel(const __grid_constant__ SplitParams P) {
     bar_sync(kBarProd, kWsProd);
     int q = 0;                                         // sweeps done: parity = table buffer
     int it = 0;
+    double acc[8];
     for (int64_t tile_i = blockIdx.x; tile_i < n_tiles; tile_i += G, ++it) {
       const int b = it & 1, ring = it % 3, ring1 = (it + 1) % 3, ring2 = (it + 2) % 3;
       const bool more = tile_i + G < n_tiles;
@@ -1102,14 +1104,16 @@ fused_ws_kernel(const __grid_constant__ SplitParams P) {
         f_off = A.pair_ctm_off[f_pair];
         f_old = A.staged[4 * A.n_pairs + f_pair];      // gridded by oisat_pair_alive
       }
-      double acc[8];
+      if (P.probe != 2 || it == 0) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = 0.0;
+        for (int e = 0; e < 8; ++e) acc[e] = 0.0;
+      }
+      const bool gather = P.probe != 2 || it == 0;   // probe 2: every tile repeats the first one
 #pragma unroll 1
       for (int base = 0; base < S; base += kWsSW, ++q) {
         const int nk = (S - base) < kWsSW ? (S - base) : kWsSW;
         const int sb = q & 1;
-        if (active) {
+        if (active && gather) {
 #pragma unroll
           for (int e = 0; e < kWsSW; ++e) {
             if (e < nk) {
@@ -1131,7 +1135,7 @@ fused_ws_kernel(const __grid_constant__ SplitParams P) {
           prefetch_model(ring1);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (active) {
+        if (active && gather) {
 #pragma unroll
           for (int e = 0; e < kWsSW; ++e) {
             if (e < nk) {
@@ -1198,7 +1202,7 @@ fused_ws_kernel(const __grid_constant__ SplitParams P) {
     if (t == 0) sm.unsorted[p] = n_ctm >= 8 ? 0 : 1;
     RowViewP<kTP> r{tile + p};
     const double vcd = r.at(2 * L);
-    const bool work = live && vcd == vcd;  // amf_recal.py:99-100
+    const bool work = live && vcd == vcd && P.probe != 1;  // amf_recal.py:99-100
     const double trop = HAS_TROP ? r.at(2 * L + 1) : 0.0;
     const bool descending = r.at(L) > r.at(2 * L - 1);
     bar_sync(kBarCons, kWsCons);   // every thread has read the raw pressures before they turn into logs
@@ -1377,6 +1381,7 @@ extern "C" int oisat_fused_amf_split(const oisat_fused_args* h_args, double* row
   P.nrow = rec_rows(a.n_sat_lev, a.has_trop);
   P.nchunk = rec_chunks(a.n_sat_lev, a.has_trop);
   P.nrow_out = (int)oisat_rows_per_pair(a.n_sat_lev, a.has_trop);
+  P.probe = 0;
   OISAT_CHECK_ARG(P.nchunk < 16, "record too wide for the half-warp gather: use oisat_fused_amf");
   OISAT_CHECK_ARG(a.n_records > 0 && a.n_records * P.nchunk < ((int64_t)1 << 32),
                   "record block too large for 32-bit chunk indices: split the batch");
@@ -1467,6 +1472,7 @@ extern "C" int oisat_fused_amf_tile(const oisat_fused_args* h_args, void* stream
   P.nrow = rec_rows(a.n_sat_lev, a.has_trop);
   P.nchunk = rec_chunks(a.n_sat_lev, a.has_trop);
   P.nrow_out = (int)oisat_rows_per_pair(a.n_sat_lev, a.has_trop);
+  P.probe = 0;
   OISAT_CHECK_ARG(P.nchunk < 16, "record too wide for the half-warp gather: use oisat_fused_amf");
   OISAT_CHECK_ARG(a.n_records > 0 && a.n_records * P.nchunk < ((int64_t)1 << 32),
                   "record block too large for 32-bit chunk indices: split the batch");
@@ -1483,6 +1489,8 @@ extern "C" int oisat_fused_amf_tile(const oisat_fused_args* h_args, void* stream
   const bool packed = !(pk && pk[0] == '0');
   // the warp-specialised persistent form (default) needs the per-pair tables and records of at
   // most 14 chunks; OISAT_TILE_WS=0 runs the one-tile-per-block form (A/B runs, tests)
+  const char* prenv = getenv("OISAT_WS_PROBE");
+  P.probe = prenv ? atoi(prenv) : 0;
   const char* wsenv = getenv("OISAT_TILE_WS");
   const bool ws = !(wsenv && wsenv[0] == '0') && a.pair_record0 && a.pair_ctm_off && P.nchunk <= 14;
   if (ws) {

@@ -227,6 +227,7 @@ class OptMonthPipeline:
 
         L = _lib.lib()
         mark("start")
+        self._model_on_mesh = {}     # the model is resampled inside the step, once per model day
         acc = _dev.zeros((10, self.n_cell))
         self._acc = acc
         for g in self.granules:
