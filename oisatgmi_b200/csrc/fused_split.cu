@@ -947,7 +947,8 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Warp-specialised, persistent form of the tile kernel (the default)
+// Warp-specialised, persistent form of the tile kernel (OISAT_TILE_WS=1; an experiment, see
+// oisat_fused_amf_tile for what it measured)
 // ---------------------------------------------------------------------------------------------
 // The tile kernel above is latency bound (ncu, profiles/r02_*): a block starts with three
 // DEPENDENT global loads (live-pair list -> stencil -> record index) before it can request a
@@ -1487,12 +1488,16 @@ extern "C" int oisat_fused_amf_tile(const oisat_fused_args* h_args, void* stream
   const bool generic = gen && gen[0] == '1';
   const char* pk = getenv("OISAT_TILE_PACKED");   // "0": half-warp-per-pair gather lanes (A/B runs, tests)
   const bool packed = !(pk && pk[0] == '0');
-  // the warp-specialised persistent form (default) needs the per-pair tables and records of at
-  // most 14 chunks; OISAT_TILE_WS=0 runs the one-tile-per-block form (A/B runs, tests)
+  // OISAT_TILE_WS=1 runs the warp-specialised persistent form (needs the per-pair tables and
+  // records of at most 14 chunks).  Measured on the OMI HCHO month (profiles/r02_ws_probe.md):
+  // 5.70 ms against 5.21 ms for the one-tile-per-block form -- each role alone needs ~4.3 ms
+  // with its 14-16 warps per SM, both are latency bound, and the 32 interchangeable warps of
+  // the one-tile-per-block form hide latency better than two fixed groups do -- so it is NOT
+  // the default; the tests keep the two forms bit-identical.
   const char* prenv = getenv("OISAT_WS_PROBE");
   P.probe = prenv ? atoi(prenv) : 0;
   const char* wsenv = getenv("OISAT_TILE_WS");
-  const bool ws = !(wsenv && wsenv[0] == '0') && a.pair_record0 && a.pair_ctm_off && P.nchunk <= 14;
+  const bool ws = (wsenv && wsenv[0] == '1') && a.pair_record0 && a.pair_ctm_off && P.nchunk <= 14;
   if (ws) {
     if (generic) {
     } else if (!a.has_trop && L == 47 && S == 12 && N == 72) {
