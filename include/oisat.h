@@ -485,6 +485,19 @@ int oisat_fused_amf_split(const oisat_fused_args* h_args, double* rows, void* st
  * table of the args is not used; pair_granule / pair_cell are. */
 int oisat_fused_amf_tile(const oisat_fused_args* h_args, void* stream);
 
+/* Pair tables of a month, on the device, from the concatenated granule plans (pairs in granule
+ * order, cells ascending inside a granule).  oisat_segment_tables: for every model cell the
+ * list of its pairs in GRANULE order -- seg_start [n_cell + 1], seg_pair [n_pairs] -- by a
+ * counting sort whose result is deterministic (every cell sorts its own short segment by pair
+ * index at the end); `work` = n_cell int32.  oisat_pair_tables: pair_record0 / pair_ctm_off of
+ * oisat_fused_args from the per-granule tables (n_slots = time slots in the model block). */
+int oisat_segment_tables(const int32_t* pair_cell, int64_t n_pairs, int64_t n_cell,
+                         int64_t* seg_start, int64_t* seg_pair, int32_t* work, void* stream);
+int oisat_pair_tables(int64_t n_pairs, const int32_t* pair_granule, const int32_t* pair_cell,
+                      const int64_t* gran_px0, const int32_t* gran_slot, int32_t n_ctm_lev,
+                      int64_t n_cell, int64_t n_slots, int64_t* pair_record0,
+                      uint32_t* pair_ctm_off, void* stream);
+
 /* ordered segmented reduction of the staged pair values into the accumulators:
  * for model cell c the pairs seg_pair[seg_start[c] .. seg_start[c+1]) are listed
  * in granule order, so the running sums equal numpy's sequential nanmean

@@ -104,6 +104,8 @@ PROTOTYPES = {
     "oisat_rows_per_pair": (i64, [i32, i32]),
     "oisat_fused_amf_split": (C.c_int, [C.POINTER(FusedArgs), vp, vp]),
     "oisat_fused_amf_tile": (C.c_int, [C.POINTER(FusedArgs), vp]),
+    "oisat_segment_tables": (C.c_int, [vp, i64, i64, vp, vp, vp, vp]),
+    "oisat_pair_tables": (C.c_int, [i64, vp, vp, vp, vp, i32, i64, i64, vp, vp, vp]),
     "oisat_accum_pairs": (C.c_int, [vp, i64, vp, vp, vp, i64, vp]),
 }
 

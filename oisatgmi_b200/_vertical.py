@@ -61,17 +61,28 @@ class _DeviceCache:
     def __init__(self):
         self._store = {}
 
+    @staticmethod
+    def _fingerprint(arr):
+        """Cheap content check (257 strided elements): an in-place rescaling or replacement of a
+        model field between two calls is seen and the device copy refreshed.  An edit that
+        touches none of the sampled elements is not -- model arrays are to be treated as
+        immutable while a month is processed (clear_cache() otherwise)."""
+        a = np.asarray(arr)
+        flat = a.reshape(-1)
+        step = max(1, flat.size // 257)
+        return (a.shape, a.dtype.str, flat[::step][:257].tobytes())
+
     def get(self, arr: np.ndarray, tag, make):
         key = (id(arr), tag)
         hit = self._store.get(key)
-        if hit is not None and hit[0]() is arr:
+        if hit is not None and hit[0]() is arr and hit[2] == self._fingerprint(arr):
             return hit[1]
         val = make()
         try:
             ref = weakref.ref(arr)
         except TypeError:
             return val
-        self._store[key] = (ref, val)
+        self._store[key] = (ref, val, self._fingerprint(arr))
         if len(self._store) > 64:
             self._store = {k: v for k, v in self._store.items() if v[0]() is not None}
         return val
@@ -103,14 +114,11 @@ def ctm_time_mean_device(field4d: np.ndarray):
     return _cache.get(field4d, ("tmean",), make)
 
 
-def resample_to_sat(requests, ctm_data, granule):
-    """K6: model fields -> satellite grid (amf_recal.py:58-83,
-    ak_conv_mopitt.py:79-110).  `requests` is a list of (src, src2, op) with
-    device [nlev][ny*nx] tensors; op selects the value itself, the float32
-    partial column of (delta_p, profile) or the float32 air column of delta_p.
-    Outputs float64 [nlev][n_sat] device tensors."""
-    L = _lib.lib()
-    sat = {"Longitude": granule.longitude_center, "Latitude": granule.latitude_center}
+def resample_geometry(ctm_data, sat_lon, sat_lat):
+    """Geometry of K6 for one (model grid, satellite mesh) pair: window extent, nearest model
+    node of every mesh node (cKDTree, cached) and the reach mask, on the device.  Constant over
+    a month: the month pipelines build it once."""
+    sat = {"Longitude": sat_lon, "Latitude": sat_lat}
     dlon_s, dlat_s = _plan.grid_spacing(sat)
     thr = np.sqrt(dlon_s ** 2 + dlat_s ** 2)
     clon, clat = ctm_data[0].longitude, ctm_data[0].latitude
@@ -126,16 +134,33 @@ def resample_to_sat(requests, ctm_data, granule):
     nn = _cache.get(idx, ("nn",), lambda: _dev.to_device(idx.astype(np.int32)))
     okd = _dev.to_device(ok.astype(np.uint8))
     H, W = clon.shape
+    return dict(ky=ky, kx=kx, nn=nn, ok=okd, n=int(idx.size), H=H, W=W)
+
+
+def resample_with(geom, requests):
+    """K6 launches for a list of (src, src2, op): float64 [nlev][n_sat] device tensors."""
+    L = _lib.lib()
     outs = []
     for src, src2, op in requests:
         nlev = src.shape[0]
-        out = _dev.empty((nlev, idx.size))
+        out = _dev.empty((nlev, geom["n"]))
         _lib.check(L.oisat_grid_resample(src.data_ptr(), _dev.ptr(src2), op, _dev.dtype_code(src),
-                                         nlev, H, W, ky, kx, 1.0 / (kx * ky), nn.data_ptr(),
-                                         okd.data_ptr(), idx.size, out.data_ptr(), idx.size,
+                                         nlev, geom["H"], geom["W"], geom["ky"], geom["kx"],
+                                         1.0 / (geom["kx"] * geom["ky"]), geom["nn"].data_ptr(),
+                                         geom["ok"].data_ptr(), geom["n"], out.data_ptr(), geom["n"],
                                          _dev.stream()))
         outs.append(out)
     return outs
+
+
+def resample_to_sat(requests, ctm_data, granule):
+    """K6: model fields -> satellite grid (amf_recal.py:58-83,
+    ak_conv_mopitt.py:79-110).  `requests` is a list of (src, src2, op) with
+    device [nlev][ny*nx] tensors; op selects the value itself, the float32
+    partial column of (delta_p, profile) or the float32 air column of delta_p.
+    Outputs float64 [nlev][n_sat] device tensors."""
+    return resample_with(resample_geometry(ctm_data, granule.longitude_center,
+                                           granule.latitude_center), requests)
 
 
 def compact(arr, valid_flat, nlev=None):

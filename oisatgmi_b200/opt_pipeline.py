@@ -60,6 +60,7 @@ class OptMonthPipeline:
         self._stamps, _ = _v.ctm_clock(ctm_data)
         self._model_on_mesh = {}       # model day -> (p_mid, profile, third, mode) on the device
         self._fill = None              # GOSAT: (grid plan of the filler mesh, X, Y)
+        self._resample = None          # K6 geometry (model grid -> output mesh)
         self._acc = None
         self.n_skipped = 0
 
@@ -180,12 +181,12 @@ class OptMonthPipeline:
         if not self.gplan.upscale:
             if pmid_d.dtype != _dev.torch().float32:
                 raise _lib.OisatError("model fields must be float32 as delivered by the readers")
-            X, Y = self.gplan.mesh()
-            import types
-            mesh = types.SimpleNamespace(longitude_center=X, latitude_center=Y)
-            pm, pr, third = _v.resample_to_sat(
-                [(pmid_d, None, _lib.SRC_VALUE), (prof_d, None, _lib.SRC_VALUE),
-                 (dp_d, None, _lib.SRC_AIR_COLUMN)], self.ctm_data, mesh)
+            if self._resample is None:       # geometry of the resampling: once per pipeline
+                X, Y = self.gplan.mesh()
+                self._resample = _v.resample_geometry(self.ctm_data, X, Y)
+            pm, pr, third = _v.resample_with(
+                self._resample, [(pmid_d, None, _lib.SRC_VALUE), (prof_d, None, _lib.SRC_VALUE),
+                                 (dp_d, None, _lib.SRC_AIR_COLUMN)])
             hit = (pm, pr, third, 1)
         else:
             hit = (pmid_d, prof_d, dp_d, 0)

@@ -326,13 +326,15 @@ class MonthPipeline:
                     total_px=int(sum(g.n_px for g in G)), cells=cells, gran=gran)
         d = _dev.to_device
         pair_cell = d(cells.astype(np.int32))
-        # segments: pairs of each model cell in granule order (stable sort by cell), built on
-        # the device -- the host only concatenated the cell lists
-        pc64 = pair_cell.to(t.int64)
-        order = t.sort(pc64, stable=True).indices
-        seg_start = t.zeros(self.n_cell + 1, dtype=t.int64, device=pair_cell.device)
-        t.cumsum(t.bincount(pc64, minlength=self.n_cell), 0, out=seg_start[1:])
-        dev = dict(vert=vert, w=w, seg_start=seg_start, seg_pair=order, gran_px0=d(px0),
+        # segments: pairs of each model cell in granule order, built on the device
+        # (oisat_segment_tables) -- the host only concatenated the cell lists
+        seg_start = _dev.empty((self.n_cell + 1,), "int64")
+        seg_pair = _dev.empty((n_pairs,), "int64")
+        seg_work = _dev.empty((self.n_cell,), "int32")
+        _lib.check(_lib.lib().oisat_segment_tables(pair_cell.data_ptr(), n_pairs, self.n_cell,
+                                                   seg_start.data_ptr(), seg_pair.data_ptr(),
+                                                   seg_work.data_ptr(), _dev.stream()))
+        dev = dict(vert=vert, w=w, seg_start=seg_start, seg_pair=seg_pair, gran_px0=d(px0),
                    pair_gran=d(gran), pair_cell=pair_cell,
                    gran_slot=d(np.array([slot_index[g.slot] for g in G], np.int32)))
         self._tables = (host, dev)
@@ -482,13 +484,15 @@ class MonthPipeline:
         a.pair_granule = dev["pair_gran"].data_ptr()
         a.pair_cell = dev["pair_cell"].data_ptr()
         if "pair_rec0" not in dev:     # per-pair copies of the per-granule facts (tile form)
-            t = _dev.torch()
-            gi = dev["pair_gran"].to(t.int64)
-            dev["pair_rec0"] = dev["gran_px0"][gi].contiguous()
-            off = dev["gran_slot"].to(t.int64)[gi] * (pm.shape[1] * self.n_cell) + dev["pair_cell"].to(t.int64)
             if int(pm.shape[0]) * pm.shape[1] * self.n_cell >= 2 ** 31:
                 raise _lib.OisatError("model fields too large for 32-bit element offsets")
-            dev["pair_ctm_off"] = off.to(t.int32).contiguous()
+            dev["pair_rec0"] = _dev.empty((host["n_pairs"],), "int64")
+            dev["pair_ctm_off"] = _dev.empty((host["n_pairs"],), "int32")
+            _lib.check(_lib.lib().oisat_pair_tables(
+                host["n_pairs"], dev["pair_gran"].data_ptr(), dev["pair_cell"].data_ptr(),
+                dev["gran_px0"].data_ptr(), dev["gran_slot"].data_ptr(), int(pm.shape[1]),
+                self.n_cell, int(pm.shape[0]), dev["pair_rec0"].data_ptr(),
+                dev["pair_ctm_off"].data_ptr(), _dev.stream()))
         a.pair_record0 = dev["pair_rec0"].data_ptr()
         a.pair_ctm_off = dev["pair_ctm_off"].data_ptr()
         if self.fused_form == "tile":

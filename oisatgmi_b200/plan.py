@@ -391,6 +391,25 @@ def _plan_v0(lon, lat, gplan, keep):
     return GranulePlan(gplan, cells, vert.astype(np.int32), w, keep, builder="v0")
 
 
+def _plan_v0_device(lon, lat, lonlat_dev, gplan, keep_dev):
+    """Qhull's triangulation with the device's point location and stencil fill: the fallback
+    for a swath whose exact Delaunay triangulation has a NEAR tie inside a quadrilateral that
+    holds a kept mesh node (Qhull merges such a quadrilateral into one facet and splits it its
+    own way, so its answer is needed) -- but only its triangles are: scipy's sequential walk over
+    the 1.04 M mesh nodes (0.3 s of the 0.7 s this fallback used to cost, and what made one
+    granule in 120 stall an 8-rank step) is K1's job as in builder v1.  Lattice inputs, whose
+    mesh nodes sit ON triangle edges everywhere, keep the host walk (_plan_v0): there the
+    choice among the triangles sharing an edge decides which NaN vertices a node sees."""
+    try:
+        tri = triangulate(lon, lat)
+    except Exception:
+        return None
+    simp = np.ascontiguousarray(tri.simplices.astype(np.int32))
+    plan = _plan_v1_finish(_plan_v1_enqueue(simp, lonlat_dev, gplan, keep_dev), gplan)
+    plan.builder = "v0q"
+    return plan
+
+
 def _plan_v1_enqueue(tri_host, lonlat_dev, gplan, keep_dev, half_host=None, maxabs=0.0):
     """First half of the device part of a v1 plan, queued without waiting for anything:
     upload of the triangulation, near-tie scan (with `half_host`, native_delaunay_adj),
@@ -565,6 +584,8 @@ def granule_plan(lon, lat, gplan: GridPlan, radius: float, lonlat_dev=None, cach
                 return None
             if ties == 0 or _plan_mode() == "v1":
                 plan = _plan_v1_device(tri, lonlat_dev, gplan, keep_dev, half, maxabs)
+                if plan is None and _plan_mode() != "v0walk":
+                    plan = _plan_v0_device(lon, lat, lonlat_dev, gplan, keep_dev)   # near tie
         if plan is None:
             plan = _plan_v0(lon, lat, gplan, _dev.to_host(keep_dev).astype(bool))
     if plan is not None and cache:
@@ -643,6 +664,8 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
     t_pool = _time.perf_counter()
     for i, st in pending:     # second half: kept cells on the host, stencil fill queued
         out[i] = _plan_v1_finish(st, gplan)
+        if out[i] is None and _plan_mode() != "v0walk":      # near tie: Qhull's triangles, K1's walk
+            out[i] = _plan_v0_device(lons[i], lats[i], lonlat_dev[i], gplan, keeps[i])
         if out[i] is None:
             out[i] = _plan_v0(lons[i], lats[i], gplan, _dev.to_host(keeps[i]).astype(bool))
     if trace is not None:
