@@ -36,7 +36,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, ROOT)
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]   # tests/: the synthetic generators (synth.py)
 
 P_OMI = 1644 * 60
 GRID_SIZE = 0.25
@@ -66,7 +66,7 @@ def orbit_geo(i, n_orbits):
 
 
 def make_day(seed0, n_orbits):
-    from oisatgmi_b200 import synth
+    import synth
     grans = []
     for i in range(n_orbits):
         t = datetime.datetime(2005, 6, 1) + datetime.timedelta(seconds=1800 + i * 5933)
@@ -76,7 +76,7 @@ def make_day(seed0, n_orbits):
 
 
 def make_model(seed=11):
-    from oisatgmi_b200 import synth
+    import synth
     return [synth.make_ctm(seed, synth.ctm_coordinates(), averaged=True)]
 
 
@@ -135,7 +135,7 @@ def _cpu_sample(seed):
     algorithm, pinned bit-identical to it): interpolator -> amf_recal -> this granule's share
     of averaging and OI.  Measured, nothing extrapolated."""
     import types
-    from oisatgmi_b200 import synth
+    import synth
     from oracle import averaging as oavg, interp as ointerp, oi as ooi, vertical as overt
     coords = synth.ctm_coordinates()
     model = [synth.make_ctm(11, coords, nslots=1, averaged=True)]
@@ -158,7 +158,7 @@ def _cpu_sample(seed):
 
 def _cpu_warm(_):
     """Pages numpy / scipy / the oracle in (a 200-line regional granule, 3 levels)."""
-    from oisatgmi_b200 import synth
+    import synth
     from oracle import interp as ointerp
     coords = synth.ctm_coordinates((30.0, 50.0, -105.0, -75.0))
     g = synth.make_amf_granule(1, PRODUCT, nt=200, nxt=60, geo=synth.regional_geo(

@@ -30,12 +30,13 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]   # tests/: the synthetic generators (synth.py)
 
 import torch  # noqa: E402
 
 import bench  # noqa: E402
-from oisatgmi_b200 import _lib, plan as _plan, synth  # noqa: E402
+from oisatgmi_b200 import _lib, plan as _plan  # noqa: E402
+import synth  # noqa: E402
 from oisatgmi_b200.pipeline import MonthPipeline  # noqa: E402
 
 CONFIGS = {

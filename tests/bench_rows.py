@@ -28,7 +28,8 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 import torch  # noqa: E402
 
-from oisatgmi_b200 import _dev, _lib, plan as _plan, reader_frontend as rf, synth  # noqa: E402
+from oisatgmi_b200 import _dev, _lib, plan as _plan, reader_frontend as rf  # noqa: E402
+import synth  # noqa: E402
 
 
 def peak():

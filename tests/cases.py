@@ -8,7 +8,7 @@ import types
 
 import numpy as np
 
-from oisatgmi_b200 import synth
+import synth
 
 REGION = (30.0, 50.0, -105.0, -75.0)        # 41 x 49 model cells
 REGION_AK = (10.0, 60.0, -130.0, -60.0)     # MOPITT / GOSAT: 1 degree lattice needs room

@@ -18,7 +18,7 @@ import datetime as _dt
 
 import numpy as np
 
-from .config import ctm_model, satellite_amf, satellite_opt
+from oisatgmi_b200.config import ctm_model, satellite_amf, satellite_opt
 
 R_EARTH_KM = 6371.0
 

@@ -20,7 +20,7 @@ import datetime
 import numpy as np
 import pytest
 
-from oisatgmi_b200 import synth
+import synth
 
 pytestmark = pytest.mark.gpu
 

@@ -9,7 +9,8 @@ import pytest
 
 import cases
 import emu
-from oisatgmi_b200 import _lib, kneedle, plan, synth
+from oisatgmi_b200 import _lib, kneedle, plan
+import synth
 from util import assert_field
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
