@@ -44,6 +44,20 @@ FLAG_THRESH = 0.0
 PRODUCT = "OMI_HCHO"
 N_LEV = 47
 
+# --config: the default (and the headline) is BASELINE configs[1]; tropomi_no2 is configs[4]
+# (TROPOMI-scale NO2, days sharded over the ranks), for the scaling evidence under profiles/
+WORKLOADS = {
+    "omi_hcho": dict(product="OMI_HCHO", sensor="OMI", gas="HCHO", grid_size=0.25, thresh=0.0,
+                     n_lev=47, trop=False, orbits=15, days=29, px=1644 * 60, reader_bytes_px=216,
+                     label="OMI HCHO one-month OI with AMF recalculation from scattering weights "
+                           "(BASELINE configs[1])"),
+    "tropomi_no2": dict(product="TROPOMI_NO2", sensor="TROPOMI", gas="NO2", grid_size=0.10, thresh=0.75,
+                        n_lev=34, trop=True, orbits=14, days=1, px=4172 * 450, reader_bytes_px=156,
+                        label="TROPOMI-scale NO2 OI (BASELINE configs[4]), days sharded over the "
+                              "ranks: 14 orbits x 4172 x 450 px x 34 levels per day, 0.10 degree "
+                              "mesh, 90-entry stencils"),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -51,8 +65,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--days", type=int, default=29)
-    ap.add_argument("--orbits", type=int, default=15)
+    ap.add_argument("--config", default="omi_hcho", choices=sorted(WORKLOADS))
+    ap.add_argument("--days", type=int, default=None, help="days per rank (weak) / in total (--strong)")
+    ap.add_argument("--orbits", type=int, default=None)
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: the --days days of ONE job are dealt to the ranks")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -65,12 +82,12 @@ def orbit_geo(i, n_orbits):
     return dict(node_lon_deg=150.0 - i * (360.0 / 14.6))
 
 
-def make_day(seed0, n_orbits):
+def make_day(seed0, n_orbits, product=PRODUCT):
     import synth
     grans = []
     for i in range(n_orbits):
         t = datetime.datetime(2005, 6, 1) + datetime.timedelta(seconds=1800 + i * 5933)
-        grans.append(synth.make_amf_granule(seed0 + i, PRODUCT, geo=orbit_geo(i, n_orbits),
+        grans.append(synth.make_amf_granule(seed0 + i, product, geo=orbit_geo(i, n_orbits),
                                             bad_fraction=0.2, time=t))
     return grans
 
@@ -252,11 +269,17 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         pg = dist.group.WORLD
     t_setup = time.perf_counter()
+    wl = WORKLOADS[args.config]
+    n_orbits = args.orbits or wl["orbits"]
+    total_days = args.days or wl["days"]
+    # weak scaling (default): every rank processes `days` days of its own; --strong: the days of
+    # one job are dealt to the ranks round-robin (rank r owns days r, r + N, ...)
+    my_days = list(range(rank, total_days, world)) if args.strong else list(range(total_days))
     model = make_model()
-    day = make_day(1000 * rank, args.orbits)
+    day = make_day(0 if args.strong else 1000 * rank, n_orbits, wl["product"])
 
     def new_pipe():
-        return MonthPipeline(model, GRID_SIZE, FLAG_THRESH, sensor="OMI", gas="HCHO",
+        return MonthPipeline(model, wl["grid_size"], wl["thresh"], sensor=wl["sensor"], gas=wl["gas"],
                              error_ctm=50.0, process_group=pg)
 
     pipe = new_pipe()
@@ -264,10 +287,10 @@ def main():
     lons = [np.asarray(g.longitude_center) for g in day]
     lats = [np.asarray(g.latitude_center) for g in day]
     t0 = time.perf_counter()
-    plans = _plan.granule_plans(lons, lats, pipe.gplan, GRID_SIZE * 2.0)
+    plans = _plan.granule_plans(lons, lats, pipe.gplan, wl["grid_size"] * 2.0)
     plan_build_s = time.perf_counter() - t0
     import copy
-    for d in range(args.days):
+    for d in my_days:
         for i, g in enumerate(day):
             gg = copy.copy(g)
             gg.time = g.time + datetime.timedelta(days=d)
@@ -336,7 +359,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     g0 = pipe.granules[0]
-    rec_bytes = 2 * (2 * N_LEV + 2)            # float16 rows of one pixel (SW, p, vcd, sigma)
+    rec_bytes = 2 * (2 * wl["n_lev"] + 2 + int(wl["trop"]))   # float16 rows of one pixel (SW, p, vcd, sigma, trop)
     px_bytes = rec_bytes + 8 + 1               # + amf (f64) + quality byte
     pair_bytes = 3 * 72 * 4 + 5 * 8            # model column (3 x 72 f32) + 5 staged f64
     n_pairs = host_t["n_pairs"]
@@ -344,7 +367,7 @@ def main():
     fused_ms = phase_ms.get("fused", float("nan"))
     achieved = fused_bytes / (fused_ms * 1e-3) / 1e9
     # whole-pipeline view with SURVEY.md section 8d's per-pixel figure (427 B/px for OMI HCHO)
-    pipe_bytes_px = 216 + (n_pairs / n_px) * (864 + 160) + 207936 * 14 * 8 / n_px
+    pipe_bytes_px = wl["reader_bytes_px"] + (n_pairs / n_px) * (864 + 160) + 207936 * 14 * 8 / n_px
     # measured DRAM traffic of the same two kernels: one `ncu --set full` capture (profiles/), scaled
     # linearly from the captured launch's pixel count to this launch's
     traffic = None
@@ -424,7 +447,7 @@ def main():
                "breakdown_s": {k: float(np.mean(v)) for k, v in parts.items()}}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == "omi_hcho":
         cpu, _ = cpu_baseline(1)     # one full granule on one core, measured (about a minute)
 
     if world > 1:
@@ -436,11 +459,14 @@ def main():
     line = {
         "metric": "L2 pixels/sec through interp+AMF+grid+OI", "value": value, "unit": "px/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": "OMI HCHO one-month OI with AMF recalculation from scattering weights "
-                               "(BASELINE configs[1]): %d granules x 98,640 px x 47 levels per GPU, "
-                               "GMI 361x576x72 grid, 8 model slots" % len(pipe.granules),
+        "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %d granules x %s px x %d levels per GPU, GMI 361x576x72 grid, "
+                               "8 model slots%s" % (wl["label"], len(pipe.granules),
+                                                    format(wl["px"], ","), wl["n_lev"],
+                                                    "; ONE job of %d days dealt to %d ranks"
+                                                    % (total_days, world) if args.strong else ""),
+                   "name": args.config,
                    "granules_per_gpu": len(pipe.granules), "pixels_per_gpu": n_px,
                    "pairs_per_gpu": int(n_pairs), "l2": "inputs_larger_than_L2 (%.1f GB resident)"
                    % (pipe.input_bytes() / 1e9), "geometry_plan": "cached in HBM for `value`, rebuilt "
