@@ -197,6 +197,18 @@ int oisat_reader_pmid(int32_t mode, const double* a, const double* b, const void
 int oisat_reader_tropopause(const int32_t* layer, const void* p_mid, int32_t n_lev, int64_t n_px,
                             void* out, void* stream);
 
+/* MOPITT / GOSAT clean-up (reader.py:1143-1203 mopitt_reader_co, :1228-1262 gosat_reader_xch4):
+ * out[lev][px] = cast_out(post(factors(pre(src)))) with pre bit 0: v <= 0 -> NaN, bit 1: inf ->
+ * NaN on the source value; up to three HOST factors multiplied one after the other in the
+ * source dtype (float32 / float64); post bit 0: r <= 0 -> NaN on the converted value;
+ * pixel_major != 0: src is [px][lev] (the files' profile variables) and is transposed. */
+int oisat_reader_clean(const void* src, int32_t dtype, int64_t n_px, int32_t n_lev,
+                       int32_t pixel_major, int32_t pre, const double* h_factors,
+                       int32_t n_factors, int32_t out_dtype, int32_t post, void* out, void* stream);
+/* MOPITT x_col (reader.py:1168): float32(float16(1e6 * vcd16) / float32(dry * 1e-15)). */
+int oisat_reader_mopitt_xcol(const void* vcd_f16, const float* dry_air, int64_t n, float* x_col,
+                             void* stream);
+
 /* good[p] = (quality_flag[p] > thresh)  (interpolator.py:126-128) */
 int oisat_quality_mask(const void* qflag, int32_t dtype, int64_t n_px, double thresh,
                        uint8_t* good, void* stream);

@@ -72,6 +72,8 @@ PROTOTYPES = {
     "oisat_reader_weights": (C.c_int, [vp, i32, i32, i32, i64, vp, i32, vp, vp]),
     "oisat_reader_pmid": (C.c_int, [i32, vp, vp, vp, i32, f64, i32, i64, vp, vp]),
     "oisat_reader_tropopause": (C.c_int, [vp, vp, i32, i64, vp, vp]),
+    "oisat_reader_clean": (C.c_int, [vp, i32, i64, i32, i32, i32, C.POINTER(f64), i32, i32, i32, vp, vp]),
+    "oisat_reader_mopitt_xcol": (C.c_int, [vp, vp, i64, vp, vp]),
     "oisat_quality_mask": (C.c_int, [vp, i32, i64, f64, vp, vp]),
     "oisat_interp_apply": (C.c_int, [vp, vp, i32, i64, vp, C.POINTER(Field), i32, vp, i64, vp, vp]),
     "oisat_vertical_amf": (C.c_int, [i64, vp, vp, vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, i32,

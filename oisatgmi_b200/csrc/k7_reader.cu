@@ -192,6 +192,47 @@ rd_tropopause_kernel(const int32_t* __restrict__ layer, const __half* __restrict
 
 static bool float_dtype(int d) { return d == OISAT_F16 || d == OISAT_F32 || d == OISAT_F64; }
 
+// MOPITT / GOSAT clean-up (reader.py:1143-1203, 1228-1262): optional thresholds on the SOURCE
+// value (bit 0: v <= 0 -> NaN, bit 1: inf -> NaN), up to three factors multiplied in the
+// array's own dtype (NEP 50: a Python float times a float32 array stays float32), cast to the
+// output dtype, optional threshold on the RESULT (bit 0: r <= 0 -> NaN, as for the a-priori
+// column, :1180-1181), and the (pixel, level) -> (level, pixel) transposition of the files'
+// profile variables.  Thread = output element; a NaN compares false, so it stays NaN.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+rd_clean_kernel(const TI* __restrict__ src, int64_t n_px, int n_lev, int pixel_major, int pre,
+                double f0, double f1, double f2, int nf, int post, TO* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_px * n_lev) return;
+  const int64_t lev = i / n_px, px = i - lev * n_px;
+  TI v = src[pixel_major ? px * n_lev + lev : i];
+  if (((pre & 1) && v <= (TI)0) || ((pre & 2) && isinf(v))) v = (TI)CUDART_NAN;
+  if (nf > 0) v = v * (TI)f0;      // (--fmad=false: one rounding per multiply)
+  if (nf > 1) v = v * (TI)f1;
+  if (nf > 2) v = v * (TI)f2;
+  TO r;
+  if constexpr (sizeof(TO) == 2) {
+    r = sizeof(TI) == 8 ? __double2half((double)v) : __float2half_rn((float)v);
+    if ((post & 1) && __half2float(r) <= 0.0f) r = __float2half_rn(CUDART_NAN_F);
+  } else {
+    r = (TO)v;
+    if ((post & 1) && r <= (TO)0) r = (TO)CUDART_NAN;
+  }
+  out[i] = r;
+}
+
+// x_col of the MOPITT reader (reader.py:1168): (1e6 * vcd / (dry * 1e-15)).astype(float32) with
+// vcd float16 -- numpy forms 1e6 * vcd in float16 (it overflows to inf: kept, the reference
+// does the same), dry * 1e-15 in float32, and the quotient in float32.
+__global__ void __launch_bounds__(256)
+rd_mopitt_xcol_kernel(const __half* __restrict__ vcd, const float* __restrict__ dry, int64_t n,
+                      float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const __half num = __float2half_rn(__fmul_rn(__half2float(vcd[i]), __half2float(__float2half_rn(1e6f))));
+  out[i] = __fdiv_rn(__half2float(num), __fmul_rn(dry[i], 1e-15f));
+}
+
 }  // namespace oisat
 
 using namespace oisat;
@@ -273,6 +314,53 @@ extern "C" int oisat_reader_tropopause(const int32_t* layer, const void* p_mid, 
   OISAT_CHECK_ARG(layer && p_mid && out && n_lev >= 1, "null pointer");
   rd_tropopause_kernel<<<(unsigned)ceil_div(n_px, 256), 256, 0, (cudaStream_t)stream>>>(
       layer, (const __half*)p_mid, n_lev, n_px, (__half*)out);
+  OISAT_CHECK_LAUNCH();
+  return OISAT_OK;
+}
+
+template <typename TI>
+static int launch_clean(const void* src, int64_t n_px, int n_lev, int pixel_major, int pre, double f0,
+                        double f1, double f2, int nf, int out_dtype, int post, void* out,
+                        cudaStream_t s) {
+  const unsigned blocks = (unsigned)ceil_div(n_px * n_lev, 256);
+  if (out_dtype == OISAT_F16)
+    rd_clean_kernel<TI, __half><<<blocks, 256, 0, s>>>((const TI*)src, n_px, n_lev, pixel_major, pre,
+                                                       f0, f1, f2, nf, post, (__half*)out);
+  else if (out_dtype == OISAT_F32)
+    rd_clean_kernel<TI, float><<<blocks, 256, 0, s>>>((const TI*)src, n_px, n_lev, pixel_major, pre,
+                                                      f0, f1, f2, nf, post, (float*)out);
+  else
+    rd_clean_kernel<TI, double><<<blocks, 256, 0, s>>>((const TI*)src, n_px, n_lev, pixel_major, pre,
+                                                       f0, f1, f2, nf, post, (double*)out);
+  OISAT_CHECK_LAUNCH();
+  return OISAT_OK;
+}
+
+extern "C" int oisat_reader_clean(const void* src, int32_t dtype, int64_t n_px, int32_t n_lev,
+                                  int32_t pixel_major, int32_t pre, const double* h_factors,
+                                  int32_t n_factors, int32_t out_dtype, int32_t post, void* out,
+                                  void* stream) {
+  if (n_px <= 0 || n_lev <= 0) return OISAT_OK;
+  OISAT_CHECK_ARG(src && out, "null pointer");
+  OISAT_CHECK_ARG(dtype == OISAT_F32 || dtype == OISAT_F64, "source must be float32 or float64");
+  OISAT_CHECK_ARG(float_dtype(out_dtype), "bad output dtype");
+  OISAT_CHECK_ARG(n_factors >= 0 && n_factors <= 3 && (n_factors == 0 || h_factors), "bad factors");
+  const double f0 = n_factors > 0 ? h_factors[0] : 1.0, f1 = n_factors > 1 ? h_factors[1] : 1.0,
+               f2 = n_factors > 2 ? h_factors[2] : 1.0;
+  cudaStream_t s = (cudaStream_t)stream;
+  return dtype == OISAT_F32
+             ? launch_clean<float>(src, n_px, n_lev, pixel_major, pre, f0, f1, f2, n_factors, out_dtype,
+                                   post, out, s)
+             : launch_clean<double>(src, n_px, n_lev, pixel_major, pre, f0, f1, f2, n_factors,
+                                    out_dtype, post, out, s);
+}
+
+extern "C" int oisat_reader_mopitt_xcol(const void* vcd_f16, const float* dry_air, int64_t n,
+                                        float* x_col, void* stream) {
+  if (n <= 0) return OISAT_OK;
+  OISAT_CHECK_ARG(vcd_f16 && dry_air && x_col, "null pointer");
+  rd_mopitt_xcol_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)vcd_f16, dry_air, n, x_col);
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
 }

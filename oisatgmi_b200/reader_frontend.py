@@ -184,3 +184,89 @@ def tropomi_no2(v, trop, read_ak=True, device=False):
         tropopause = np.empty((1))
     vcd, unc, qf, p_mid, sw, tropopause = _finish([vcd, unc, qf, p_mid, sw, tropopause], device)
     return _record(vcd, amf, time, tropopause, lat, lon, unc, qf, p_mid, sw)
+
+
+# ------------------------------------------------------------------ satellite_opt products
+def _clean(src, shape_px, n_lev=1, pixel_major=False, pre=0, factors=(), out="float32", post=0):
+    """oisat_reader_clean on one file variable: returns a device tensor shaped
+    (n_lev,) + shape_px (or shape_px when n_lev == 1)."""
+    L = _lib.lib()
+    a = np.asarray(src)
+    if a.dtype not in (np.float32, np.float64):
+        a = a.astype(np.float64)
+    d = _dev.to_device(np.ascontiguousarray(a))
+    n_px = int(np.prod(shape_px))
+    o = _dev.empty((n_lev * n_px,), out)
+    f = (C.c_double * max(len(factors), 1))(*factors)
+    code = {"float16": _lib.F16, "float32": _lib.F32, "float64": _lib.F64}[out]
+    _lib.check(L.oisat_reader_clean(d.data_ptr(), _dev.dtype_code(d), n_px, n_lev, int(pixel_major),
+                                    pre, f, len(factors), code, post, o.data_ptr(), _dev.stream()))
+    return o.reshape(((n_lev,) if n_lev > 1 else ()) + tuple(shape_px))
+
+
+def _native(a):
+    a = np.asarray(a)
+    return "float64" if a.dtype not in (np.float32,) else "float32"
+
+
+def mopitt_co(v, read_ak=True, device=False):
+    """reader.py:1143-1203 (`mopitt_reader_co` up to its interpolator call).  `v`: the MOP03
+    'Data Fields' variables plus StartTime / StopTime of the file attributes."""
+    from .config import satellite_opt
+    _dev.require_cuda()
+    L = _lib.lib()
+    time = _epoch(0.5 * (v["StartTime"] + v["StopTime"]), 1993)
+    lat = np.asarray(v["Latitude"]).astype("float32")
+    lon = np.asarray(v["Longitude"]).astype("float32")
+    lon, lat = np.meshgrid(lon, lat)
+    lon, lat = np.transpose(lon), np.transpose(lat)
+    shape = lat.shape
+    vcd = _clean(v["RetrievedCOTotalColumnDay"], shape, pre=3, factors=(1e-15,), out="float16")
+    dry = _up(np.asarray(v["DryAirColumnDay"]).astype(np.float32))
+    x_col = _dev.empty((vcd.numel(),), "float32")
+    _lib.check(L.oisat_reader_mopitt_xcol(vcd.data_ptr(), dry.data_ptr(), vcd.numel(),
+                                          x_col.data_ptr(), _dev.stream()))
+    x_col = x_col.reshape(tuple(shape))
+    ap_prof = _clean(v["APrioriCOMixingRatioProfileDay"], shape, 9, True, pre=1,
+                     out=_native(v["APrioriCOMixingRatioProfileDay"]))
+    ap_sfc = _clean(v["APrioriCOSurfaceMixingRatioDay"], shape, pre=1,
+                    out=_native(v["APrioriCOSurfaceMixingRatioDay"]))
+    ap_col = _clean(v["APrioriCOTotalColumnDay"], shape, factors=(1e-15,), out="float16", post=1)
+    unc = _clean(v["RetrievedCOTotalColumnMeanUncertaintyDay"], shape, factors=(1e-15,), out="float32")
+    levels = np.asarray(v["Pressure"]).astype("float16").astype(np.float64)
+    p_mid = _pmid(0, levels, None, None, 0.0, 9, shape)
+    if read_ak:
+        aks = _clean(v["TotalColumnAveragingKernelDay"], shape, 10, True, factors=(1e-15,), out="float16")
+    else:
+        aks = np.empty((1))
+    vcd, x_col, ap_prof, ap_sfc, ap_col, unc, p_mid, aks = _finish(
+        [vcd, x_col, ap_prof, ap_sfc, ap_col, unc, p_mid, aks], device)
+    quality = np.ones(shape, dtype=np.float16)
+    return satellite_opt(vcd, time, [], np.empty((1)), lat, lon, [], [], unc, quality, p_mid, aks, [],
+                         [], [], [], ap_col, ap_prof, v["SurfacePressureDay"], ap_sfc, x_col, [],
+                         "MOPITT")
+
+
+def gosat_xch4(v, read_ak=True, device=False):
+    """reader.py:1228-1264 (`gosat_reader_xch4` up to the gap filler)."""
+    from .config import satellite_opt
+    _dev.require_cuda()
+    time = datetime.datetime(1970, 1, 1) + datetime.timedelta(
+        seconds=int(np.squeeze(np.nanmean(v["time"]))))
+    lat = np.asarray(v["latitude"]).astype("float32")
+    lon = np.asarray(v["longitude"]).astype("float32")
+    n = (lat.size,)
+    nlev = int(np.shape(v["pressure_levels"])[1])
+    xch4 = _clean(v["xch4"], n, pre=3, out=_native(v["xch4"]))
+    ap = _clean(v["ch4_profile_apriori"], n, nlev, True, pre=1, out=_native(v["ch4_profile_apriori"]))
+    p_mid = _clean(v["pressure_levels"], n, nlev, True, pre=1, out=_native(v["pressure_levels"]))
+    if read_ak:
+        aks = _clean(v["xch4_averaging_kernel"], n, nlev, True, pre=1,
+                     out=_native(v["xch4_averaging_kernel"]))
+        pw = _clean(v["pressure_weight"], n, nlev, True, pre=1, out=_native(v["pressure_weight"]))
+    else:
+        aks, pw = np.empty((1)), np.empty((1))
+    xch4, ap, p_mid, aks, pw = _finish([xch4, ap, p_mid, aks, pw], device)
+    return satellite_opt(xch4, time, [], np.empty((1)), lat, lon, [], [], v["xch4_uncertainty"],
+                         1 - v["xch4_quality_flag"], p_mid, aks, [], [], [], [], np.empty((1)), ap,
+                         np.empty((1)), np.empty((1)), xch4, pw, "GOSAT")

@@ -77,36 +77,36 @@ def o3_chain(ref):
                           cases.o3_case()["granules"])
 
 
-READER_CALLS = [("omi_no2", (True,)), ("omi_no2", (False,)), ("omi_hcho", ()),
-                ("tropomi_no2", (True,)), ("tropomi_no2", (False,))]
-READER_FIELDS = ("vcd", "amf", "tropopause", "latitude_center", "longitude_center", "uncertainty",
-                 "quality_flag", "pressure_mid", "scattering_weights")
-
-
 def reader_chain(ref, product):
-    """Outputs of the reference's own reader functions (reader.py:707-983) with their file
-    access (`_read_group_nc`) answered from cases.reader_vars()."""
+    """Outputs of the reference's own reader functions (reader.py:707-983, 1130-1275) with their
+    file access (`_read_group_nc`, `_read_nc`, the MOPITT file attributes) answered from
+    cases.reader_vars().  GOSAT: the record is taken where the reader hands it to the gap
+    filler (reader.py:1266), which has its own fixtures."""
+    import chains
     rd = sys.modules["oisatgmi.reader"]
     fn = {"omi_no2": rd.omi_reader_no2, "omi_hcho": rd.omi_reader_hcho,
-          "tropomi_no2": rd.tropomi_reader_no2}[product]
+          "tropomi_no2": rd.tropomi_reader_no2, "mopitt_co": rd.mopitt_reader_co,
+          "gosat_xch4": rd.gosat_reader_xch4}[product]
     v = cases.reader_vars(product)
-    saved = rd._read_group_nc
+    saved = {n: getattr(rd, n) for n in ("_read_group_nc", "_read_nc", "_get_nc_attr_group_mopitt",
+                                         "filler_gosatxch4")}
     rd._read_group_nc = lambda fname, group, var: np.squeeze(np.array(v[var]))
+    rd._read_nc = lambda fname, var: np.squeeze(np.array(v[var]))
+    rd._get_nc_attr_group_mopitt = lambda fname: {"StartTime": v["StartTime"], "StopTime": v["StopTime"]}
+    rd.filler_gosatxch4 = lambda grid_size, sat, flag_thresh=0.75: sat
     store = {}
     try:
-        for prod, args in READER_CALLS:
+        for prod, args in chains.READER_CALLS:
             if prod != product:
                 continue
-            r = quiet(fn, "dir/granule.nc", None, True) if product == "omi_hcho" else \
-                quiet(fn, "dir/granule.nc", args[0], None, True)
-            tag = "trop%d" % int(args[0]) if args else "all"
-            store[tag + ".time"] = np.array(r.time.isoformat())
-            for n in READER_FIELDS:
-                a = np.asarray(getattr(r, n))
-                if a.size > 1:
-                    store["%s.%s" % (tag, n)] = a
+            if product in ("omi_hcho", "mopitt_co", "gosat_xch4"):
+                r = quiet(fn, "dir/granule.nc", None, True)
+            else:
+                r = quiet(fn, "dir/granule.nc", args[0], None, True)
+            chains.reader_record(store, "trop%d" % int(args[0]) if args else "all", r)
     finally:
-        rd._read_group_nc = saved
+        for n, f in saved.items():
+            setattr(rd, n, f)
     return store
 
 

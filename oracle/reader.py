@@ -4,7 +4,8 @@ reference's level-2 readers do to the file variables before they call
 quality flags, scattering-weight clean-up, mid-level pressures, tropopause.
 
 Follows /root/reference/oisatgmi/reader.py: omi_reader_no2 (:807-903),
-omi_reader_hcho (:906-983), tropomi_reader_no2 (:707-804).  File access is not
+omi_reader_hcho (:906-983), tropomi_reader_no2 (:707-804), mopitt_reader_co (:1130-1213),
+gosat_reader_xch4 (:1216-1275, up to the gap filler).  File access is not
 part of it: `v` maps the variable names those functions read to arrays with the
 file's dtypes and shapes (what `_read_group_nc`, :51-67, returns: np.squeeze of the
 variable).  Every expression keeps numpy's promotion rules (NEP 50: Python
@@ -150,3 +151,71 @@ def tropomi_no2(v, trop, read_ak=True):
         tropopause = np.empty((1))
     return satellite_amf(vcd, amf, time, tropopause, lat, lon, [], [], unc, qf, p_mid, sw, [], [],
                          [], [], [])
+
+
+# ------------------------------------------------------------------ satellite_opt products
+def mopitt_co(v, read_ak=True):
+    """reader.py:1143-1203 (mopitt_reader_co before its interpolator call).  `v` holds the
+    MOP03 'Data Fields' variables plus StartTime / StopTime of the file attributes
+    (_get_nc_attr_group_mopitt, :47-56)."""
+    from oisatgmi_b200.config import satellite_opt
+    t = 0.5 * (v["StartTime"] + v["StopTime"])
+    time = _epoch(t, 1993)
+    lat = v["Latitude"].astype("float32")
+    lon = v["Longitude"].astype("float32")
+    lon, lat = np.meshgrid(lon, lat)
+    lon, lat = np.transpose(lon), np.transpose(lat)
+    vcd = np.array(v["RetrievedCOTotalColumnDay"])
+    vcd[np.where((vcd <= 0) | (np.isinf(vcd)))] = np.nan
+    vcd = (vcd * 1e-15).astype("float16")
+    dry = v["DryAirColumnDay"]
+    with np.errstate(all="ignore"):
+        x_col = (1e6 * vcd / (dry * 1e-15)).astype("float32")     # 1e6 * float16 overflows: kept
+    ap_prof = np.array(v["APrioriCOMixingRatioProfileDay"]).transpose((2, 0, 1))
+    ap_prof[ap_prof <= 0] = np.nan
+    ap_sfc = np.array(v["APrioriCOSurfaceMixingRatioDay"])
+    p_sfc = v["SurfacePressureDay"]
+    ap_sfc[ap_sfc <= 0] = np.nan
+    ap_col = (v["APrioriCOTotalColumnDay"] * 1e-15).astype("float16")
+    ap_col[ap_col <= 0] = np.nan
+    unc = (v["RetrievedCOTotalColumnMeanUncertaintyDay"] * 1e-15).astype("float32")
+    ps = v["Pressure"].astype("float16")
+    p_mid = np.zeros((9, np.shape(vcd)[0], np.shape(vcd)[1])).astype("float16")
+    if read_ak == True:  # noqa: E712
+        aks = v["TotalColumnAveragingKernelDay"] * 1e-15
+        aks = aks.transpose((2, 0, 1)).astype("float16")
+    else:
+        aks = np.empty((1))
+    for z in range(0, 9):
+        p_mid[z, :, :] = ps[z]
+    return satellite_opt(vcd, time, [], np.empty((1)), lat, lon, [], [], unc, np.ones_like(vcd),
+                         p_mid, aks, [], [], [], [], ap_col, ap_prof, p_sfc, ap_sfc, x_col, [],
+                         "MOPITT")
+
+
+def gosat_xch4(v, read_ak=True):
+    """reader.py:1228-1264 (gosat_reader_xch4 before the gap filler)."""
+    from oisatgmi_b200.config import satellite_opt
+    time = datetime.datetime(1970, 1, 1) + datetime.timedelta(
+        seconds=int(np.squeeze(np.nanmean(v["time"]))))
+    lat = v["latitude"].astype("float32")
+    lon = v["longitude"].astype("float32")
+    xch4 = np.array(v["xch4"])
+    xch4[np.where((xch4 <= 0) | (np.isinf(xch4)))] = np.nan
+    ap = np.array(v["ch4_profile_apriori"]).transpose()
+    ap[ap <= 0] = np.nan
+    qflag = v["xch4_quality_flag"]
+    unc = v["xch4_uncertainty"]
+    p_mid = np.array(v["pressure_levels"])
+    p_mid[p_mid <= 0] = np.nan
+    if read_ak == True:  # noqa: E712
+        aks = np.array(v["xch4_averaging_kernel"]).transpose()
+        pw = np.array(v["pressure_weight"]).transpose()
+        aks[aks <= 0] = np.nan
+        pw[pw <= 0] = np.nan
+    else:
+        aks, pw = np.empty((1)), np.empty((1))
+    p_mid = np.transpose(p_mid)
+    return satellite_opt(xch4, time, [], np.empty((1)), lat, lon, [], [], unc, 1 - qflag, p_mid,
+                         aks, [], [], [], [], np.empty((1)), ap, np.empty((1)), np.empty((1)), xch4,
+                         pw, "GOSAT")

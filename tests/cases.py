@@ -146,7 +146,7 @@ def subset_levels(a):
 
 
 # ---------------------------------------------------------------- reader front-end
-READER_PRODUCTS = ("omi_no2", "omi_hcho", "tropomi_no2")
+READER_PRODUCTS = ("omi_no2", "omi_hcho", "tropomi_no2", "mopitt_co", "gosat_xch4")
 
 
 def reader_vars(product, seed=3, nt=90, nxt=24):
@@ -218,4 +218,45 @@ def reader_vars(product, seed=3, nt=90, nxt=24):
             v[name] = f32(np.exp(rng.normal(-9.5, 1.0, shape)))               # mol m-2
             v[name + "_precision"] = f32(np.exp(rng.normal(-11.0, 0.5, shape)))
         return v
+    if product == "mopitt_co":
+        # MOP03 daily L3 'Data Fields' (reader.py:1143-1203): (lon, lat[, level]) float32 grids
+        # with the product's -9999 fill value, 9 fixed pressure levels
+        nlon, nlat = 72, 36
+        shp = (nlon, nlat)
+
+        def fill(a, frac=0.3):
+            a = f32(a)
+            a[rng.uniform(size=a.shape) < frac] = -9999.0
+            return a
+        return {"StartTime": 3.93e8, "StopTime": 3.93e8 + 86399.0,
+                "Latitude": f32(np.linspace(-87.5, 87.5, nlat)),
+                "Longitude": f32(np.linspace(-177.5, 177.5, nlon)),
+                "RetrievedCOTotalColumnDay": fill(np.exp(rng.normal(42.0, 0.3, shp))),
+                "DryAirColumnDay": f32(2.1e25 * (1.0 + 0.02 * rng.normal(size=shp))),
+                "APrioriCOMixingRatioProfileDay": fill(rng.uniform(40.0, 160.0, shp + (9,)), 0.1),
+                "APrioriCOSurfaceMixingRatioDay": fill(rng.uniform(60.0, 200.0, shp), 0.1),
+                "SurfacePressureDay": f32(rng.uniform(600.0, 1030.0, shp)),
+                "APrioriCOTotalColumnDay": fill(np.exp(rng.normal(42.0, 0.2, shp)), 0.1),
+                "RetrievedCOTotalColumnMeanUncertaintyDay": f32(np.exp(rng.normal(39.0, 0.4, shp))),
+                "Pressure": f32([900., 800., 700., 600., 500., 400., 300., 200., 100.]),
+                "TotalColumnAveragingKernelDay": fill(np.exp(rng.normal(37.0, 0.5, shp + (10,))), 0.1)}
+    if product == "gosat_xch4":
+        # GOSAT proxy XCH4 level 2 (reader.py:1228-1262): per-sounding vectors, (N, 20) profiles
+        n, L = 700, 20
+        frac = (np.arange(L) + 0.5) / L
+        ps = rng.uniform(600.0, 1013.0, n)
+
+        def holes(a, frac_bad=0.05, val=-999.0):
+            a = np.array(a, dtype=np.float32)
+            a[rng.uniform(size=a.shape) < frac_bad] = val
+            return a
+        return {"time": 1.118e9 + np.arange(n) * 4.0,
+                "latitude": f32(rng.uniform(-60.0, 75.0, n)), "longitude": f32(rng.uniform(-170.0, 170.0, n)),
+                "xch4": holes(rng.normal(1800.0, 20.0, n)),
+                "ch4_profile_apriori": holes(1850.0 - 300.0 * frac[None] ** 2 + rng.normal(0, 5.0, (n, L))),
+                "xch4_quality_flag": (rng.uniform(size=n) < 0.2).astype(np.int8),
+                "xch4_uncertainty": f32(rng.uniform(5.0, 15.0, n)),
+                "pressure_levels": holes(ps[:, None] * (1.0 - frac[None]) + 0.1, 0.02, 0.0),
+                "xch4_averaging_kernel": holes(rng.uniform(0.3, 1.2, (n, L)), 0.03, -1.0),
+                "pressure_weight": holes(np.full((n, L), 1.0 / L), 0.03, 0.0)}
     raise KeyError(product)

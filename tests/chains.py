@@ -204,9 +204,22 @@ def cuda_impl():
 
 
 READER_CALLS = [("omi_no2", (True,)), ("omi_no2", (False,)), ("omi_hcho", ()),
-                ("tropomi_no2", (True,)), ("tropomi_no2", (False,))]
+                ("tropomi_no2", (True,)), ("tropomi_no2", (False,)),
+                ("mopitt_co", ()), ("gosat_xch4", ())]
 READER_FIELDS = ("vcd", "amf", "tropopause", "latitude_center", "longitude_center", "uncertainty",
                  "quality_flag", "pressure_mid", "scattering_weights")
+READER_FIELDS_OPT = ("vcd", "latitude_center", "longitude_center", "uncertainty", "quality_flag",
+                     "pressure_mid", "averaging_kernels", "aprior_column", "apriori_profile",
+                     "surface_pressure", "apriori_surface", "x_col", "pressure_weight")
+
+
+def reader_record(store, tag, r):
+    store[tag + ".time"] = np.array(r.time.isoformat())
+    names = READER_FIELDS if hasattr(r, "scattering_weights") else READER_FIELDS_OPT
+    for n in names:
+        a = np.asarray(getattr(r, n))
+        if a.size > 1:
+            store["%s.%s" % (tag, n)] = a
 
 
 def reader_chain(module, product):
@@ -219,12 +232,7 @@ def reader_chain(module, product):
         if prod != product:
             continue
         r = getattr(module, product)(v, *args)
-        tag = "trop%d" % int(args[0]) if args else "all"
-        store[tag + ".time"] = np.array(r.time.isoformat())
-        for n in READER_FIELDS:
-            a = np.asarray(getattr(r, n))
-            if a.size > 1:
-                store["%s.%s" % (tag, n)] = a
+        reader_record(store, "trop%d" % int(args[0]) if args else "all", r)
     return store
 
 

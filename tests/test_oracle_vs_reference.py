@@ -55,43 +55,14 @@ def test_bias_table_matches_driver():
         assert np.array_equal(d.sat_averaged_vcd, (np.array([[2.0, 5.0]]) - a) / b)
 
 
-READER_CALLS = [("omi_no2", (True,)), ("omi_no2", (False,)), ("omi_hcho", ()),
-                ("tropomi_no2", (True,)), ("tropomi_no2", (False,))]
-READER_FIELDS = ("vcd", "amf", "tropopause", "latitude_center", "longitude_center", "uncertainty",
-                 "quality_flag", "pressure_mid", "scattering_weights")
-
-
-def reference_reader(product, v, args):
-    """The unmodified reader function of the reference, with its only file access
-    (`_read_group_nc`, reader.py:51-67) answered from the dictionary `v`."""
-    import sys
-    ref_shim.load_reference()
-    rd = sys.modules["oisatgmi.reader"]
-    fn = {"omi_no2": rd.omi_reader_no2, "omi_hcho": rd.omi_reader_hcho,
-          "tropomi_no2": rd.tropomi_reader_no2}[product]
-    saved = rd._read_group_nc
-    rd._read_group_nc = lambda fname, group, var: np.squeeze(np.array(v[var]))
-    try:
-        with contextlib.redirect_stdout(io.StringIO()):
-            if product == "omi_hcho":
-                return fn("dir/granule.nc", None, True)
-            return fn("dir/granule.nc", args[0], None, True)
-    finally:
-        rd._read_group_nc = saved
-
-
-@pytest.mark.parametrize("product,args", READER_CALLS)
-def test_reader_front_end_is_bit_identical_to_reference(product, args):
-    from oracle import reader as oreader
-    v = cases.reader_vars(product)
-    want = reference_reader(product, v, args)
-    got = getattr(oreader, product)(v, *args)
-    assert want is not None and got.time == want.time
-    for n in READER_FIELDS:
-        a, b = np.asarray(getattr(got, n)), np.asarray(getattr(want, n))
-        if b.size > 1:
-            assert a.dtype == b.dtype and a.shape == b.shape, n
-            assert np.array_equal(a, b, equal_nan=True), n
+@pytest.mark.parametrize("product", cases.READER_PRODUCTS)
+def test_reader_front_end_is_bit_identical_to_reference(product):
+    """The unmodified reader functions of the reference (reader.py:707-983, 1130-1275), their
+    file access answered from a dictionary (oracle/make_golden.py:reader_chain), against the
+    restatement: every field, dtype and NaN bit for bit."""
+    from oracle import make_golden, reader as oreader
+    want = make_golden.reader_chain(ref_shim.load_reference(), product)
+    chains.same_bits(chains.reader_chain(oreader, product), want)
 
 
 def test_output_fields_are_bit_identical_to_write_to_nc(tmp_path):
