@@ -36,3 +36,16 @@ def output_fields(obj):
         "lon": f32(first.longitude_center), "lat": f32(first.latitude_center),
         "time": obj.avg_time.strftime("%Y-%m-%d %H:%M:%S"),
     }
+
+
+def ext_fields(lat, lon, scaling_factor, year, month):
+    """tools/convert2EXT.py:32-78 (data side): the variables of one GEOS ExtData file from the
+    `lat`, `lon`, `scaling_factor` arrays of a diagnostics file.  PINNED: the unmodified script
+    is run against recording stand-ins for netCDF4.Dataset (tests/test_oracle_vs_reference.py)."""
+    import datetime
+    t0 = datetime.datetime(int(year), int(month), 1) + datetime.timedelta(seconds=int(0.0))
+    sf = np.zeros((1,) + np.shape(lat), dtype=np.float64)
+    sf[:, :, :] = scaling_factor
+    return {"time": np.array([0.0]), "time_units": "hours since " + t0.strftime("%Y-%m-%d %H:%M:%S"),
+            "lat": np.array(lat[:, 0].squeeze(), dtype=np.float64),
+            "lon": np.array(lon[0, :].squeeze(), dtype=np.float64), "SF": sf}

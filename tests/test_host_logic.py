@@ -427,3 +427,22 @@ def test_granule_plans_routes_ties_and_failures(monkeypatch):
     assert out == [("v1", 0), ("v0", 1), ("v0", 2), None, ("v1", 0), ("v1", 0)]
     assert sorted(calls) == [1, 2]
     assert plan._plan_pool(3) is plan._plan_pool(3)
+
+
+def test_ext_fields_match_the_oracle_restatement():
+    """oisatgmi_b200.ext_output (GEOS ExtData form of the scaling factors, tools/convert2EXT.py)
+    against oracle.output.ext_fields, which is pinned to the unmodified script where the
+    reference is present."""
+    from oisatgmi_b200 import ext_output
+    from oracle import output as ooutput
+    rng = np.random.default_rng(9)
+    lat, lon = np.meshgrid(np.arange(-90.0, 90.5, 0.5), np.arange(-180.0, 180.0, 0.625), indexing="ij")
+    f = {"lat": lat.astype(np.float32), "lon": lon.astype(np.float32),
+         "scaling_factor": rng.uniform(0.2, 3.0, lat.shape).astype(np.float32)}
+    got = ext_output.ext_fields(f, "201912")
+    want = ooutput.ext_fields(f["lat"], f["lon"], f["scaling_factor"], 2019, 12)
+    assert got["time_units"] == want["time_units"] == "hours since 2019-12-01 00:00:00"
+    for k in ("time", "lat", "lon", "SF"):
+        assert got[k].dtype == np.float64 and np.array_equal(got[k], want[k]), k
+    ones = ext_output.ones_fields(f["lat"], f["lon"], 1990, 1)
+    assert ones["SF"].shape == (1,) + lat.shape and np.all(ones["SF"] == 1.0)

@@ -112,3 +112,86 @@ def test_output_fields_are_bit_identical_to_write_to_nc(tmp_path):
         else:
             assert a.dtype == got[k].dtype == np.float32
             assert np.array_equal(a, got[k], equal_nan=True), k
+
+
+def test_ext_fields_are_bit_identical_to_convert2EXT(tmp_path, monkeypatch):
+    """tools/convert2EXT.py, unmodified, run as the script it is against recording stand-ins
+    for netCDF4.Dataset (read side: one diagnostics file held in memory; write side: every
+    assignment recorded): the variables of the ExtData files equal oracle.output.ext_fields
+    and oisatgmi_b200.ext_output (a host-only module), for the real month and for the all-ones
+    months the script fabricates."""
+    import runpy
+    import sys
+    import types
+    from oisatgmi_b200 import ext_output
+    from oracle import output as ooutput
+    rng = np.random.default_rng(5)
+    lat, lon = np.meshgrid(np.arange(-90.0, 90.5, 10.0), np.arange(-180.0, 180.0, 20.0), indexing="ij")
+    diag = {"lat": lat.astype(np.float32), "lon": lon.astype(np.float32),
+            "scaling_factor": rng.uniform(0.5, 2.0, lat.shape).astype(np.float32)}
+    diag_dir, ext_dir = tmp_path / "diag", tmp_path / "ext"
+    diag_dir.mkdir()
+    (diag_dir / "HCHO_200506.nc").write_bytes(b"")
+    written = {}
+
+    class Var:
+        def __init__(self, store, name):
+            self.store, self.name = store, name
+
+        def __setitem__(self, key, value):
+            self.store[self.name] = np.array(np.broadcast_to(
+                np.asarray(value, dtype=np.float64), self.store["_shape_" + self.name]))
+
+    class FakeDataset:
+        def __init__(self, path, mode, format=None):
+            self.mode = mode
+            if mode == "r":
+                self.variables = diag
+            else:
+                self.store = written.setdefault(path.split("/")[-1], {})
+                self.dims = {}
+
+        def createDimension(self, name, size):
+            self.dims[name] = size
+            return size
+
+        def createVariable(self, name, kind, dims):
+            assert kind == "f8"
+            self.store["_shape_" + name] = tuple(self.dims[d] for d in dims)
+            v = Var(self.store, name)
+            object.__setattr__(self, "_last", v)
+            return _Attr(v, self.store)
+
+        def close(self):
+            pass
+
+    class _Attr:
+        """Variable handle that records attributes (units) as well as data."""
+        def __init__(self, var, store):
+            object.__setattr__(self, "_var", var)
+            object.__setattr__(self, "_store", store)
+
+        def __setitem__(self, key, value):
+            self._var[key] = value
+
+        def __setattr__(self, name, value):
+            self._store[self._var.name + "." + name] = value
+
+    monkeypatch.setitem(sys.modules, "netCDF4", types.SimpleNamespace(Dataset=FakeDataset))
+    monkeypatch.setattr(sys, "argv", ["convert2EXT.py", str(diag_dir), str(ext_dir)])
+    with contextlib.redirect_stdout(io.StringIO()):
+        runpy.run_path(ref_shim.REFERENCE_ROOT + "/tools/convert2EXT.py", run_name="__main__")
+    assert "HCHO_200506.nc" in written and "HCHO_199001.nc" in written
+
+    def check(store, want):
+        for k in ("time", "lat", "lon", "SF"):
+            assert store[k].dtype == want[k].dtype == np.float64 and store[k].shape == want[k].shape, k
+            assert np.array_equal(store[k], want[k]), k
+        assert store["time.units"] == want["time_units"]
+
+    real = written["HCHO_200506.nc"]
+    check(real, ooutput.ext_fields(diag["lat"], diag["lon"], diag["scaling_factor"], 2005, 6))
+    check(real, ext_output.ext_fields(diag, "200506"))
+    fake = written["HCHO_199001.nc"]
+    check(fake, ext_output.ones_fields(diag["lat"], diag["lon"], 1990, 1))
+    assert np.all(fake["SF"] == 1.0)
