@@ -392,11 +392,14 @@ int oisat_pack_batch_indexed(const oisat_pack_item* items, int32_t n_items, int6
                              void* records, double* amf_masked, void* stream);
 /* The same, also writing the mask itself: px_bad[px0 + p] = 1 where NOT(qflag > flag_thresh)
  * (interpolator.py:126), [total pixels] device bytes, NULL = not wanted.  oisat_pair_alive
- * reads it. */
+ * reads it.  skip_masked_records != 0: the all-NaN records of masked pixels are not written
+ * (a fifth of the record traffic of a typical month) -- for callers that run the fused step
+ * over the live pairs only, which never read them. */
 int oisat_pack_batch_masked(const oisat_pack_item* items, int32_t n_items, int64_t total_blocks,
                             const int32_t* block_item, int32_t n_sat_lev, int32_t has_trop,
                             int32_t qflag_dtype, double flag_thresh, int32_t amf_dtype,
-                            void* records, double* amf_masked, uint8_t* px_bad, void* stream);
+                            void* records, double* amf_masked, uint8_t* px_bad,
+                            int32_t skip_masked_records, void* stream);
 
 /* derived model fields, once per month instead of once per granule
  * (amf_recal.py:151-152): logp = float32 log(p_mid) (:108), pcol = float32 partial

@@ -99,7 +99,7 @@ PROTOTYPES = {
     "oisat_pack_blocks": (i64, [i64]),
     "oisat_pack_batch": (C.c_int, [vp, i32, i64, i32, i32, i32, f64, i32, vp, vp, vp]),
     "oisat_pack_batch_indexed": (C.c_int, [vp, i32, i64, vp, i32, i32, i32, f64, i32, vp, vp, vp]),
-    "oisat_pack_batch_masked": (C.c_int, [vp, i32, i64, vp, i32, i32, i32, f64, i32, vp, vp, vp, vp]),
+    "oisat_pack_batch_masked": (C.c_int, [vp, i32, i64, vp, i32, i32, i32, f64, i32, vp, vp, vp, i32, vp]),
     "oisat_pair_alive": (C.c_int, [i64, i32, vp, vp, vp, vp, vp, vp, vp, f64, vp, vp, vp, vp]),
     "oisat_ctm_prepare": (C.c_int, [vp, vp, vp, i64, vp, vp, vp]),
     "oisat_fused_amf": (C.c_int, [C.POINTER(FusedArgs), vp]),

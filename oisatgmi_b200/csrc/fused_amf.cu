@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(256, 4)
 pack_batch_kernel(const oisat_pack_item* __restrict__ items, int n_items, int L, int has_trop,
                   int qflag_dtype, double thresh, int amf_dtype, __half* __restrict__ records,
                   double* __restrict__ amf_masked, int use_bulk,
-                  const int32_t* __restrict__ block_item, uint8_t* __restrict__ px_bad) {
+                  const int32_t* __restrict__ block_item, uint8_t* __restrict__ px_bad,
+                  int skip_masked) {
   extern __shared__ __align__(128) __half tile[];
   __shared__ unsigned char bad[kPackPixels];
   __shared__ __align__(8) unsigned long long mbar;
@@ -315,9 +316,11 @@ pack_batch_kernel(const oisat_pack_item* __restrict__ items, int n_items, int L,
     v.y = (uint32_t)e[2 * kstride] | ((uint32_t)e[3 * kstride] << 16);
     v.z = (uint32_t)e[4 * kstride] | ((uint32_t)e[5 * kstride] << 16);
     v.w = (uint32_t)e[6 * kstride] | ((uint32_t)e[7 * kstride] << 16);
-    // a masked pixel is a NaN vertex for EVERY field (interpolator.py:126-128,163)
+    // a masked pixel is a NaN vertex for EVERY field (interpolator.py:126-128,163); when the
+    // caller runs over the live pairs only (oisat_pair_alive) its record is never read and is
+    // not written at all
     if (bad[px]) v = make_uint4(nan2, nan2, nan2, nan2);
-    dst[c] = v;
+    if (!(skip_masked && bad[px])) dst[c] = v;
     px += dpx;
     q += dq;
     if (q >= nchunk) { q -= nchunk; ++px; }
@@ -595,15 +598,17 @@ extern "C" int oisat_pack_batch_indexed(const oisat_pack_item* items, int32_t n_
                                         double* amf_masked, void* stream) {
   return oisat_pack_batch_masked(items, n_items, total_blocks, block_item, n_sat_lev, has_trop,
                                  qflag_dtype, flag_thresh, amf_dtype, records, amf_masked, nullptr,
-                                 stream);
+                                 0, stream);
 }
 
 extern "C" int oisat_pack_batch_masked(const oisat_pack_item* items, int32_t n_items,
                                        int64_t total_blocks, const int32_t* block_item,
                                        int32_t n_sat_lev, int32_t has_trop, int32_t qflag_dtype,
                                        double flag_thresh, int32_t amf_dtype, void* records,
-                                       double* amf_masked, uint8_t* px_bad, void* stream) {
+                                       double* amf_masked, uint8_t* px_bad,
+                                       int32_t skip_masked_records, void* stream) {
   if (n_items <= 0 || total_blocks <= 0) return OISAT_OK;
+  OISAT_CHECK_ARG(!skip_masked_records || px_bad, "skipping masked records needs the mask output");
   OISAT_CHECK_ARG(items && records && amf_masked, "null pointer");
   OISAT_CHECK_ARG(amf_dtype == OISAT_F16 || amf_dtype == OISAT_F32 || amf_dtype == OISAT_F64,
                   "bad amf dtype");
@@ -620,7 +625,7 @@ extern "C" int oisat_pack_batch_masked(const oisat_pack_item* items, int32_t n_i
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pack_batch_kernel<<<(unsigned)total_blocks, 256, smem, (cudaStream_t)stream>>>(
       items, n_items, n_sat_lev, has_trop, qflag_dtype, flag_thresh, amf_dtype, (__half*)records,
-      amf_masked, use_bulk, block_item, px_bad);
+      amf_masked, use_bulk, block_item, px_bad, skip_masked_records);
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
 }

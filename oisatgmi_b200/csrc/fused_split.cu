@@ -575,12 +575,13 @@ struct TileSmem {   // static part
 // (the BASELINE products), 0 = read from the arguments: with constants the record and
 // tile geometry fold into immediates and the loops unroll (the generic build spends more
 // than half of its instructions outside the arithmetic).
-template <bool HAS_TROP, int H, int CL, int CS, int CN, int SW, int MINB, bool PACKED>
+template <bool HAS_TROP, int H, int CL, int CS, int CN, int SW, int MINB, bool PACKED, bool BULK = false>
 __global__ void __launch_bounds__(kTileThreads, MINB)
 fused_tile_kernel(const __grid_constant__ SplitParams P) {
   const oisat_fused_args& A = P.a;
   extern __shared__ __align__(16) unsigned char tsm[];
   __shared__ TileSmem sm;
+  __shared__ __align__(8) unsigned long long gather_bar;   // BULK: completion of a sweep's record copies
   const int lane = threadIdx.x & 31;
   const int gl = lane & 15;
   const int col = threadIdx.x >> 4;                                    // pair of the tile (gather phase)
@@ -601,6 +602,11 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
     sm.tab[i] = make_double2(g_log_table.r[i], g_log_table.neg_log_r[i]);
   }
   if (threadIdx.x < 16) sm.unsorted[threadIdx.x] = n_ctm >= 8 ? 0 : 1;
+  if (BULK && threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(&gather_bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   // identity of this thread in the vertical phase (pair p = gather lane, t = gather pair):
   // known now, so the model column's offset is loaded early and the column itself is
   // prefetched into L2 while the records are in flight
@@ -671,18 +677,39 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
         sm.gw[col * SW + gl] = wt;
       }
       __syncthreads();
-      if (active) {
-#pragma unroll
-        for (int e = 0; e < SW; ++e) {
-          if (e < nk) {
-            const uint32_t ck = sm.gcix[pp * SW + e] + (uint32_t)ch;
-            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + e * nchunk);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(records + ck)
-                         : "memory");
+      if constexpr (BULK) {
+        // One bulk asynchronous copy (TMA engine, cp.async.bulk) per (pair, entry): a record is
+        // nchunk * 16 contiguous bytes on both sides, so the 16 x nk records of the sweep are
+        // 16 x nk instructions in the whole block instead of 16 x nk x nchunk lane copies with
+        // their address arithmetic; completion is counted on an mbarrier.
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&gather_bar);
+        const uint32_t rec_bytes = (uint32_t)nchunk * 16u;
+        if (tid == 0)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                       ::"r"(bar), "r"(16u * (uint32_t)nk * rec_bytes) : "memory");
+        if (tid < 16 * SW) {
+          const int p2 = tid / SW, e2 = tid - p2 * SW;
+          if (e2 < nk) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stage + (p2 * sweep + e2) * nchunk);
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(dst), "l"(records + sm.gcix[p2 * SW + e2]), "r"(rec_bytes), "r"(bar) : "memory");
           }
         }
+      } else {
+        if (active) {
+#pragma unroll
+          for (int e = 0; e < SW; ++e) {
+            if (e < nk) {
+              const uint32_t ck = sm.gcix[pp * SW + e] + (uint32_t)ch;
+              const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + e * nchunk);
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(records + ck)
+                           : "memory");
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
       if (base == 0 && live) {
 #pragma unroll
         for (int i = 0; i < H; ++i) {
@@ -694,7 +721,18 @@ fused_tile_kernel(const __grid_constant__ SplitParams P) {
           }
         }
       }
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if constexpr (BULK) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&gather_bar);
+        const uint32_t parity = (uint32_t)((base / SW) & 1);
+        uint32_t done = 0;
+        while (!done)
+          asm volatile("{ .reg .pred p;\n\t"
+                       "  mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                       "  selp.b32 %0, 1, 0, p; }"
+                       : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
       if (active) {
 #pragma unroll
         for (int e = 0; e < SW; ++e) {
@@ -1414,7 +1452,8 @@ extern "C" int oisat_fused_amf_split(const oisat_fused_args* h_args, double* row
   return OISAT_OK;
 }
 
-template <bool HAS_TROP, int H, int CL, int CS, int CN, bool PACKED = false, int SW = 15, int MINB = 4>
+template <bool HAS_TROP, int H, int CL, int CS, int CN, bool PACKED = false, int SW = 15, int MINB = 4,
+          bool BULK = false>
 static int launch_tile(const SplitParams& P, cudaStream_t s) {
   const oisat_fused_args& a = P.a;
   const int sweep = 3 * a.nwin < SW ? 3 * a.nwin : SW;
@@ -1422,9 +1461,9 @@ static int launch_tile(const SplitParams& P, cudaStream_t s) {
   const size_t stage_bytes = (size_t)16 * sweep * P.nchunk * sizeof(uint4);
   const size_t vert_bytes = (size_t)(kSearchRows + a.n_sat_lev) * kXP * sizeof(double);
   const size_t smem = tile_bytes + (stage_bytes > vert_bytes ? stage_bytes : vert_bytes);
-  OISAT_CHECK_CUDA(cudaFuncSetAttribute(fused_tile_kernel<HAS_TROP, H, CL, CS, CN, SW, MINB, PACKED>,
+  OISAT_CHECK_CUDA(cudaFuncSetAttribute(fused_tile_kernel<HAS_TROP, H, CL, CS, CN, SW, MINB, PACKED, BULK>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fused_tile_kernel<HAS_TROP, H, CL, CS, CN, SW, MINB, PACKED>
+  fused_tile_kernel<HAS_TROP, H, CL, CS, CN, SW, MINB, PACKED, BULK>
       <<<(unsigned)ceil_div(P.a.n_pairs, 16), kTileThreads, smem, s>>>(P);
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
@@ -1488,6 +1527,10 @@ extern "C" int oisat_fused_amf_tile(const oisat_fused_args* h_args, void* stream
   const bool generic = gen && gen[0] == '1';
   const char* pk = getenv("OISAT_TILE_PACKED");   // "0": half-warp-per-pair gather lanes (A/B runs, tests)
   const bool packed = !(pk && pk[0] == '0');
+  // records fetched with one bulk asynchronous copy (TMA engine) per (pair, entry) -- the default
+  // for the packed builds; OISAT_TILE_BULK=0: 16-byte cp.async per lane (A/B runs, tests)
+  const char* bk = getenv("OISAT_TILE_BULK");
+  const bool bulk = (bk && bk[0] == '1') && (reinterpret_cast<uintptr_t>(a.records) & 15) == 0;
   // OISAT_TILE_WS=1 runs the warp-specialised persistent form (needs the per-pair tables and
   // records of at most 14 chunks).  Measured on the OMI HCHO month (profiles/r02_ws_probe.md):
   // 5.70 ms against 5.21 ms for the one-tile-per-block form -- each role alone needs ~4.3 ms
@@ -1513,10 +1556,13 @@ extern "C" int oisat_fused_amf_tile(const oisat_fused_args* h_args, void* stream
   }
   if (generic) {
   } else if (!a.has_trop && L == 47 && S == 12 && N == 72) {
+    if (packed && bulk) return launch_tile<false, 5, 47, 12, 72, true, 15, 4, true>(P, s);
     return packed ? launch_tile<false, 5, 47, 12, 72, true>(P, s) : launch_tile<false, 5, 47, 12, 72>(P, s);
   } else if (a.has_trop && L == 35 && S == 12 && N == 72) {
+    if (packed && bulk) return launch_tile<true, 5, 35, 12, 72, true, 15, 4, true>(P, s);
     return packed ? launch_tile<true, 5, 35, 12, 72, true>(P, s) : launch_tile<true, 5, 35, 12, 72>(P, s);
   } else if (a.has_trop && L == 34 && S == 90 && N == 72) {
+    if (packed && bulk) return launch_tile<true, 5, 34, 90, 72, true, 15, 4, true>(P, s);
     return packed ? launch_tile<true, 5, 34, 90, 72, true>(P, s) : launch_tile<true, 5, 34, 90, 72>(P, s);
   }
   const int half = ((N / 8) + 1) / 2;

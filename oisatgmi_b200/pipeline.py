@@ -445,7 +445,7 @@ class MonthPipeline:
             buf["pack_block_item"].data_ptr(), g0.nlev, int(g0.has_trop),
             _dev.dtype_code(g0.dev["qflag"]), self.flag_thresh, _dev.dtype_code(g0.dev["amf"]),
             buf["records"].data_ptr(), buf["amf_masked"].data_ptr(), buf["px_bad"].data_ptr(),
-            _dev.stream()))
+            int(self.fused_form == "tile"), _dev.stream()))
 
     def fused_args(self):
         host, dev = self.build_tables()

@@ -297,3 +297,21 @@ def test_warp_specialised_form_equals_one_tile_per_block_form(name, generic, mon
     # and a second run of the persistent kernel gives the same bits (no race between the roles)
     pipe_c, _ = run_pipeline(name)
     assert same_bits_where_defined(b, pipe_c._buf["staged"].cpu().numpy())
+
+
+@pytest.mark.parametrize("name", ["omi_hcho", "omi_no2", "tropomi_no2", "omi_no2_kinked"])
+def test_bulk_copy_gather_equals_lane_copy_gather(name, monkeypatch):
+    """Records fetched by one bulk asynchronous copy per (pair, entry) (TMA engine, the default
+    of the packed builds) or by 16-byte cp.async per lane (OISAT_TILE_BULK=0): same bytes in
+    shared memory, same arithmetic, identical staged bits (tropomi_no2: six sweeps, so the
+    mbarrier goes through six phases)."""
+    monkeypatch.setenv("OISAT_FUSED", "tile")
+    monkeypatch.setenv("OISAT_TILE_BULK", "0")
+    pipe_a, _ = run_pipeline(name)
+    a = pipe_a._buf["staged"].cpu().numpy()
+    monkeypatch.setenv("OISAT_TILE_BULK", "1")
+    monkeypatch.setenv("OISAT_GUARD", "1")
+    pipe_b, _ = run_pipeline(name)
+    assert pipe_b.check_guards()
+    b = pipe_b._buf["staged"].cpu().numpy()
+    assert a.size > 0 and same_bits_where_defined(a, b)
