@@ -513,6 +513,19 @@ int oisat_pair_tables(int64_t n_pairs, const int32_t* pair_granule, const int32_
                       int64_t n_cell, int64_t n_slots, int64_t* pair_record0,
                       uint32_t* pair_ctm_off, void* stream);
 
+/* ---- SSMIS precipitable water ------------------------------------
+ * oisat_reader_ssmis: reader.py:1292-1297 -- pwv = float32(src); > 250 -> NaN; * 0.3; >= 75 or
+ *   inf -> NaN; uncertainty = pwv * 0.05; all in float32.  src: uint8 / int32 / float.
+ * oisat_pwv_partial: pwv_cal.py:62,68 -- delta_p * q / g / 10000 in float32, n elements.
+ * oisat_pwv_column: pwv_cal.py:91-93 -- out[c] = nansum_k(partial[k][c] / 1000) accumulated in
+ *   the partial's dtype (float32 / float64) in layer order, NaN where sat_vcd[c] is NaN or inf. */
+int oisat_reader_ssmis(const void* src, int32_t dtype, int64_t n, float* pwv, float* uncertainty,
+                       void* stream);
+int oisat_pwv_partial(const float* delta_p, const float* profile, int64_t n, float* out,
+                      void* stream);
+int oisat_pwv_column(const void* partial, int32_t dtype, int32_t n_lev, int64_t n_cell,
+                     const double* sat_vcd, double* out, void* stream);
+
 /* ordered segmented reduction of the staged pair values into the accumulators:
  * for model cell c the pairs seg_pair[seg_start[c] .. seg_start[c+1]) are listed
  * in granule order, so the running sums equal numpy's sequential nanmean

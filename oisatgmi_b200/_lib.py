@@ -108,6 +108,9 @@ PROTOTYPES = {
     "oisat_fused_amf_tile": (C.c_int, [C.POINTER(FusedArgs), vp]),
     "oisat_segment_tables": (C.c_int, [vp, i64, i64, vp, vp, vp, vp]),
     "oisat_pair_tables": (C.c_int, [i64, vp, vp, vp, vp, i32, i64, i64, vp, vp, vp]),
+    "oisat_reader_ssmis": (C.c_int, [vp, i32, i64, vp, vp, vp]),
+    "oisat_pwv_partial": (C.c_int, [vp, vp, i64, vp, vp]),
+    "oisat_pwv_column": (C.c_int, [vp, i32, i32, i64, vp, vp, vp]),
     "oisat_accum_pairs": (C.c_int, [vp, i64, vp, vp, vp, i64, vp]),
 }
 

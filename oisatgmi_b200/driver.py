@@ -55,6 +55,11 @@ class oisatgmi(object):
     def recal_amf(self):
         self.reader_obj.sat_data = amf_recal(self.reader_obj.ctm_data, self.reader_obj.sat_data)
 
+    def cal_pwv(self):
+        from .pwv_cal import pwv_calculator
+        self.reader_obj.sat_data = pwv_calculator(self.reader_obj.ctm_data,
+                                                  self.reader_obj.sat_data)
+
     def conv_ak(self, sensor: str):
         if sensor == 'MOPITT':
             self.reader_obj.sat_data = ak_conv_mopitt(self.reader_obj.ctm_data,

@@ -270,3 +270,25 @@ def gosat_xch4(v, read_ak=True, device=False):
     return satellite_opt(xch4, time, [], np.empty((1)), lat, lon, [], [], v["xch4_uncertainty"],
                          1 - v["xch4_quality_flag"], p_mid, aks, [], [], [], [], np.empty((1)), ap,
                          np.empty((1)), np.empty((1)), xch4, pw, "GOSAT")
+
+
+def ssmis_wv(v, yyyymm, device=False):
+    """reader.py:1280-1297 (`ssmis_reader_wv` up to its interpolator call): `v` holds the
+    'latitude' / 'longitude' axes and the scaled 'atmosphere_water_vapor_content' map; `yyyymm`
+    is the month the reader parses from the file name."""
+    from .config import satellite_ssmis
+    _dev.require_cuda()
+    time = datetime.datetime(int(yyyymm[0:4]), int(yyyymm[4:6]), 1)
+    lat = np.asarray(v["latitude"]).astype("float32")
+    lon = np.asarray(v["longitude"]).astype("float32")
+    lon[lon > 180.0] = lon[lon > 180.0] - 360.0
+    lon, lat = np.meshgrid(lon, lat)
+    raw = np.asarray(v["atmosphere_water_vapor_content"])
+    src = _dev.to_device(np.ascontiguousarray(raw)) if raw.dtype == np.uint8 else _up(raw)
+    pwv = _dev.empty((src.numel(),), "float32")
+    unc = _dev.empty((src.numel(),), "float32")
+    _lib.check(_lib.lib().oisat_reader_ssmis(src.data_ptr(), _dev.dtype_code(src), src.numel(),
+                                             pwv.data_ptr(), unc.data_ptr(), _dev.stream()))
+    pwv, unc = pwv.reshape(lat.shape), unc.reshape(lat.shape)
+    pwv, unc = _finish([pwv, unc], device)
+    return satellite_ssmis(pwv, unc, time, lat, lon, False, [], "SSMI")

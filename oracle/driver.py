@@ -2,6 +2,7 @@
 `oisatgmi` class, the calls run/job.py:61-84 makes after `read_data`:
 
   recal_amf     /root/reference/oisatgmi/driver.py:36-39
+  cal_pwv       /root/reference/oisatgmi/driver.py:41-43
   conv_ak       /root/reference/oisatgmi/driver.py:45-51
   average       /root/reference/oisatgmi/driver.py:53-63   (O3: model column -> DU)
   bias_correct  /root/reference/oisatgmi/driver.py:65-106
@@ -26,6 +27,11 @@ class oisatgmi(object):
     def recal_amf(self):
         self.reader_obj.sat_data = _vert.amf_recal(self.reader_obj.ctm_data,
                                                    self.reader_obj.sat_data)
+
+    def cal_pwv(self):
+        from oracle import ssmis as _ssmis
+        self.reader_obj.sat_data = _ssmis.pwv_calculator(self.reader_obj.ctm_data,
+                                                         self.reader_obj.sat_data)
 
     def conv_ak(self, sensor):
         if sensor == "MOPITT":

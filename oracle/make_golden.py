@@ -71,6 +71,18 @@ def gosat_chain(ref):
                           cases.gosat_case()["granules"])
 
 
+def ssmis_chain(ref, fine):
+    import chains
+    store = chains.ssmis_chain(chains.reference_impl(), fine)[0]
+    v = cases.ssmis_case(fine)["vars"]
+    h = hashlib.sha256()
+    for k in sorted(v):
+        h.update(np.ascontiguousarray(v[k]).tobytes())
+    out = {"input_sha256": np.array(h.hexdigest())}
+    out.update(store)
+    return out
+
+
 def o3_chain(ref):
     import chains
     return _with_checksum(chains.o3_chain(chains.reference_impl())[0],
@@ -117,6 +129,8 @@ def main():
     jobs["mopitt_co"] = lambda: mopitt_chain(ref)
     jobs["gosat_xch4"] = lambda: gosat_chain(ref)
     jobs["omi_o3"] = lambda: o3_chain(ref)
+    jobs["ssmis_pwv"] = lambda: ssmis_chain(ref, False)
+    jobs["ssmis_pwv_fine"] = lambda: ssmis_chain(ref, True)
     for product in cases.READER_PRODUCTS:
         jobs["reader_" + product] = lambda p=product: reader_chain(ref, p)
     only = sys.argv[1:]

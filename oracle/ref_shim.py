@@ -93,5 +93,7 @@ def load_reference():
     ns.error_averager = av.error_averager
     ns.OI = importlib.import_module("oisatgmi.optimal_interpolation").OI
     ns.driver = importlib.import_module("oisatgmi.driver")
+    ns.interpolator_ssmis = importlib.import_module("oisatgmi.interpolator_ssmis").interpolator_ssmis
+    ns.pwv_calculator = importlib.import_module("oisatgmi.pwv_cal").pwv_calculator
     _loaded = ns
     return ns

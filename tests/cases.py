@@ -130,6 +130,38 @@ def o3_case():
                 flag_thresh=0.0, sensor="OMI", gas="O3")
 
 
+def ssmis_vars(seed=51, region=REGION):
+    """Variables of one monthly SSMIS map as ssmis_reader_wv reads them (reader.py:1285-1292):
+    0.25 degree axes (longitude 0..360) and the scaled-byte water-vapour map with its flag
+    values above 250 (land, ice, no data)."""
+    rng = np.random.default_rng(seed)
+    la0, la1, lo0, lo1 = region
+    lat = np.arange(la0 - 2.0, la1 + 2.0, 0.25) + 0.125
+    lon = (np.arange(lo0 - 2.0, lo1 + 2.0, 0.25) + 0.125) % 360.0
+    shape = (lat.size, lon.size)
+    wv = 60.0 + 90.0 * (synth._smooth2d(rng, shape, scale=3.0) + 0.5)
+    wv = np.clip(wv, 0.0, 249.0)
+    land = synth._coherent_mask(rng, shape, 0.3)
+    wv[~land] = rng.choice([251.0, 252.0, 253.0, 254.0, 255.0], size=int((~land).sum()))
+    wv[rng.uniform(size=shape) < 0.01] = 250.0          # 75.0 after scaling: rejected (>= 75)
+    return {"latitude": lat.astype(np.float64), "longitude": lon.astype(np.float64),
+            "atmosphere_water_vapor_content": wv.astype(np.uint8)}
+
+
+def ssmis_case(fine=False):
+    """SSMIS precipitable water against a water-vapour model field: the model coarser than the
+    0.25 degree working mesh (the reference's production setting) or finer (`fine`: the
+    interpolator leaves the map on the mesh and pwv_calculator resamples the model)."""
+    if fine:
+        c = synth.ctm_coordinates(REGION_FINE, dlat=0.125, dlon=0.125)
+        region = REGION_FINE
+    else:
+        c, region = coords(), REGION
+    model = [synth.make_ctm(61, c, ctmtype="ECCOH", averaged=False, gas_scale=2.0e3,
+                            date=datetime.datetime(2005, 6, 1))]
+    return dict(vars=ssmis_vars(region=region), yyyymm="200506", coords=c, ctm=model, grid_size=0.25)
+
+
 def reader_ns(sat_data, ctm_data=None):
     return types.SimpleNamespace(sat_data=sat_data, ctm_data=ctm_data)
 

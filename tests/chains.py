@@ -59,10 +59,12 @@ def month_tail(impl, store, sensor, gas, ctm, grids, per_granule, skip_aux=False
     d = impl.driver(ctm, grids)
     if sensor in ("MOPITT", "GOSAT"):
         d.conv_ak(sensor)
+    elif sensor == "SSMIS":
+        d.cal_pwv()
     else:
         d.recal_amf()
     grids = d.reader_obj.sat_data
-    tag = "ak" if sensor in ("MOPITT", "GOSAT") else "amf"
+    tag = {"MOPITT": "ak", "GOSAT": "ak", "SSMIS": "pwv"}.get(sensor, "amf")
     for i, r in enumerate(grids):
         put(store, "%s%d" % (tag, i), r, per_granule)
     d.average("2005-06-01", "2005-07-01", gasname=gas)
@@ -132,6 +134,20 @@ def o3_chain(impl):
     return store, grids
 
 
+def ssmis_chain(impl, fine=False):
+    """SSMIS water vapour (run/job.py:67-68): reader front-end -> interpolator_ssmis ->
+    pwv_calculator -> average -> oi, the month through the oisatgmi class."""
+    c = cases.ssmis_case(fine)
+    store = {}
+    r = impl.ssmis_wv({k: np.array(v) for k, v in c["vars"].items()}, c["yyyymm"])
+    put(store, "read", r, ["vcd", "uncertainty", "latitude_center", "longitude_center"])
+    g = impl.interpolator_ssmis(1, c["grid_size"], r, c["coords"])
+    assert g is not None and bool(g.ctm_upscaled_needed) == bool(fine)
+    put(store, "interp", g, ["vcd", "uncertainty", "latitude_center", "longitude_center"])
+    month_tail(impl, store, "SSMIS", "H2O", c["ctm"], [g], ["ctm_vcd"], skip_aux=True)
+    return store, [g]
+
+
 def _attached(d, ctm, grids):
     d.reader_obj = cases.reader_ns(grids, ctm)
     return d
@@ -139,11 +155,13 @@ def _attached(d, ctm, grids):
 
 def oracle_impl():
     import types
-    from oracle import averaging as oavg, driver as odriver, interp as ointerp, oi as ooi, vertical as overt
+    from oracle import (averaging as oavg, driver as odriver, interp as ointerp, oi as ooi,
+                        ssmis as ossmis, vertical as overt)
     return types.SimpleNamespace(
         interpolator=ointerp.interpolator, filler_gosatxch4=ointerp.filler_gosatxch4,
         amf_recal=overt.amf_recal, ak_conv_mopitt=overt.ak_conv_mopitt,
         ak_conv_gosat=overt.ak_conv_gosat, averaging=oavg.averaging, OI=ooi.OI, bias=ooi.BIAS,
+        ssmis_wv=ossmis.ssmis_wv, interpolator_ssmis=ossmis.interpolator_ssmis,
         driver=lambda ctm, grids: _attached(odriver.oisatgmi(), ctm, grids))
 
 
@@ -174,7 +192,7 @@ def reference_impl():
     class QuietDriver(ref.driver.oisatgmi):
         pass
 
-    for meth in ("recal_amf", "conv_ak", "average", "bias_correct", "oi"):
+    for meth in ("recal_amf", "conv_ak", "cal_pwv", "average", "bias_correct", "oi"):
         setattr(QuietDriver, meth, quiet(getattr(ref.driver.oisatgmi, meth)))
 
     return types.SimpleNamespace(
@@ -188,18 +206,41 @@ def reference_impl():
         averaging=quiet(ref.averaging), OI=quiet(ref.OI),
         bias={("TROPOMI", "NO2"): (0.32, 0.66), ("TROPOMI", "HCHO"): (0.90, 0.59),
               ("OMI", "NO2"): (0.32, 0.63), ("OMI", "HCHO"): (0.821, 0.79)},
+        ssmis_wv=_reference_ssmis_reader(ref, quiet),
+        interpolator_ssmis=quiet(lambda k, gs, g, c: ref.interpolator_ssmis(
+            k, gs, g if isinstance(g, ref.config.satellite_ssmis)
+            else config.convert(g, ref.config.satellite_ssmis), c)),
         driver=lambda models, grids: _attached(QuietDriver(), ctm(models), grids))
+
+
+def _reference_ssmis_reader(ref, quiet):
+    """ssmis_reader_wv (reader.py:1277-1305), unmodified, with its file access (`_read_nc`,
+    `_read_ssmi`) answered from the dictionary and the month in a file name it can parse."""
+    import sys
+
+    def run(v, yyyymm):
+        rd = sys.modules["oisatgmi.reader"]
+        saved = rd._read_nc, rd._read_ssmi
+        rd._read_nc = lambda fname, var: np.squeeze(np.array(v[var]))
+        rd._read_ssmi = lambda fname, var: np.squeeze(np.array(v[var]))
+        try:
+            return quiet(rd.ssmis_reader_wv)("dir/f17_%sv7.nc" % yyyymm, None)
+        finally:
+            rd._read_nc, rd._read_ssmi = saved
+    return run
 
 
 def cuda_impl():
     import types
     from oisatgmi_b200 import (ak_conv_gosat, ak_conv_mopitt, amf_recal, averaging, driver,
-                               filler_gosat, interpolator, optimal_interpolation)
+                               filler_gosat, interpolator, interpolator_ssmis,
+                               optimal_interpolation, reader_frontend)
     return types.SimpleNamespace(
         interpolator=interpolator.interpolator, filler_gosatxch4=filler_gosat.filler_gosatxch4,
         amf_recal=amf_recal.amf_recal, ak_conv_mopitt=ak_conv_mopitt.ak_conv_mopitt,
         ak_conv_gosat=ak_conv_gosat.ak_conv_gosat, averaging=averaging.averaging,
         OI=optimal_interpolation.OI, bias=driver.BIAS_CORRECTION,
+        ssmis_wv=reader_frontend.ssmis_wv, interpolator_ssmis=interpolator_ssmis.interpolator_ssmis,
         driver=lambda ctm, grids: _attached(driver.oisatgmi(), ctm, grids))
 
 

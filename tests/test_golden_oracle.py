@@ -11,7 +11,7 @@ from util import assert_field
 # fields that pass through numpy's float32 log (amf_recal.py:108) can move in the
 # last float32 ulp between CPUs with different SIMD dispatch; everything else is
 # float64 arithmetic in a fixed order
-LOOSE = ("amf", "ak", "avg.", "oi")
+LOOSE = ("amf", "ak", "pwv", "avg.", "oi")
 
 
 def _compare(store, gold):
@@ -41,6 +41,12 @@ def test_gosat_chain_matches_reference_fixture(golden):
 def test_o3_chain_matches_reference_fixture(golden):
     store, _ = chains.o3_chain(chains.oracle_impl())
     _compare(store, golden("omi_o3"))
+
+
+@pytest.mark.parametrize("fine", [False, True])
+def test_ssmis_chain_matches_reference_fixture(fine, golden):
+    store, _ = chains.ssmis_chain(chains.oracle_impl(), fine)
+    _compare(store, golden("ssmis_pwv_fine" if fine else "ssmis_pwv"))
 
 
 def test_inputs_did_not_drift(golden):

@@ -67,6 +67,20 @@ def test_o3_chain_vs_oracle_and_golden(golden):
     _compare(got, golden("omi_o3"), tight=("interp",))
 
 
+@pytest.mark.parametrize("fine", [False, True])
+def test_ssmis_chain_vs_oracle_and_golden(fine, golden):
+    """SSMIS water vapour: reader front-end (bit for bit), interpolator_ssmis (two Delaunay-linear
+    steps with the box mean between them), pwv_calculator (model precipitable water, on the
+    model grid or resampled to the mesh), then the month through the oisatgmi class."""
+    got, _ = chains.ssmis_chain(chains.cuda_impl(), fine)
+    want, _ = chains.ssmis_chain(chains.oracle_impl(), fine)
+    for k in ("read.vcd", "read.uncertainty", "read.latitude_center", "read.longitude_center"):
+        assert got[k].dtype == want[k].dtype and np.array_equal(got[k], want[k], equal_nan=True), k
+    assert got["pwv0.ctm_vcd"].dtype == want["pwv0.ctm_vcd"].dtype
+    print("ssmis", fine, _compare(got, want, tight=("interp", "read")))
+    _compare(got, golden("ssmis_pwv_fine" if fine else "ssmis_pwv"), tight=("interp", "read"))
+
+
 def test_distance_predicate_is_bit_exact():
     """K0 against scipy's cKDTree distances, including nodes that sit within one
     ulp of the threshold."""

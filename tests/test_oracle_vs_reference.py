@@ -195,3 +195,9 @@ def test_ext_fields_are_bit_identical_to_convert2EXT(tmp_path, monkeypatch):
     fake = written["HCHO_199001.nc"]
     check(fake, ext_output.ones_fields(diag["lat"], diag["lon"], 1990, 1))
     assert np.all(fake["SF"] == 1.0)
+
+
+@pytest.mark.parametrize("fine", [False, True])
+def test_ssmis_chain_is_bit_identical_to_reference(fine):
+    _same(chains.ssmis_chain(chains.oracle_impl(), fine)[0],
+          chains.ssmis_chain(reference_impl(), fine)[0])
