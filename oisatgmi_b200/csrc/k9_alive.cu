@@ -26,7 +26,7 @@ namespace oisat {
 constexpr int kAliveThreads = 256;
 
 __global__ void __launch_bounds__(kAliveThreads)
-pair_alive_kernel(int64_t n_pairs, int S, const int32_t* __restrict__ vert,
+pair_alive_kernel(int64_t n_pairs, int S, int vec, const int32_t* __restrict__ vert,
                   const double* __restrict__ w, const int64_t* __restrict__ pair_record0,
                   const int32_t* __restrict__ pair_granule, const int64_t* __restrict__ gran_px0,
                   const uint8_t* __restrict__ px_bad, const double* __restrict__ amf_masked,
@@ -36,7 +36,43 @@ pair_alive_kernel(int64_t n_pairs, int S, const int32_t* __restrict__ vert,
   const bool mine = pair < n_pairs;
   bool alive = mine;
   double old_amf = 0.0;
-  if (mine) {
+  if (mine && vec) {   // S == 12, 16-byte aligned tables
+    // the 2 x 2 window of the OMI products: the whole stencil of a pair is three 16-byte loads
+    // of vertices and six of weights, all issued before the first dependent mask byte is needed
+    const int64_t px0 = pair_record0 ? pair_record0[pair] : gran_px0[pair_granule[pair]];
+    const int4* v4 = reinterpret_cast<const int4*>(vert + pair * 12);
+    const int4 va = v4[0], vb = v4[1], vc = v4[2];
+    const int32_t v[12] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, vc.x, vc.y, vc.z, vc.w};
+    uint8_t bad[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) bad[e] = px_bad[px0 + v[e]];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) alive = alive && (bad[e] == 0);
+    if (alive) {
+      const double2* w2 = reinterpret_cast<const double2*>(w + pair * 12);
+      double wt[12], am[12];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) {
+        const double2 t = w2[e];
+        wt[2 * e] = t.x;
+        wt[2 * e + 1] = t.y;
+      }
+#pragma unroll
+      for (int e = 0; e < 12; ++e) am[e] = amf_masked[px0 + v[e]];
+      double z[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) z[e] = e < 12 ? wt[e] * am[e] : 0.0;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < o; ++i) z[i] = z[i] + z[i + o];
+      old_amf = z[0];
+      staged[4 * n_pairs + pair] = old_amf * box_weight;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 5; ++q) staged[q * n_pairs + pair] = qnan();
+    }
+  } else if (mine) {
     const int64_t px0 = pair_record0 ? pair_record0[pair] : gran_px0[pair_granule[pair]];
     const int32_t* v = vert + pair * S;
     const double* wt = w + pair * S;
@@ -101,7 +137,9 @@ extern "C" int oisat_pair_alive(int64_t n_pairs, int32_t nwin, const int32_t* ve
   cudaStream_t s = (cudaStream_t)stream;
   OISAT_CHECK_CUDA(cudaMemsetAsync(n_alive, 0, sizeof(int64_t), s));
   pair_alive_kernel<<<(unsigned)ceil_div(n_pairs, kAliveThreads), kAliveThreads, 0, s>>>(
-      n_pairs, 3 * nwin, vert, w, pair_record0, pair_granule, gran_px0, px_bad, amf_masked,
+      n_pairs, 3 * nwin,
+      (3 * nwin == 12 && ((reinterpret_cast<uintptr_t>(vert) | reinterpret_cast<uintptr_t>(w)) & 15) == 0) ? 1 : 0,
+      vert, w, pair_record0, pair_granule, gran_px0, px_bad, amf_masked,
       box_weight, staged, alive_pairs, reinterpret_cast<unsigned long long*>(n_alive));
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
