@@ -44,6 +44,8 @@ FLAG_THRESH = 0.0
 PRODUCT = "OMI_HCHO"
 N_LEV = 47
 
+TRAFFIC_FILE = "r02_traffic.json"     # ncu --set full capture of this round's kernels (tools/make_profiles.py)
+
 # --config: the default (and the headline) is BASELINE configs[1]; tropomi_no2 is configs[4]
 # (TROPOMI-scale NO2, days sharded over the ranks), for the scaling evidence under profiles/
 WORKLOADS = {
@@ -372,7 +374,9 @@ def main():
     # linearly from the captured launch's pixel count to this launch's
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if args.config != "omi_hcho":
+            raise KeyError("the capture is of the OMI HCHO kernels")
+        tr = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)))
         want = "fused_tile_kernel" if pipe.fused_form == "tile" else "rows_kernel"
         hit = [v for k, v in tr["kernels"].items() if want in k]
         if hit:
@@ -389,8 +393,8 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else
                                "fallback 6650 GB/s (of fallback)",
                 "traffic": traffic,
-                "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes_read+write, 120-granule "
-                                  "launch, scaled by pixel count)" if traffic else None,
+                "traffic_source": "profiles/%s (ncu dram__bytes_read+write, 120-granule "
+                                  "launch, scaled by pixel count)" % TRAFFIC_FILE if traffic else None,
                 "algorithmic_bytes_per_launch": fused_bytes,
                 "kernel_ms": fused_ms,
                 "pipeline": {"bytes_per_px": pipe_bytes_px,

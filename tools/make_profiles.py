@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Regenerate profiles/r01_* from the captures a gpurun call brought back:
+"""Regenerate profiles/<round>_* from the captures a gpurun call brought back:
 
-    python tools/make_profiles.py <launches.csv> <full.ncu-rep> <bench_n1.json>
+    python tools/make_profiles.py <launches.csv> <full.ncu-rep> <bench_n1.json> [round, default r02]
 
   launches.csv    ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv
                   of `python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline`
@@ -19,7 +19,7 @@ import sys
 
 HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PROF = os.path.join(HERE, "profiles")
-STEP = ["ctm_prepare_kernel", "pack_batch_kernel", "fused_tile_kernel", "gather_rows_kernel", "vertical_rows_kernel",
+STEP = ["ctm_prepare_kernel", "pack_batch_kernel", "pair_alive_kernel", "fused_tile_kernel", "fused_ws_kernel", "gather_rows_kernel", "vertical_rows_kernel",
         "accum_pairs_kernel", "accum_finalize_kernel", "oi_prepare_kernel", "oi_sweep_leaf_kernel",
         "oi_sweep_combine_kernel", "oi_apply_kernel"]
 
@@ -30,8 +30,9 @@ def short(k):
 
 def main():
     launches, rep, bench_path = sys.argv[1:4]
-    shutil.copy(launches, os.path.join(PROF, "r01_launches.csv"))
-    shutil.copy(bench_path, os.path.join(PROF, "r01_bench_n1.json"))
+    RND = sys.argv[4] if len(sys.argv) > 4 else "r02"
+    shutil.copy(launches, os.path.join(PROF, RND + "_launches.csv"))
+    shutil.copy(bench_path, os.path.join(PROF, RND + "_bench_n1.json"))
     bench = json.load(open(bench_path))
     rows = [r for r in csv.reader(open(launches)) if len(r) > 10]
     h = rows[0]
@@ -44,7 +45,7 @@ def main():
     in_step = {k: a for k, a in agg.items() if any(s in k for s in STEP)}
     n_steps = max(a[0] for a in in_step.values())
     tot = sum(a[1] for a in in_step.values())
-    out = ["# r01 launch list: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400` of",
+    out = ["# " + RND + " launch list: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400` of",
            "# `python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline` (435 OMI HCHO granules, "
            "42.9 M px, 7.36 M pairs per step;",
            "# %d steps captured = 1 warm-up + 2 timed; the 15 plan-building launches per kernel belong to "
@@ -59,26 +60,26 @@ def main():
     out += ["", "Set-up (geometry plans of the 15 distinct orbits, once per run; inside `e2e`, not inside "
             "`value`):", "", "| kernel | launches | total ms | ms per granule |", "|---|---|---|---|"]
     for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
-        if k in in_step or a[0] % 15:
+        if k in in_step or a[0] % 15 or a[0] == 0:
             continue
         out.append("| `%s` | %d | %.3f | %.3f |" % (short(k), a[0], a[1], a[1] / a[0]))
     ph = bench["roofline"]["phase_ms"]
     s_ph = sum(ph.values())
     pack = sum(a[1] for k, a in in_step.items() if "pack" in k)
     fused = sum(a[1] for k, a in in_step.items() if "rows_kernel" in k or "fused_tile" in k)
-    out += ["", "bench.py CUDA-event phases of the same workload without ncu (`profiles/r01_bench_n1.json`): "
+    out += ["", "bench.py CUDA-event phases of the same workload without ncu (`profiles/" + RND + "_bench_n1.json`): "
             + ", ".join("%s %.2f ms" % kv for kv in ph.items()) + " (step %.2f ms)." % bench["ms_per_step"],
             "Shares agree: pack %.0f %% (events) vs %.0f %% (ncu), fused step %.0f %% vs %.0f %%."
             % (100 * ph["pack"] / s_ph, 100 * pack / tot, 100 * ph["fused"] / s_ph, 100 * fused / tot)]
-    open(os.path.join(PROF, "r01_launches_summary.md"), "w").write("\n".join(out) + "\n")
+    open(os.path.join(PROF, RND + "_launches_summary.md"), "w").write("\n".join(out) + "\n")
 
-    header = ("# r01 (final code of the round) ncu --set full --clock-control none --import-source on; "
+    header = ("# " + RND + " (final code of the round) ncu --set full --clock-control none --import-source on; "
               "cold-cache, serialised replays -- not bench numbers\n# command: python bench.py --steps 1 "
               "--warmup 1 --days 8 --no-e2e --no-cpu-baseline   (120 OMI HCHO granules, 11.8 M px, 2.03 M "
               "pairs per launch)")
     md = subprocess.run([sys.executable, os.path.join(HERE, "tools", "ncu_summary.py"), rep, header],
                         capture_output=True, text=True).stdout
-    open(os.path.join(PROF, "r01_ncu_summary.md"), "w").write(md)
+    open(os.path.join(PROF, RND + "_ncu_summary.md"), "w").write(md)
 
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(raw.splitlines()))
@@ -93,9 +94,9 @@ def main():
             "duration_ms": float(d[hh.index("gpu__time_duration.sum")])}
     json.dump({"command": "python bench.py --steps 1 --warmup 1 --days 8 --no-e2e --no-cpu-baseline",
                "n_px": 120 * 98640, "kernels": kernels,
-               "source": "profiles/r01_ncu_summary.md (ncu --set full, one launch each)"},
-              open(os.path.join(PROF, "r01_traffic.json"), "w"), indent=1)
-    print(open(os.path.join(PROF, "r01_launches_summary.md")).read())
+               "source": "profiles/" + RND + "_ncu_summary.md (ncu --set full, one launch each)"},
+              open(os.path.join(PROF, RND + "_traffic.json"), "w"), indent=1)
+    print(open(os.path.join(PROF, RND + "_launches_summary.md")).read())
 
 
 if __name__ == "__main__":
