@@ -120,6 +120,64 @@ pair_alive_kernel(int64_t n_pairs, int S, int vec, const int32_t* __restrict__ v
   }
 }
 
+// Wide stencils (TROPOMI: 90 entries): a half warp per pair, lane = entry of a sweep of 15 --
+// the gather kernels' own layout, butterfly included -- so that the 90 dependent gathers of a
+// pair are six rounds of 15 parallel ones instead of 90 in a row in one thread.
+__global__ void __launch_bounds__(kAliveThreads)
+pair_alive_hw_kernel(int64_t n_pairs, int S, const int32_t* __restrict__ vert,
+                     const double* __restrict__ w, const int64_t* __restrict__ pair_record0,
+                     const int32_t* __restrict__ pair_granule, const int64_t* __restrict__ gran_px0,
+                     const uint8_t* __restrict__ px_bad, const double* __restrict__ amf_masked,
+                     double box_weight, double* __restrict__ staged,
+                     int32_t* __restrict__ alive_pairs, unsigned long long* __restrict__ n_alive) {
+  const int gl = threadIdx.x & 15, slot = threadIdx.x >> 4;
+  const int64_t pair_raw = (int64_t)blockIdx.x * (kAliveThreads / 16) + slot;
+  const bool mine = pair_raw < n_pairs;
+  const int64_t pair = mine ? pair_raw : n_pairs - 1;
+  const int64_t px0 = pair_record0 ? pair_record0[pair] : gran_px0[pair_granule[pair]];
+  const unsigned half_mask = 0xffffu << (threadIdx.x & 16);
+  bool any_bad = false;
+  double acc_amf = 0.0;
+  for (int base = 0; base < S; base += 15) {
+    const int nk = (S - base) < 15 ? (S - base) : 15;
+    double za = 0.0;
+    bool bad = false;
+    if (gl < nk) {
+      const int32_t v = vert[pair * S + base + gl];
+      bad = px_bad[px0 + v] != 0;
+      za = w[pair * S + base + gl] * amf_masked[px0 + v];
+    }
+    any_bad = any_bad || (__ballot_sync(0xffffffffu, bad) & half_mask) != 0;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) za += __shfl_xor_sync(0xffffffffu, za, o, 16);
+    acc_amf += za;
+  }
+  const bool alive = mine && !any_bad;
+  if (mine && gl == 0) {
+    if (alive) {
+      staged[4 * n_pairs + pair] = acc_amf * box_weight;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 5; ++q) staged[q * n_pairs + pair] = qnan();
+    }
+  }
+  __shared__ int flag[kAliveThreads / 16];
+  __shared__ unsigned long long block_base;
+  if (gl == 0) flag[slot] = alive ? 1 : 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int i = 0; i < kAliveThreads / 16; ++i) {
+      const int c = flag[i];
+      flag[i] = tot;
+      tot += c;
+    }
+    block_base = tot ? atomicAdd(n_alive, (unsigned long long)tot) : 0ull;
+  }
+  __syncthreads();
+  if (alive && gl == 0) alive_pairs[block_base + flag[slot]] = (int32_t)pair;
+}
+
 }  // namespace oisat
 
 using namespace oisat;
@@ -136,6 +194,13 @@ extern "C" int oisat_pair_alive(int64_t n_pairs, int32_t nwin, const int32_t* ve
   OISAT_CHECK_ARG(nwin >= 1 && n_pairs < ((int64_t)1 << 31), "bad stencil / too many pairs");
   cudaStream_t s = (cudaStream_t)stream;
   OISAT_CHECK_CUDA(cudaMemsetAsync(n_alive, 0, sizeof(int64_t), s));
+  if (3 * nwin > 15) {
+    pair_alive_hw_kernel<<<(unsigned)ceil_div(n_pairs, kAliveThreads / 16), kAliveThreads, 0, s>>>(
+        n_pairs, 3 * nwin, vert, w, pair_record0, pair_granule, gran_px0, px_bad, amf_masked,
+        box_weight, staged, alive_pairs, reinterpret_cast<unsigned long long*>(n_alive));
+    OISAT_CHECK_LAUNCH();
+    return OISAT_OK;
+  }
   pair_alive_kernel<<<(unsigned)ceil_div(n_pairs, kAliveThreads), kAliveThreads, 0, s>>>(
       n_pairs, 3 * nwin,
       (3 * nwin == 12 && ((reinterpret_cast<uintptr_t>(vert) | reinterpret_cast<uintptr_t>(w)) & 15) == 0) ? 1 : 0,

@@ -201,3 +201,30 @@ def test_ext_fields_are_bit_identical_to_convert2EXT(tmp_path, monkeypatch):
 def test_ssmis_chain_is_bit_identical_to_reference(fine):
     _same(chains.ssmis_chain(chains.oracle_impl(), fine)[0],
           chains.ssmis_chain(reference_impl(), fine)[0])
+
+
+def test_drop_in_signatures_match_the_reference():
+    """The switch INTEGRATION.md section 1 describes rebinds the reference's imports to the
+    drop-in modules: every replaced callable must take the same parameters (names, order,
+    defaults) as the one it replaces, and the `oisatgmi` class the same methods."""
+    import importlib
+    import inspect
+    ref_shim.load_reference()
+    pairs = [("interpolator", "interpolator"), ("interpolator", "_upscaler"),
+             ("filler_gosat", "filler_gosatxch4"), ("amf_recal", "amf_recal"),
+             ("ak_conv_mopitt", "ak_conv_mopitt"), ("ak_conv_gosat", "ak_conv_gosat"),
+             ("averaging", "averaging"), ("optimal_interpolation", "OI"),
+             ("interpolator_ssmis", "interpolator_ssmis"), ("pwv_cal", "pwv_calculator")]
+    for mod, name in pairs:
+        ref = getattr(importlib.import_module("oisatgmi." + mod), name)
+        ours = getattr(importlib.import_module("oisatgmi_b200." + mod), name)
+        a, b = inspect.signature(ref), inspect.signature(ours)
+        assert [(p.name, p.default) for p in a.parameters.values()] == \
+               [(p.name, p.default) for p in b.parameters.values()], (mod, name, str(a), str(b))
+    ref_cls = importlib.import_module("oisatgmi.driver").oisatgmi
+    our_cls = importlib.import_module("oisatgmi_b200.driver").oisatgmi
+    for meth in ("read_data", "recal_amf", "cal_pwv", "conv_ak", "average", "bias_correct", "oi",
+                 "write_to_nc"):
+        a, b = inspect.signature(getattr(ref_cls, meth)), inspect.signature(getattr(our_cls, meth))
+        assert [(p.name, p.default) for p in a.parameters.values()] == \
+               [(p.name, p.default) for p in b.parameters.values()], (meth, str(a), str(b))

@@ -32,7 +32,8 @@ def main():
     launches, rep, bench_path = sys.argv[1:4]
     RND = sys.argv[4] if len(sys.argv) > 4 else "r02"
     shutil.copy(launches, os.path.join(PROF, RND + "_launches.csv"))
-    shutil.copy(bench_path, os.path.join(PROF, RND + "_bench_n1.json"))
+    if os.path.abspath(bench_path) != os.path.join(PROF, RND + "_bench_n1.json"):
+        shutil.copy(bench_path, os.path.join(PROF, RND + "_bench_n1.json"))
     bench = json.load(open(bench_path))
     rows = [r for r in csv.reader(open(launches)) if len(r) > 10]
     h = rows[0]

@@ -24,6 +24,9 @@ METRICS = [
     ("blocks/SM limit: shared memory", "launch__occupancy_limit_shared_mem"),
     ("warp instructions", "smsp__inst_executed.sum"),
     ("fp64 pipe %", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+    ("LSU data pipe % (wavefronts)", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+    ("shared-memory wavefronts", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
+    ("shared-memory bank conflicts", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
     ("L1 hit %", "l1tex__t_sector_hit_rate.pct"),
     ("L2 hit %", "lts__t_sector_hit_rate.pct"),
     ("stall samples: long scoreboard", "smsp__pcsamp_warps_issue_stalled_long_scoreboard"),
