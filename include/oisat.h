@@ -298,6 +298,11 @@ int oisat_grid_resample(const void* src, const void* src2, int32_t src_op, int32
  * bit.  Any of the five inputs may be NULL (treated as all-NaN). */
 int oisat_accum_add(double* acc, int64_t n_cell, const double* vcd, const double* sigma,
                     const double* ctm_vcd, const double* aux1, const double* aux2, void* stream);
+/* The same with the second field already squared (sigma^2 evaluated by the caller in the
+ * uncertainty array's own dtype, as numpy does for float16 / float32 grids, averaging.py:101). */
+int oisat_accum_add_variance(double* acc, int64_t n_cell, const double* vcd,
+                             const double* variance, const double* ctm_vcd, const double* aux1,
+                             const double* aux2, void* stream);
 
 /* means and the error sqrt(sum sigma^2 / n^2); outputs may alias nothing in acc */
 int oisat_accum_finalize(const double* acc, int64_t n_cell, double* sat_vcd, double* sat_err,

@@ -86,6 +86,7 @@ PROTOTYPES = {
     "oisat_grid_resample": (C.c_int, [vp, vp, i32, i32, i32, i64, i64, i32, i32, f64, vp, vp, i64,
                                       vp, i64, vp]),
     "oisat_accum_add": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp]),
+    "oisat_accum_add_variance": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp]),
     "oisat_accum_finalize": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp]),
     "oisat_oi_prepare": (C.c_int, [vp, vp, vp, i64, f64, f64, f64, vp, vp, vp]),
     "oisat_oi_sweep_workspace": (i64, [i64, i32]),

@@ -31,12 +31,12 @@ class MonthAccumulator:
         self.n_cell = int(n_cell)
         self.acc = _dev.zeros((10, self.n_cell))
 
-    def add(self, vcd, sigma, ctm_vcd, aux1, aux2):
+    def add(self, vcd, sigma, ctm_vcd, aux1, aux2, sigma_is_variance=False):
         """Arguments: device float64 tensors of n_cell elements, or None."""
         L = _lib.lib()
-        _lib.check(L.oisat_accum_add(self.acc.data_ptr(), self.n_cell, _dev.ptr(vcd),
-                                     _dev.ptr(sigma), _dev.ptr(ctm_vcd), _dev.ptr(aux1),
-                                     _dev.ptr(aux2), _dev.stream()))
+        fn = L.oisat_accum_add_variance if sigma_is_variance else L.oisat_accum_add
+        _lib.check(fn(self.acc.data_ptr(), self.n_cell, _dev.ptr(vcd), _dev.ptr(sigma),
+                      _dev.ptr(ctm_vcd), _dev.ptr(aux1), _dev.ptr(aux2), _dev.stream()))
 
     def finalize(self):
         L = _lib.lib()
@@ -93,9 +93,15 @@ def averaging(startdate: str, enddate: str, reader_obj):
                 a1, a2 = g.x_col, g.ctm_xcol
             else:
                 a1 = a2 = None
-            acc.add(_grid_or_none(g.vcd, n_cell), _grid_or_none(g.uncertainty, n_cell),
+            unc = np.asarray(g.uncertainty)
+            narrow = unc.dtype in (np.float16, np.float32)
+            if narrow:
+                # averaging.py:101 squares the stacked uncertainties in THEIR dtype
+                with np.errstate(over="ignore"):
+                    unc = unc ** 2
+            acc.add(_grid_or_none(g.vcd, n_cell), _grid_or_none(unc, n_cell),
                     _grid_or_none(g.ctm_vcd, n_cell), _grid_or_none(a1, n_cell),
-                    _grid_or_none(a2, n_cell))
+                    _grid_or_none(a2, n_cell), sigma_is_variance=narrow)
         outs = [_dev.to_host(o).reshape(ny, nx) for o in acc.finalize()]
         mi, yi = month - min(months), year - min(years)
         sat_vcd[:, :, mi, yi], sat_err[:, :, mi, yi], ctm_vcd[:, :, mi, yi] = outs[0], outs[1], outs[2]

@@ -20,7 +20,8 @@ __device__ __forceinline__ void add_value(double* sum, double* cnt, double v) {
 __global__ void __launch_bounds__(256)
 accum_add_kernel(double* __restrict__ acc, int64_t n, const double* __restrict__ vcd,
                  const double* __restrict__ sigma, const double* __restrict__ ctm_vcd,
-                 const double* __restrict__ aux1, const double* __restrict__ aux2) {
+                 const double* __restrict__ aux1, const double* __restrict__ aux2,
+                 int sigma_is_variance) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
   if (vcd) {
@@ -30,7 +31,9 @@ accum_add_kernel(double* __restrict__ acc, int64_t n, const double* __restrict__
   }
   if (sigma) {
     const double s = sigma[c];
-    double v = __dmul_rn(s, s);  // averaging.py:101  sat_chosen_error**2
+    // averaging.py:101 sat_chosen_error**2 -- squared here in float64, or handed over already
+    // squared in the array's own dtype when that is narrower (numpy squares in the native dtype)
+    double v = sigma_is_variance ? s : __dmul_rn(s, s);
     if (isinf(v)) v = qnan();    // averaging.py:19
     add_value(&acc[1 * n + c], &acc[6 * n + c], v);
   }
@@ -96,7 +99,18 @@ extern "C" int oisat_accum_add(double* acc, int64_t n_cell, const double* vcd,
   OISAT_CHECK_ARG(acc && n_cell >= 0, "bad accumulator");
   if (n_cell == 0) return OISAT_OK;
   accum_add_kernel<<<(unsigned)ceil_div(n_cell, 256), 256, 0, (cudaStream_t)stream>>>(
-      acc, n_cell, vcd, sigma, ctm_vcd, aux1, aux2);
+      acc, n_cell, vcd, sigma, ctm_vcd, aux1, aux2, 0);
+  OISAT_CHECK_LAUNCH();
+  return OISAT_OK;
+}
+
+extern "C" int oisat_accum_add_variance(double* acc, int64_t n_cell, const double* vcd,
+                                        const double* variance, const double* ctm_vcd,
+                                        const double* aux1, const double* aux2, void* stream) {
+  OISAT_CHECK_ARG(acc && n_cell >= 0, "bad accumulator");
+  if (n_cell == 0) return OISAT_OK;
+  accum_add_kernel<<<(unsigned)ceil_div(n_cell, 256), 256, 0, (cudaStream_t)stream>>>(
+      acc, n_cell, vcd, variance, ctm_vcd, aux1, aux2, 1);
   OISAT_CHECK_LAUNCH();
   return OISAT_OK;
 }

@@ -192,6 +192,28 @@ def test_accumulator_matches_numpy_nanmean_bit_for_bit():
     assert_field(got[1], want_err, "sat_err", rtol=1e-14)   # pairwise vs sequential sum (A.6)
 
 
+def test_averaging_squares_narrow_uncertainties_in_their_own_dtype():
+    """averaging.py:101 squares the stacked uncertainty grids in THEIR dtype: a float32 (or
+    float16) grid is squared in float32 (float16), not in float64.  The drop-in against the
+    oracle on grids whose uncertainty is float32."""
+    from oisatgmi_b200 import averaging as cavg
+    from oracle import averaging as oavg
+    _, grids = chains.amf_chain(chains.oracle_impl(), "omi_no2", stop_after="amf")
+    for g in grids:
+        g.uncertainty = np.asarray(g.uncertainty).astype(np.float32)
+    want = oavg.averaging("2005-06-01", "2005-07-01", cases.reader_ns(cases.clone(grids)))
+    got = cavg.averaging("2005-06-01", "2005-07-01", cases.reader_ns(cases.clone(grids)))
+    for k, name in enumerate(["sat_vcd", "sat_err", "ctm_vcd", "aux1", "aux2"]):
+        assert_field(got[k], want[k], name, rtol=1e-14)
+    # squaring in float64 instead would be off by ~1e-8 relative: make sure that is not what runs
+    wide = [cases.clone(g) for g in grids]
+    for g in wide:
+        g.uncertainty = np.asarray(g.uncertainty).astype(np.float64)
+    other = oavg.averaging("2005-06-01", "2005-07-01", cases.reader_ns(wide))
+    f = np.isfinite(want[1])
+    assert np.max(np.abs(other[1][f] - want[1][f]) / want[1][f]) > 1e-10
+
+
 def test_constant_field_and_unit_weights_properties():
     """Known answers: a constant field grids to the same constant; SW == 1 gives
     AMF == 1 up to the float32 rounding of the reference's column sum
