@@ -2,7 +2,7 @@
 """Measurement of the widened rows at BASELINE sizes, the CPU
 restatement timed beside them.  One JSON line per row on stdout:
 
-    python tests/bench_rows.py > profiles/r01_rows.jsonl
+    python tests/bench_rows.py > profiles/rNN_rows.jsonl
 
 (It lives under tests/ because it runs the oracle next to the kernels; only tests/,
 smoke() and bench.py's CPU legs may do that.)
@@ -178,9 +178,88 @@ def row_output():
                 cpu_cells_per_s=n / cpu_s, cpu_s=cpu_s, cpu_kind="port (oracle/output.py, numpy, 1 core)")
 
 
+def row_reader_mopitt():
+    """8f-1 (round 2): MOPITT CO L3 front-end at the product's size (360 x 180 x 9 levels, 10 AK
+    rows): oisat_reader_clean / _mopitt_xcol through reader_frontend.mopitt_co (uploads of the
+    file variables and the device -> host copy of the record included: it is the drop-in call)."""
+    import cases
+    from oracle import reader as oreader
+    small = cases.reader_vars("mopitt_co")
+    rng = np.random.default_rng(2)
+    nlon, nlat = 360, 180
+    v = {}
+    for k, a in small.items():
+        a = np.asarray(a)
+        if a.ndim >= 2 and a.shape[:2] == (72, 36):
+            v[k] = np.resize(a, (nlon, nlat) + a.shape[2:]).astype(a.dtype)
+        else:
+            v[k] = a
+    v["Latitude"] = np.linspace(-89.5, 89.5, nlat).astype(np.float32)
+    v["Longitude"] = np.linspace(-179.5, 179.5, nlon).astype(np.float32)
+    n_px = nlon * nlat
+    t0 = time.perf_counter()
+    for _ in range(3):
+        rf.mopitt_co(v)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        rf.mopitt_co(v)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    t0 = time.perf_counter()
+    oreader.mopitt_co({k: np.array(a) for k, a in v.items()})
+    cpu_s = time.perf_counter() - t0
+    return dict(row="8f-1 reader front-end, MOPITT CO (K7 oisat_reader_clean)",
+                workload="MOP03 daily L3, 360x180 px, 9 levels + 10 AK rows",
+                unit="px/s", value=n_px / (ms * 1e-3), call_ms=ms,
+                note="whole drop-in call from host variables to host record (H2D + 9 launches + D2H): "
+                     "a 12 MB working set, host- and copy-bound",
+                cpu_px_per_s=n_px / cpu_s, cpu_s=cpu_s, cpu_kind="port (oracle/reader.py, numpy, 1 core)")
+
+
+def row_pwv():
+    """8f-4 (round 2): model precipitable water on the global GMI grid (72 layers x 207,936
+    cells): oisat_pwv_partial + oisat_pwv_column against the numpy statement (pwv_cal.py:62-93)."""
+    n_lev, n = 72, 361 * 576
+    rng = np.random.default_rng(3)
+    dp = rng.uniform(1.0, 30.0, (n_lev, n)).astype(np.float32)
+    q = rng.uniform(1e-6, 2e-2, (n_lev, n)).astype(np.float32)
+    vcd = rng.uniform(1.0, 60.0, n)
+    vcd[::7] = np.nan
+    dpd, qd, vd = _dev.to_device(dp), _dev.to_device(q), _dev.to_device(vcd)
+    pc = _dev.empty((n_lev, n), "float32")
+    out = _dev.empty((n,))
+    lib = _lib.lib()
+
+    def run():
+        _lib.check(lib.oisat_pwv_partial(dpd.data_ptr(), qd.data_ptr(), n_lev * n, pc.data_ptr(),
+                                         _dev.stream()))
+        _lib.check(lib.oisat_pwv_column(pc.data_ptr(), _lib.F32, n_lev, n, vd.data_ptr(),
+                                        out.data_ptr(), _dev.stream()))
+
+    ms = gpu_ms(run)
+    t0 = time.perf_counter()
+    want = np.nansum((dp * q / 9.80665 / 10000.0) / 1000.0, axis=0)
+    want[np.isnan(vcd)] = np.nan
+    cpu_s = time.perf_counter() - t0
+    got = _dev.to_host(out)
+    assert np.array_equal(got.astype(np.float32), want, equal_nan=True)     # bit for bit
+    b = n_lev * n * (4 + 4 + 4 + 4) + n * 16
+    return dict(row="8f-4 model precipitable water (oisat_pwv_partial + oisat_pwv_column)",
+                workload="72 layers x 361x576 GMI cells", unit="cells/s", value=n / (ms * 1e-3),
+                kernel_ms=ms, algorithmic_bytes=b, achieved_GBps=b / (ms * 1e-3) / 1e9,
+                peak_GBps=peak(), frac=b / (ms * 1e-3) / 1e9 / peak(), bit_identical=True,
+                cpu_cells_per_s=n / cpu_s, cpu_s=cpu_s, cpu_kind="numpy statement of pwv_cal.py:62-93, 1 core")
+
+
 def main():
     _dev.require_cuda()
-    for fn in (row_reader, row_nearest, row_output):
+    rows = (row_reader, row_nearest, row_output, row_reader_mopitt, row_pwv)
+    want = sys.argv[1:]
+    for fn in rows:
+        if want and fn.__name__ not in want:
+            continue
         print(json.dumps(fn()), flush=True)
 
 
