@@ -147,7 +147,9 @@ pair_alive_hw_kernel(int64_t n_pairs, int S, const int32_t* __restrict__ vert,
       bad = px_bad[px0 + v] != 0;
       za = w[pair * S + base + gl] * amf_masked[px0 + v];
     }
-    any_bad = any_bad || (__ballot_sync(0xffffffffu, bad) & half_mask) != 0;
+    // (the ballot must be executed by every lane in every sweep: no short-circuit around it)
+    const unsigned bad_lanes = __ballot_sync(0xffffffffu, bad);
+    any_bad = any_bad || (bad_lanes & half_mask) != 0;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) za += __shfl_xor_sync(0xffffffffu, za, o, 16);
     acc_amf += za;
