@@ -23,6 +23,12 @@ def _has_gpu():
 
 def pytest_collection_modifyitems(config, items):
     if _has_gpu():
+        # a kernel that never returns must not eat the whole GPU session: pytest-timeout's thread
+        # method ends the process (a blocked cudaDeviceSynchronize cannot be interrupted politely)
+        if config.pluginmanager.hasplugin("timeout"):
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(600, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
