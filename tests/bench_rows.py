@@ -253,9 +253,51 @@ def row_pwv():
                 cpu_cells_per_s=n / cpu_s, cpu_s=cpu_s, cpu_kind="numpy statement of pwv_cal.py:62-93, 1 core")
 
 
+def row_ssmis():
+    """8f-4 (round 2): one monthly SSMIS map (1440 x 720, 0.25 degree) onto the global GMI grid
+    through interpolator_ssmis: the first call builds the two lattice plans (Qhull + scipy's
+    walk on the host, exact for lattices; cached by geometry, every month of a record shares
+    them), later calls are the GPU work alone.  Oracle = the reference's algorithm (two Delaunay
+    triangulations and LinearNDInterpolator evaluations per field, interpolator_ssmis.py)."""
+    import types
+    from oisatgmi_b200 import interpolator_ssmis as issmis
+    from oracle import ssmis as ossmis
+    rng = np.random.default_rng(1)
+    lat = np.arange(-89.875, 90.0, 0.25)
+    lon = np.arange(0.125, 360.0, 0.25)
+    wv = np.clip(60 + 90 * (synth._smooth2d(rng, (lat.size, lon.size), scale=3.0) + 0.5), 0, 249)
+    wv[~synth._coherent_mask(rng, wv.shape, 0.3)] = 255
+    v = {"latitude": lat, "longitude": lon, "atmosphere_water_vapor_content": wv.astype(np.uint8)}
+    rec = rf.ssmis_wv({k: np.array(a) for k, a in v.items()}, "200506")
+    coords = synth.ctm_coordinates()
+    t0 = time.perf_counter()
+    got = issmis.interpolator_ssmis(1, 0.25, rec, coords)
+    torch.cuda.synchronize()
+    first_s = time.perf_counter() - t0
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        got = issmis.interpolator_ssmis(1, 0.25, rec, coords)
+    torch.cuda.synchronize()
+    later_ms = (time.perf_counter() - t0) / reps * 1e3
+    t0 = time.perf_counter()
+    want = ossmis.interpolator_ssmis(1, 0.25, ossmis.ssmis_wv({k: np.array(a) for k, a in v.items()},
+                                                              "200506"), coords)
+    cpu_s = time.perf_counter() - t0
+    same_mask = bool(np.array_equal(np.isnan(got.vcd), np.isnan(want.vcd)))
+    f = np.isfinite(want.vcd)
+    rel = float(np.max(np.abs(got.vcd[f] - want.vcd[f]) / np.abs(want.vcd[f])))
+    n_px = lat.size * lon.size
+    return dict(row="8f-4 interpolator_ssmis (two plan steps + box mean)",
+                workload="SSMIS monthly map 1440x720 onto the 361x576 GMI grid, 0.25 degree mesh",
+                unit="px/s", value=n_px / (later_ms * 1e-3), call_ms_plans_cached=later_ms,
+                first_call_s_building_plans=first_s, same_nan_mask=same_mask, max_rel_err_vcd=rel,
+                cpu_px_per_s=n_px / cpu_s, cpu_s=cpu_s, cpu_kind="port (oracle/ssmis.py, scipy, 1 core)")
+
+
 def main():
     _dev.require_cuda()
-    rows = (row_reader, row_nearest, row_output, row_reader_mopitt, row_pwv)
+    rows = (row_reader, row_nearest, row_output, row_reader_mopitt, row_pwv, row_ssmis)
     want = sys.argv[1:]
     for fn in rows:
         if want and fn.__name__ not in want:
