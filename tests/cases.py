@@ -101,8 +101,11 @@ def amf_case(name):
                 sensor=product.split("_")[0], gas=product.split("_")[1])
 
 
-def mopitt_case():
-    c = coords(REGION_AK)
+def mopitt_case(coarse=False):
+    """`coarse`: a 2 x 2.5 degree model, COARSER than the 1 degree L3 lattice -- the gridded
+    granule then lands on the model grid itself (interpolator.py:64-93) and ak_conv_mopitt uses
+    the model fields as they are (no resampling, ak_conv_mopitt.py:79)."""
+    c = synth.ctm_coordinates(REGION_AK, dlat=2.0, dlon=2.5) if coarse else coords(REGION_AK)
     model = [synth.make_ctm(21, c, ctmtype="ECCOH", averaged=False, gas_scale=40.0,
                             date=datetime.datetime(2005, 6, 1))]
     grans = [synth.make_mopitt_granule(31 + i, region=REGION_AK,

@@ -82,14 +82,14 @@ def month_tail(impl, store, sensor, gas, ctm, grids, per_granule, skip_aux=False
     return grids
 
 
-def mopitt_chain(impl):
-    c = cases.mopitt_case()
+def mopitt_chain(impl, coarse=False):
+    c = cases.mopitt_case(coarse)
     store = {}
     grids = []
     for i, g in enumerate(c["granules"]):
         r = impl.interpolator(1, c["grid_size"], cases.clone(g), c["coords"],
                               flag_thresh=c["flag_thresh"])
-        assert r is not None and r.ctm_upscaled_needed
+        assert r is not None and bool(r.ctm_upscaled_needed) == (not coarse)
         put(store, "interp%d" % i, r, ["vcd", "uncertainty", "x_col", "aprior_column",
                                         "surface_pressure", "apriori_surface", "pressure_mid",
                                         "averaging_kernels", "apriori_profile"])

@@ -241,6 +241,29 @@ OPT_KEYS = {"avg.sat_err": "sat_averaged_error", "avg.ctm_vcd": "ctm_averaged_vc
             "oi.increment_OI": "increment_OI", "oi.error_OI": "error_OI"}
 
 
+def test_opt_month_pipeline_on_a_model_coarser_than_the_lattice():
+    """MOPITT against a 2 x 2.5 degree model: the gridded granules land on the model grid
+    (box mean + nearest node, interpolator.py:64-93) and the AK convolution reads the model
+    columns as they are -- OptMonthPipeline's other branch, against the oracle's month and
+    against the stage-wise drop-ins."""
+    from oisatgmi_b200.opt_pipeline import OptMonthPipeline
+    c = cases.mopitt_case(coarse=True)
+    pipe = OptMonthPipeline(c["ctm"], c["grid_size"], c["flag_thresh"], "MOPITT")
+    assert pipe.gplan.upscale
+    for g in c["granules"]:
+        assert pipe.add_granule(cases.clone(g))
+    res = pipe.results_to_host(pipe.run())
+    want, _ = chains.mopitt_chain(chains.oracle_impl(), coarse=True)
+    got, _ = chains.mopitt_chain(chains.cuda_impl(), coarse=True)
+    for key, attr in (("avg.sat_err", "sat_averaged_error"), ("avg.ctm_vcd", "ctm_averaged_vcd"),
+                      ("avg.aux1", "aux1"), ("avg.aux2", "aux2"), ("oi.y", "sat_averaged_vcd"),
+                      ("oi.ctm_averaged_vcd_corrected", "ctm_averaged_vcd_corrected"),
+                      ("oi.ak_OI", "ak_OI"), ("oi.error_OI", "error_OI")):
+        assert_field(res[attr], want[key], key, rtol=RTOL_FP64)
+        assert_field(got[key], want[key], key + " (drop-ins)", rtol=RTOL_FP64)
+    assert np.isfinite(res["ctm_averaged_vcd_corrected"]).sum() > 50
+
+
 @pytest.mark.parametrize("sensor", ["MOPITT", "GOSAT"])
 def test_opt_month_pipeline_matches_oracle_month(sensor, golden):
     """The device-resident satellite_opt month (gap filling, gridding, model resampling, AK

@@ -228,3 +228,9 @@ def test_drop_in_signatures_match_the_reference():
         a, b = inspect.signature(getattr(ref_cls, meth)), inspect.signature(getattr(our_cls, meth))
         assert [(p.name, p.default) for p in a.parameters.values()] == \
                [(p.name, p.default) for p in b.parameters.values()], (meth, str(a), str(b))
+
+
+def test_mopitt_chain_on_a_coarse_model_is_bit_identical_to_reference():
+    """The other branch of _upscaler / ak_conv_mopitt: a model coarser than the L3 lattice."""
+    _same(chains.mopitt_chain(chains.oracle_impl(), coarse=True)[0],
+          chains.mopitt_chain(reference_impl(), coarse=True)[0])
