@@ -286,7 +286,7 @@ def row_ssmis():
     cpu_s = time.perf_counter() - t0
     same_mask = bool(np.array_equal(np.isnan(got.vcd), np.isnan(want.vcd)))
     f = np.isfinite(want.vcd)
-    rel = float(np.max(np.abs(got.vcd[f] - want.vcd[f]) / np.abs(want.vcd[f])))
+    rel = float(np.max(np.abs(got.vcd[f] - want.vcd[f]) / np.maximum(np.abs(want.vcd[f]), 1e-300)))
     n_px = lat.size * lon.size
     return dict(row="8f-4 interpolator_ssmis (two plan steps + box mean)",
                 workload="SSMIS monthly map 1440x720 onto the 361x576 GMI grid, 0.25 degree mesh",
