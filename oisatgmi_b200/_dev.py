@@ -65,6 +65,34 @@ def native_float(arr: np.ndarray) -> np.ndarray:
     return arr.astype(np.float64)
 
 
+_keep = None   # a list while a recording wants every allocation kept alive (see keep_allocations)
+
+
+class keep_allocations:
+    """While active, every tensor the helpers below create is also appended to `store`: the
+    launches recorded by `_lib.recording` refer to raw addresses, which must stay valid for as
+    long as the recording is replayed."""
+
+    def __init__(self, store):
+        self.store = store
+
+    def __enter__(self):
+        global _keep
+        self._saved, _keep = _keep, self.store
+        return self.store
+
+    def __exit__(self, *exc):
+        global _keep
+        _keep = self._saved
+        return False
+
+
+def _kept(t):
+    if _keep is not None:
+        _keep.append(t)
+    return t
+
+
 def to_device(arr, dtype=None, pin=False):
     """numpy -> device tensor (contiguous, dtype preserved unless given)."""
     t = require_cuda()
@@ -72,22 +100,22 @@ def to_device(arr, dtype=None, pin=False):
     h = t.from_numpy(a)
     if pin:
         h = h.pin_memory()
-    return h.to(device(), non_blocking=pin)
+    return _kept(h.to(device(), non_blocking=pin))
 
 
 def empty(shape, dtype="float64"):
     t = require_cuda()
-    return t.empty(shape, dtype=getattr(t, dtype), device=device())
+    return _kept(t.empty(shape, dtype=getattr(t, dtype), device=device()))
 
 
 def full(shape, value, dtype="float64"):
     t = require_cuda()
-    return t.full(shape, value, dtype=getattr(t, dtype), device=device())
+    return _kept(t.full(shape, value, dtype=getattr(t, dtype), device=device()))
 
 
 def zeros(shape, dtype="float64"):
     t = require_cuda()
-    return t.zeros(shape, dtype=getattr(t, dtype), device=device())
+    return _kept(t.zeros(shape, dtype=getattr(t, dtype), device=device()))
 
 
 def ptr(t):

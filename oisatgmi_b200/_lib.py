@@ -123,9 +123,59 @@ class OisatError(RuntimeError):
     pass
 
 
+class Recorder:
+    """Stands in for the library while it is installed (`with recording() as rec`): every
+    kernel-launching entry point called on this thread is executed AND noted as (function,
+    arguments).  A month step whose arguments do not change from one run to the next -- resident
+    inputs, cached plans, buffers kept alive by `_dev.keep_allocations` -- can then be replayed
+    call by call (`replay`) without the Python work that assembled it (descriptor structs,
+    allocations, look-ups: ~30 us per launch, more than the small kernels themselves take)."""
+
+    def __init__(self, real):
+        self._real = real
+        self.calls = []
+
+    def __getattr__(self, name):
+        fn = getattr(self._real, name)
+        if not name.startswith("oisat_") or fn.restype is not C.c_int or name == "oisat_abi_version":
+            return fn
+
+        def call(*args):
+            self.calls.append((fn, args))
+            return fn(*args)
+        return call
+
+    def replay(self):
+        for fn, args in self.calls:
+            rc = fn(*args)
+            if rc != 0:
+                check(rc)
+
+
+_recorder = None
+_recorder_thread = None
+
+
+class recording:
+    def __enter__(self):
+        global _recorder, _recorder_thread
+        if _recorder is not None:
+            raise OisatError("a recording is already in progress")
+        rec = Recorder(lib())
+        _recorder, _recorder_thread = rec, threading.get_ident()
+        return rec
+
+    def __exit__(self, *exc):
+        global _recorder, _recorder_thread
+        _recorder = _recorder_thread = None
+        return False
+
+
 def lib():
     """The loaded library (raises if it has not been built)."""
     global _lib
+    if _recorder is not None and threading.get_ident() == _recorder_thread:
+        return _recorder
     if _lib is not None:
         return _lib
     with _lock:

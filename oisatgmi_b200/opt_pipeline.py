@@ -62,6 +62,8 @@ class OptMonthPipeline:
         self._fill = None              # GOSAT: (grid plan of the filler mesh, X, Y)
         self._resample = None          # K6 geometry (model grid -> output mesh)
         self._acc = None
+        self._program = None           # recorded launches of the granule loop (see run)
+        self._program_keep = None
         self.n_skipped = 0
 
     # ------------------------------------------------------------------ inputs
@@ -107,6 +109,7 @@ class OptMonthPipeline:
             self.n_skipped += 1
             return False
         self.granules.append(g)
+        self._program = self._program_keep = None
         return True
 
     def n_pixels(self):
@@ -219,29 +222,59 @@ class OptMonthPipeline:
         return out[layout["x_col"][0]], None, xcol       # ctm_vcd is NaN by design (:138)
 
     # --------------------------------------------------------------------- run
-    def run(self, marks=None):
-        def mark(name):
-            if marks is not None:
-                e = _dev.torch().cuda.Event(enable_timing=True)
-                e.record()
-                marks.append((name, e))
-
+    def _granule_steps(self, acc):
+        """Every launch of the granule loop, in order (gap filling, gridding, model resampling
+        once per model day, AK convolution, accumulation)."""
         L = _lib.lib()
-        mark("start")
         self._model_on_mesh = {}     # the model is resampled inside the step, once per model day
-        acc = _dev.zeros((10, self.n_cell))
-        self._acc = acc
         for g in self.granules:
             out, layout, _keep = self._grid(g)
             vcd, col, xcol = self._convolve(g, out, layout)
             _lib.check(L.oisat_accum_add(
                 acc.data_ptr(), self.n_cell, vcd.data_ptr(), out[layout["uncertainty"][0]].data_ptr(),
                 _dev.ptr(col), out[layout["x_col"][0]].data_ptr(), xcol.data_ptr(), _dev.stream()))
+
+    def run(self, marks=None):
+        """One month step.  The first run executes the granule loop through the Python layers
+        and RECORDS its launches (`_lib.recording`): inputs are resident, plans cached and
+        every buffer of the loop is kept alive, so the arguments of those ~8 launches per
+        granule never change; later runs replay them call by call -- the months of these
+        sensors are 30 small granules, and assembling a launch in Python (descriptor structs,
+        allocations, look-ups) costs more than the kernel it starts.  OISAT_OPT_REPLAY=0 runs
+        the loop afresh every time; add_granule() drops the recording."""
+        import os
+
+        def mark(name):
+            if marks is not None:
+                e = _dev.torch().cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
+        mark("start")
+        stream = _dev.stream()
+        replay = os.environ.get("OISAT_OPT_REPLAY", "1") != "0"
+        if replay and self._program is not None and self._program[2] == stream:
+            rec, acc, _ = self._program
+            acc.zero_()
+            rec.replay()
+        else:
+            acc = _dev.zeros((10, self.n_cell))
+            if replay:
+                keep = [acc]
+                with _dev.keep_allocations(keep), _lib.recording() as rec:
+                    self._granule_steps(acc)
+                self._program = (rec, acc, stream)
+                self._program_keep = keep
+            else:
+                self._granule_steps(acc)
+        self._acc = acc
         mark("granules")
+        merged = acc
         if self.pg is not None:
             from .sharding import merge_accumulators
-            merge_accumulators(acc, self.pg)
-        res = finalize_and_oi(acc, self.n_cell, self.sensor, self.gas, self.error_ctm)
+            merged = acc.clone()          # the recording's block keeps this rank's own sums
+            merge_accumulators(merged, self.pg)
+        res = finalize_and_oi(merged, self.n_cell, self.sensor, self.gas, self.error_ctm)
         mark("oi")
         return res
 

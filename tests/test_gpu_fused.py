@@ -292,6 +292,24 @@ def test_opt_month_pipeline_matches_oracle_month(sensor, golden):
         assert_field(res[attr], want[key], key, rtol=RTOL_FP64, scale=scale)
         assert_field(res[attr], gold[key], key + "(golden)", rtol=RTOL_FP64, scale=scale)
     assert np.isfinite(res["ctm_averaged_vcd_corrected"]).sum() > 100
+    # the second run REPLAYS the recorded launches of the granule loop: same bits; and so does a
+    # pipeline that never records (OISAT_OPT_REPLAY=0)
+    again = pipe.results_to_host(pipe.run())
+    assert pipe._program is not None and len(pipe._program[0].calls) >= 4 * len(c["granules"])
+    import os
+    os.environ["OISAT_OPT_REPLAY"] = "0"
+    try:
+        plain_pipe = OptMonthPipeline(c["ctm"], c["grid_size"], c["flag_thresh"], sensor)
+        for g in c["granules"]:
+            assert plain_pipe.add_granule(cases.clone(g))
+        plain = plain_pipe.results_to_host(plain_pipe.run())
+        assert plain_pipe._program is None
+    finally:
+        del os.environ["OISAT_OPT_REPLAY"]
+    for k, v in res.items():
+        if isinstance(v, np.ndarray):
+            assert np.array_equal(v, again[k], equal_nan=True), k
+            assert np.array_equal(v, plain[k], equal_nan=True), k
     from oracle import oi as ooi
     pick = ooi.oi_from_means(sensor, np.array(want["avg.ctm_vcd"]), np.array(want["avg.sat_vcd"]),
                              np.array(want["avg.sat_err"]), np.array(want["avg.aux1"]),
