@@ -33,7 +33,8 @@ def main():
         return p, p.results_to_host(p.run())
 
     mine = sharding.assign(times, rank, world)
-    assert mine, "test case has fewer days than ranks"
+    # more ranks than days leaves some ranks without a granule: they must still join the
+    # all-reduce with a zero block (MonthPipeline.run) and end with the same month
     p, res = run(mine, dist.group.WORLD)
     _, ref = run(range(len(times)), None)
     ok = res["knee_index"] == ref["knee_index"]
