@@ -108,6 +108,44 @@ int64_t oisat_h_delaunay_swath_adj(const double* h_x, const double* h_y, int64_t
                                    int64_t n_cols, int32_t* h_tri, int64_t tri_capacity,
                                    int32_t* h_half, int64_t* n_ties, int32_t* path);
 
+/* ---- K12: the triangulation of a swath finished on the device (round 2) -------------------
+ * Replaces, for structured swaths, the host triangulation behind interpolator.py:153
+ * (scipy.spatial.Delaunay inside LinearNDInterpolator).  The lattice the pixels come in is
+ * already a triangulation of almost the whole footprint; the host only classifies its quads
+ * and triangulates what the lattice leaves of the convex hull (outline pockets, the lips of a
+ * date-line tear), the device assembles the seed and turns it into the Delaunay
+ * triangulation by rounds of independent edge flips (Lawson).
+ *
+ * HOST: oisat_h_delaunay_seed_parts -- h_qtri[(n_rows-1)*(n_cols-1)]: first triangle of every
+ *   seeded quad (-1: not seeded); h_otri / h_ohalf (3 per triangle, out_capacity triangles):
+ *   the triangles outside the lattice and their twin half-edges in the numbering of the
+ *   result; info[5] = {seeded quads, seam vertices, outside triangles, sigma, declining
+ *   check}.  Returns the number of triangles, 0 when the construction does not apply (the
+ *   caller uses oisat_h_delaunay_swath_adj), negative OISAT_E_* on bad arguments.
+ * HOST: oisat_h_delaunay_seed -- the same construction whole on the host (flags bit 0: with
+ *   Lawson's flips; bit 1: with the near-tie scan), and oisat_h_flip_rounds, the device
+ *   rounds replayed serially (same per-edge code, csrc/flip_rounds.h): the CPU tests' model.
+ * DEVICE: oisat_seed_assemble -- tri / half (3 * (2 n_quads + n_outside) each) from the
+ *   uploaded parts.  oisat_flip_delaunay -- flips in place until every edge is locally
+ *   Delaunay; result[4] = {rounds, flips, edges still not Delaunay (rounds cut off), edges
+ *   the floating-point filter cannot decide}: when either of the last two is non-zero the
+ *   caller must take the exact host builder.  workspace: oisat_flip_workspace_bytes. */
+int64_t oisat_h_delaunay_seed_parts(const double* h_x, const double* h_y, int64_t n_rows,
+                                    int64_t n_cols, int32_t* h_qtri, int32_t* h_otri,
+                                    int32_t* h_ohalf, int64_t out_capacity, int64_t* info);
+int64_t oisat_h_delaunay_seed(const double* h_x, const double* h_y, int64_t n_rows,
+                              int64_t n_cols, int32_t* h_tri, int64_t tri_capacity,
+                              int32_t* h_half, int64_t* n_ties, int32_t flags, int64_t* info);
+int oisat_h_flip_rounds(const double* h_x, const double* h_y, int32_t* h_tri, int32_t* h_half,
+                        int64_t n_tri, int64_t max_rounds, int64_t* result);
+int oisat_seed_assemble(const int32_t* qtri, int64_t n_rows, int64_t n_cols, int32_t sigma,
+                        int64_t n_quads, const int32_t* otri, const int32_t* ohalf,
+                        int64_t n_outside, int32_t* tri, int32_t* half, void* stream);
+int64_t oisat_flip_workspace_bytes(int64_t n_tri);
+int oisat_flip_delaunay(int32_t* tri, int32_t* half, int64_t n_tri, const void* px,
+                        const void* py, int32_t coord_dtype, void* workspace, uint64_t* result,
+                        void* stream);
+
 /* Device part of the tie report: edges whose fourth point lies within Qhull's tolerance of
  * the circumcircle (2e-14 x max_abs_coord^2 x twice the triangle area; exact co-circular
  * quadruples included).  tri / half: device copies of the arrays above; px / py: the

@@ -59,6 +59,12 @@ PROTOTYPES = {
     "oisat_h_delaunay": (i64, [vp, vp, i64, vp, i64, C.POINTER(i64)]),
     "oisat_h_delaunay_swath": (i64, [vp, vp, i64, i64, vp, i64, C.POINTER(i64), C.POINTER(i32)]),
     "oisat_h_delaunay_swath_adj": (i64, [vp, vp, i64, i64, vp, i64, vp, C.POINTER(i64), C.POINTER(i32)]),
+    "oisat_h_delaunay_seed_parts": (i64, [vp, vp, i64, i64, vp, vp, vp, i64, vp]),
+    "oisat_h_delaunay_seed": (i64, [vp, vp, i64, i64, vp, i64, vp, C.POINTER(i64), i32, vp]),
+    "oisat_h_flip_rounds": (C.c_int, [vp, vp, vp, vp, i64, i64, vp]),
+    "oisat_seed_assemble": (C.c_int, [vp, i64, i64, i32, i64, vp, vp, i64, vp, vp, vp]),
+    "oisat_flip_workspace_bytes": (i64, [i64]),
+    "oisat_flip_delaunay": (C.c_int, [vp, vp, i64, vp, vp, i32, vp, vp, vp]),
     "oisat_near_ties": (C.c_int, [vp, vp, i64, vp, vp, i32, f64, vp, vp, vp]),
     "oisat_flagged_nodes": (C.c_int, [vp, i64, vp, vp, vp]),
     "oisat_locate": (C.c_int, [vp, i64, vp, vp, i32, vp, i64, vp, i64, vp, vp, vp, vp]),

@@ -17,8 +17,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["api.cu", "k0_geometry.cu", "k1_locate.cu", "k2_interp.cu", "k3_vertical.cu",
-           "k4_accum.cu", "k5_oi.cu", "k7_reader.cu", "k8_output.cu", "k9_alive.cu", "k10_tables.cu", "k11_pwv.cu", "fused_amf.cu", "fused_split.cu", "delaunay.cpp"]
-HEADERS = ["common.cuh", "vertical.cuh", "delaunay_swath.inl",os.path.join("..", "..", "include", "oisat.h")]
+           "k4_accum.cu", "k5_oi.cu", "k7_reader.cu", "k8_output.cu", "k9_alive.cu", "k10_tables.cu", "k11_pwv.cu", "k12_flip.cu", "fused_amf.cu", "fused_split.cu", "delaunay.cpp"]
+HEADERS = ["common.cuh", "vertical.cuh", "delaunay_swath.inl", "delaunay_seed.inl", "flip_rounds.h", os.path.join("..", "..", "include", "oisat.h")]
 LIB = os.path.join(HERE, "liboisat.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",

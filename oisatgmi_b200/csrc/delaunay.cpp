@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "../../include/oisat.h"
+#include "flip_rounds.h"
 
 namespace {
 
@@ -499,7 +500,8 @@ struct Builder {
   }
 };
 
-#include "delaunay_swath.inl"  // GridBuilder: structured-swath builder (uses the predicates above)
+#include "delaunay_swath.inl"  // LatticeBuilder: structured-swath builder (uses the predicates above)
+#include "delaunay_seed.inl"   // SeedBuilder: the lattice itself as the seed of a flip-only construction
 
 }  // namespace
 
@@ -589,4 +591,123 @@ extern "C" int64_t oisat_h_delaunay(const double* h_x, const double* h_y, int64_
   std::copy(b.tri.begin(), b.tri.begin() + 3 * b.ntri, h_tri);
   if (n_ties) *n_ties = b.ties;
   return b.ntri;
+}
+
+// Lattice-seeded construction (delaunay_seed.inl), whole on the host.  flags bit 0: finish
+// with Lawson's flips (the result is then the Delaunay triangulation; without it the SEED is
+// returned, a valid triangulation of the convex hull); bit 1: add the near-tie scan to *n_ties
+// (only meaningful with bit 0).  h_half as in oisat_h_delaunay_swath_adj.  info (may be NULL)
+// receives {seeded quads, seam vertices, triangles outside the lattice, host flips, declining
+// check}.  Returns the number of triangles, or 0 when the construction does not apply to this
+// lattice (a check of delaunay_seed.inl declined: the caller uses oisat_h_delaunay_swath_adj).
+extern "C" int64_t oisat_h_delaunay_seed(const double* h_x, const double* h_y, int64_t n_rows,
+                                         int64_t n_cols, int32_t* h_tri, int64_t tri_capacity,
+                                         int32_t* h_half, int64_t* n_ties, int32_t flags,
+                                         int64_t* info) {
+  if (!h_x || !h_y || !h_tri || !h_half || n_rows < 1 || n_cols < 1 ||
+      n_rows * n_cols > (int64_t)0x3fffffff)
+    return OISAT_E_ARG;
+  static thread_local SeedBuilder g;
+  g.x = h_x;
+  g.y = h_y;
+  g.rows = n_rows;
+  g.cols = n_cols;
+  const int rc = g.seed();
+  if (info) { info[0] = g.n_quads; info[1] = g.n_seam; info[2] = g.n_outside; info[3] = 0; info[4] = g.why * 100 - g.rec_fail; }
+  if (rc != 0) { g.release_if_large(); return 0; }
+  if (g.ntri > tri_capacity) { g.release_if_large(); return OISAT_E_ARG; }
+  g.assemble();
+  if (flags & 1) g.lawson();
+  if (info) info[3] = g.flips;
+  std::copy(g.tri.begin(), g.tri.begin() + 3 * g.ntri, h_tri);
+  std::copy(g.half.begin(), g.half.begin() + 3 * g.ntri, h_half);
+  if (n_ties) {
+    *n_ties = g.ties;
+    if ((flags & 3) == 3)
+      *n_ties += count_near_ties(h_x, h_y, g.n, g.tri.data(), g.half.data(), g.ntri);
+  }
+  const int64_t nt = g.ntri;
+  g.release_if_large();
+  return nt;
+}
+
+// The host's share of the device construction (k12_flip.cu): h_qtri[(n_rows-1)*(n_cols-1)]
+// receives, per lattice quad, the index of the first of its two triangles (-1: the quad is
+// not part of the seed); h_otri / h_ohalf (3 per triangle, out_capacity triangles) the
+// triangles outside the lattice and their twins in the numbering of the result.  info
+// receives {seeded quads, seam vertices, outside triangles, sigma, declining check}.
+// Returns the number of triangles of the seed, 0 when the construction does not apply.
+extern "C" int64_t oisat_h_delaunay_seed_parts(const double* h_x, const double* h_y, int64_t n_rows,
+                                               int64_t n_cols, int32_t* h_qtri, int32_t* h_otri,
+                                               int32_t* h_ohalf, int64_t out_capacity,
+                                               int64_t* info) {
+  if (!h_x || !h_y || !h_qtri || !h_otri || !h_ohalf || !info || n_rows < 1 || n_cols < 1 ||
+      n_rows * n_cols > (int64_t)0x3fffffff)
+    return OISAT_E_ARG;
+  static thread_local SeedBuilder g;
+  g.x = h_x;
+  g.y = h_y;
+  g.rows = n_rows;
+  g.cols = n_cols;
+  const int rc = g.seed();
+  info[0] = g.n_quads; info[1] = g.n_seam; info[2] = g.n_outside; info[3] = g.sigma;
+  info[4] = g.why * 100 - g.rec_fail;
+  if (rc != 0 || g.ties != 0) { g.release_if_large(); return 0; }
+  if (g.n_outside > out_capacity) { g.release_if_large(); return OISAT_E_ARG; }
+  std::copy(g.qtri.begin(), g.qtri.end(), h_qtri);
+  std::copy(g.otri.begin(), g.otri.end(), h_otri);
+  std::copy(g.ohalf.begin(), g.ohalf.end(), h_ohalf);
+  const int64_t nt = g.ntri;
+  g.release_if_large();
+  return nt;
+}
+
+// The rounds of oisat_flip_delaunay replayed on the host, threads one after the other (the
+// same per-edge steps, flip_rounds.h): what the CPU tests run, and the model the device
+// kernel is compared with.  h_tri / h_half are changed in place; result as on the device:
+// {rounds, flips, edges certainly not Delaunay, edges the filter cannot decide}.
+extern "C" int oisat_h_flip_rounds(const double* h_x, const double* h_y, int32_t* h_tri,
+                                   int32_t* h_half, int64_t n_tri, int64_t max_rounds,
+                                   int64_t* result) {
+  if (!h_x || !h_y || !h_tri || !h_half || !result || n_tri < 0 || max_rounds < 1 ||
+      max_rounds > 65536 || 3 * n_tri > (int64_t)0x7ffffff0)
+    return OISAT_E_ARG;
+  std::vector<int32_t> stamp((size_t)n_tri, -1), cand((size_t)(3 * n_tri), 0),
+      list0((size_t)n_tri), list1((size_t)n_tri), edges((size_t)(3 * n_tri / 2 + 1));
+  std::vector<unsigned long long> owner((size_t)n_tri, 0ull);
+  std::vector<unsigned int> n_listed((size_t)max_rounds, 0u), n_marked((size_t)max_rounds, 0u);
+  oisat_flip::Mesh m{h_tri, h_half, 3 * n_tri, stamp.data(), cand.data(), owner.data(),
+                     {list0.data(), list1.data()}, edges.data(), n_listed.data(), n_marked.data()};
+  auto P = [&](int v, int axis) { return axis ? h_y[v] : h_x[v]; };
+  struct HostOps {
+    unsigned long long max(unsigned long long* p, unsigned long long v) const {
+      const unsigned long long o = *p;
+      if (v > o) *p = v;
+      return o;
+    }
+    unsigned int add(unsigned int* p, unsigned int v) const { const unsigned int o = *p; *p = o + v; return o; }
+    int32_t exch(int32_t* p, int32_t v) const { const int32_t o = *p; *p = v; return o; }
+  } ops;
+  int64_t round = 0, flips = 0;
+  for (; round < max_rounds; ++round) {
+    const int r = (int)round;
+    if (r == 0)
+      for (int64_t e = 0; e < m.n_half; ++e) oisat_flip::mark_edge(m, (int32_t)e, r, P, ops);
+    else
+      for (unsigned int i = 0; i < n_listed[(size_t)r - 1]; ++i) {
+        const int32_t t = ((r & 1) ? list1 : list0)[i];
+        for (int e = 0; e < 3; ++e) oisat_flip::mark_edge(m, 3 * t + e, r, P, ops);
+      }
+    for (unsigned int i = 0; i < n_marked[(size_t)r]; ++i)
+      flips += oisat_flip::apply_edge(m, edges[i], r, ops);
+    if (n_marked[(size_t)r] == 0) { ++round; break; }
+  }
+  int64_t bad = 0, unsure = 0;
+  for (int64_t a = 0; a < m.n_half; ++a) {
+    const int c = oisat_flip::check_edge(h_tri, h_half, a, P);
+    bad += c & 1;
+    unsure += (c >> 1) & 1;
+  }
+  result[0] = round; result[1] = flips; result[2] = bad; result[3] = unsure;
+  return OISAT_OK;
 }

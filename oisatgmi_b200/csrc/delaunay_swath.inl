@@ -137,6 +137,93 @@ struct LatticeBuilder {
     return real(s) ? s : f - f % 3;
   }
 
+  // first triangle (p0, p1, p2 counter-clockwise) and its three ghosts
+  void begin(int32_t p0, int32_t p1, int32_t p2) {
+    const int32_t t = new_triangle(p0, p1, p2);
+    const int32_t g1 = new_triangle(p1, p0, G), g2 = new_triangle(p2, p1, G),
+                  g3 = new_triangle(p0, p2, G);
+    link(t, g1); link(t + 1, g2); link(t + 2, g3);
+    link(g1 + 1, g3 + 2); link(g2 + 1, g1 + 2); link(g3 + 1, g2 + 2);
+  }
+
+  // insert p: walk from a real triangle that has near_pt (an inserted vertex), split what the
+  // walk ends in, restore the Delaunay property.  false when the walk does not end.
+  bool insert(int32_t p, int64_t near_pt, int64_t max_steps) {
+    const int32_t start = real_triangle_of(near_pt);
+    int32_t s = start, from = -1;
+    int64_t steps = 0;
+    for (;;) {
+      if (++steps > max_steps) return false;
+      // s is real here
+      int32_t cross = -1;
+      int zeros = 0, zero_edge = -1;
+      for (int e = 0; e < 3; ++e) {
+        const int32_t h = s + e;
+        if (h == from) continue;
+        const int o = orient(tri[h], tri[next(h)], p);
+        if (o < 0) { cross = h; break; }
+        if (o == 0) { ++zeros; zero_edge = h; }
+      }
+      if (cross >= 0) {
+        const int32_t t = half[cross];
+        const int32_t ts = t - t % 3;
+        if (!real(ts)) {                // left the hull through a visible edge
+          split3(ts, p);
+          break;
+        }
+        from = t;
+        s = ts;
+        continue;
+      }
+      if (zeros == 0) {
+        split3(s, p);
+      } else if (zeros == 1) {
+        split4(zero_edge, p);
+      } else {
+        // coincides with a vertex: a repeated point, not a vertex of the triangulation
+      }
+      break;
+    }
+    relax();
+    return true;
+  }
+
+  // hull: collinear triples make Qhull's answer non-unique (counted into `ties`)
+  int hull_ties() {
+    hull_next.assign(n, -1);
+    int32_t start = -1;
+    for (int64_t t = 0; t < ntri; ++t) {
+      const int32_t s = (int32_t)(3 * t);
+      if (real(s)) continue;
+      const int32_t g = tri[s] == G ? s : (tri[s + 1] == G ? s + 1 : s + 2);
+      const int32_t v = tri[next(g)], u = tri[prev(g)];   // real edge v -> u, hull edge u -> v
+      hull_next[u] = v;
+      start = u;
+    }
+    if (start < 0) return -1;
+    int32_t p = start;
+    int64_t nh = 0;
+    do {
+      const int32_t q = hull_next[p], r = hull_next[q];
+      if (orient(p, q, r) == 0) ++ties;
+      p = q;
+      if (++nh > n) return -1;
+    } while (p != start);
+    return 0;
+  }
+
+  void drop_ghosts() {
+    for (int64_t t = 0; t < ntri; ++t) {
+      const int32_t s = (int32_t)(3 * t);
+      if (real(s)) continue;
+      for (int e = 0; e < 3; ++e) {
+        if (half[s + e] >= 0) half[half[s + e]] = -1;
+        half[s + e] = -1;
+      }
+      tri[s] = tri[s + 1] = tri[s + 2] = -1;
+    }
+  }
+
   // 0 on success, -1 when this builder does not apply (caller falls back)
   int run() {
     if (rows < 2 || cols < 2) return -1;
@@ -234,14 +321,7 @@ struct LatticeBuilder {
       }
     }
     if (p2 < 0) return -1;
-    {
-      const int32_t t = new_triangle(p0, p1, p2);
-      const int32_t g1 = new_triangle(p1, p0, G), g2 = new_triangle(p2, p1, G),
-                    g3 = new_triangle(p0, p2, G);
-      link(t, g1); link(t + 1, g2); link(t + 2, g3);
-      link(g1 + 1, g3 + 2); link(g2 + 1, g1 + 2); link(g3 + 1, g2 + 2);
-    }
-    int32_t cur = 0;                      // a real triangle near the previous point
+    begin(p0, p1, p2);
     // The walk to a new point starts at a triangle that HAS the nearest of: the previous point,
     // and the (up to four) corners of the coarser lattice cell around the new point, all
     // inserted at earlier levels (vtri is kept exact through every split and flip: 2.7 triangles
@@ -270,74 +350,11 @@ struct LatticeBuilder {
           if (d < best) { best = d; near_pt = cand[c]; }
         }
       }
-      const int32_t start = real_triangle_of(near_pt);
-      int32_t s = start, from = -1;
-      int64_t steps = 0;
-      for (;;) {
-        if (++steps > max_steps) return -1;
-        // s is real here
-        int32_t cross = -1;
-        int zeros = 0, zero_edge = -1;
-        for (int e = 0; e < 3; ++e) {
-          const int32_t h = s + e;
-          if (h == from) continue;
-          const int o = orient(tri[h], tri[next(h)], p);
-          if (o < 0) { cross = h; break; }
-          if (o == 0) { ++zeros; zero_edge = h; }
-        }
-        if (cross >= 0) {
-          const int32_t t = half[cross];
-          const int32_t ts = t - t % 3;
-          if (!real(ts)) {                // left the hull through a visible edge
-            cur = split3(ts, p);
-            break;
-          }
-          from = t;
-          s = ts;
-          continue;
-        }
-        if (zeros == 0) {
-          cur = split3(s, p);
-        } else if (zeros == 1) {
-          cur = split4(zero_edge, p);
-        } else {
-          cur = s;                        // coincides with a vertex: a repeated point
-        }
-        break;
-      }
-      relax();
+      if (!insert(p, near_pt, max_steps)) return -1;
       if (vtri[p] >= 0) prev_pt = p;      // (a repeated point is not a vertex)
     }
-    // hull: collinear triples make Qhull's answer non-unique; then drop the ghosts
-    {
-      hull_next.assign(n, -1);
-      int32_t start = -1;
-      for (int64_t t = 0; t < ntri; ++t) {
-        const int32_t s = (int32_t)(3 * t);
-        if (real(s)) continue;
-        const int32_t g = tri[s] == G ? s : (tri[s + 1] == G ? s + 1 : s + 2);
-        const int32_t v = tri[next(g)], u = tri[prev(g)];   // real edge v -> u, hull edge u -> v
-        hull_next[u] = v;
-        start = u;
-      }
-      int32_t p = start;
-      int64_t nh = 0;
-      do {
-        const int32_t q = hull_next[p], r = hull_next[q];
-        if (orient(p, q, r) == 0) ++ties;
-        p = q;
-        if (++nh > n) return -1;
-      } while (p != start);
-      for (int64_t t = 0; t < ntri; ++t) {
-        const int32_t s = (int32_t)(3 * t);
-        if (real(s)) continue;
-        for (int e = 0; e < 3; ++e) {
-          if (half[s + e] >= 0) half[half[s + e]] = -1;
-          half[s + e] = -1;
-        }
-        tri[s] = tri[s + 1] = tri[s + 2] = -1;
-      }
-    }
+    if (hull_ties() != 0) return -1;
+    drop_ghosts();
     return 0;
   }
 

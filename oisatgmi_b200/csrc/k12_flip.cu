@@ -1,0 +1,250 @@
+// K12: the Delaunay triangulation of a swath finished on the device.
+//
+// The host part (oisat_h_delaunay_seed_parts, delaunay_seed.inl) classifies the lattice quads
+// and triangulates what the lattice does not cover -- the pockets between the curved outline
+// and the convex hull, the lips of a date-line tear: a few thousand triangles.  Here:
+//   oisat_seed_assemble   the two triangles of every seeded quad and all twin pointers, one
+//                         thread per quad (what SeedBuilder::assemble does serially: 5 of the
+//                         host's 12 ms per granule, plus the upload of 4.7 MB of triangles);
+//   oisat_flip_delaunay   Lawson's flips as rounds of independent flips (flip_rounds.h) in ONE
+//                         cooperative launch: mark | grid barrier | apply | grid barrier, until
+//                         a round flips nothing, then the check of every edge.
+// The triangles never visit the host: the near-tie scan, K1 and the stencil fill read them
+// where they are.  The predicate is the floating-point filter; an edge it cannot decide is
+// counted and the caller gives that granule to the exact host builder.
+#include <cooperative_groups.h>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "flip_rounds.h"
+
+namespace cg = cooperative_groups;
+
+namespace oisat {
+namespace {
+
+template <typename T>
+struct FlipCoords {
+  const T* x;
+  const T* y;
+  __device__ __forceinline__ double operator()(int v, int axis) const {
+    return (double)(axis ? y[v] : x[v]);
+  }
+};
+
+struct DeviceOps {
+  __device__ __forceinline__ unsigned long long max(unsigned long long* p, unsigned long long v) const {
+    return atomicMax(p, v);
+  }
+  __device__ __forceinline__ unsigned int add(unsigned int* p, unsigned int v) const {
+    return atomicAdd(p, v);
+  }
+  __device__ __forceinline__ int32_t exch(int32_t* p, int32_t v) const { return atomicExch(p, v); }
+};
+
+// half-edge of the seeded quad whose first triangle is t on the given side
+// (0 top: row r, 1 left: column c, 2 right, 3 bottom); see SeedBuilder::slot
+__device__ __forceinline__ int32_t quad_slot(int32_t t, int side, int sigma) {
+  const int32_t t0 = 3 * t, t1 = t0 + 3;
+  if (sigma > 0) return side == 0 ? t0 : side == 1 ? t0 + 2 : side == 2 ? t1 : t1 + 1;
+  return side == 0 ? t0 + 2 : side == 1 ? t0 : side == 2 ? t1 + 2 : t1 + 1;
+}
+
+__global__ void __launch_bounds__(256)
+seed_assemble_kernel(const int32_t* __restrict__ qtri, int64_t rows, int64_t cols, int sigma,
+                     const int32_t* __restrict__ otri, const int32_t* __restrict__ ohalf,
+                     int64_t n_out3, int64_t base, int32_t* __restrict__ tri,
+                     int32_t* __restrict__ half) {
+  const int64_t qc = cols - 1, nq = (rows - 1) * qc;
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < nq) {
+    const int32_t t = qtri[i];
+    if (t < 0) return;
+    const int64_t r = i / qc, c = i - r * qc;
+    const int32_t a = (int32_t)(r * cols + c), b = a + 1, cc = a + (int32_t)cols, d = cc + 1;
+    const int32_t t0 = 3 * t, t1 = t0 + 3;
+    if (sigma > 0) {
+      tri[t0] = a; tri[t0 + 1] = b; tri[t0 + 2] = cc;
+      tri[t1] = b; tri[t1 + 1] = d; tri[t1 + 2] = cc;
+      half[t0 + 1] = t1 + 2;
+      half[t1 + 2] = t0 + 1;
+    } else {
+      tri[t0] = a; tri[t0 + 1] = cc; tri[t0 + 2] = b;
+      tri[t1] = b; tri[t1 + 1] = cc; tri[t1 + 2] = d;
+      half[t0 + 1] = t1;
+      half[t1] = t0 + 1;
+    }
+    // every thread writes its own four outer slots; a side without a seeded neighbour is a
+    // seam edge, written by the thread of the outside triangle across it (or stays -1: hull)
+    int32_t u;
+    if (r > 0 && (u = qtri[i - qc]) >= 0) half[quad_slot(t, 0, sigma)] = quad_slot(u, 3, sigma);
+    if (c > 0 && (u = qtri[i - 1]) >= 0) half[quad_slot(t, 1, sigma)] = quad_slot(u, 2, sigma);
+    if (c + 1 < qc && (u = qtri[i + 1]) >= 0) half[quad_slot(t, 2, sigma)] = quad_slot(u, 1, sigma);
+    if (r + 2 < rows && (u = qtri[i + qc]) >= 0) half[quad_slot(t, 3, sigma)] = quad_slot(u, 0, sigma);
+    return;
+  }
+  const int64_t j = i - nq;
+  if (j >= n_out3) return;
+  tri[base + j] = otri[j];
+  const int32_t g = ohalf[j];
+  half[base + j] = g;
+  if (g >= 0 && g < base) half[g] = (int32_t)(base + j);
+}
+
+// The rounds.  While a round has more than `tail` triangles to look at, the whole grid works
+// on it (two grid barriers per round); the long tail of short rounds -- an OMI granule needs
+// ~97 rounds, 80 of them with fewer than 500 flips -- is run by block 0 alone with block
+// barriers, the other blocks leave.  result[0] = rounds run, result[1] = flips.
+template <typename T>
+__global__ void __launch_bounds__(512)
+flip_rounds_kernel(oisat_flip::Mesh m, FlipCoords<T> P, int max_rounds, unsigned int tail,
+                   unsigned long long* __restrict__ result) {
+  cg::grid_group grid = cg::this_grid();
+  int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const DeviceOps ops;
+  bool solo = gridDim.x == 1;
+  int round = 0;
+  unsigned int flips = 0;
+  for (; round < max_rounds; ++round) {
+    if (round == 0) {
+      for (int64_t e = tid; e < m.n_half; e += nthreads) oisat_flip::mark_edge(m, (int32_t)e, 0, P, ops);
+    } else {
+      const int64_t n3 = 3 * (int64_t)*(volatile unsigned int*)&m.n_listed[round - 1];
+      const int32_t* list = (round & 1) ? m.tri_list[1] : m.tri_list[0];
+      for (int64_t i = tid; i < n3; i += nthreads) {
+        const int64_t k = i / 3;
+        oisat_flip::mark_edge(m, 3 * list[k] + (int32_t)(i - 3 * k), round, P, ops);
+      }
+    }
+    if (solo) __syncthreads(); else grid.sync();
+    const int64_t n_marked = *(volatile unsigned int*)&m.n_marked[round];
+    if (n_marked == 0) { ++round; break; }
+    for (int64_t i = tid; i < n_marked; i += nthreads)
+      flips += oisat_flip::apply_edge(m, m.edge_list[i], round, ops);
+    if (solo) __syncthreads(); else grid.sync();
+    if (!solo && *(volatile unsigned int*)&m.n_listed[round] <= tail) {
+      if (blockIdx.x != 0) break;
+      solo = true;
+      tid = threadIdx.x;
+      nthreads = blockDim.x;
+    }
+  }
+  flips = __reduce_add_sync(0xffffffffu, flips);
+  if ((threadIdx.x & 31) == 0 && flips) atomicAdd(&result[1], (unsigned long long)flips);
+  if (blockIdx.x == 0 && threadIdx.x == 0) result[0] = (unsigned long long)round;
+}
+
+// every edge once more: result[2] = edges certainly not Delaunay (only when the rounds were
+// cut off), result[3] = edges the filter cannot decide
+template <typename T>
+__global__ void __launch_bounds__(256)
+flip_check_kernel(const int32_t* __restrict__ tri, const int32_t* __restrict__ half, int64_t n_half,
+                  FlipCoords<T> P, unsigned long long* __restrict__ result) {
+  const int64_t a = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int c = a < n_half ? oisat_flip::check_edge(tri, half, a, P) : 0;
+  const unsigned int bad = __reduce_add_sync(0xffffffffu, (unsigned int)(c & 1));
+  const unsigned int unsure = __reduce_add_sync(0xffffffffu, (unsigned int)((c >> 1) & 1));
+  if ((threadIdx.x & 31) == 0) {
+    if (bad) atomicAdd(&result[2], (unsigned long long)bad);
+    if (unsure) atomicAdd(&result[3], (unsigned long long)unsure);
+  }
+}
+
+constexpr int kMaxRounds = 4096;
+
+}  // namespace
+}  // namespace oisat
+
+using namespace oisat;
+
+extern "C" int oisat_seed_assemble(const int32_t* qtri, int64_t n_rows, int64_t n_cols,
+                                   int32_t sigma, int64_t n_quads, const int32_t* otri,
+                                   const int32_t* ohalf, int64_t n_outside, int32_t* tri,
+                                   int32_t* half, void* stream) {
+  OISAT_CHECK_ARG(qtri && tri && half && (n_outside == 0 || (otri && ohalf)), "null pointer");
+  OISAT_CHECK_ARG(n_rows >= 2 && n_cols >= 2 && n_quads >= 1 && n_outside >= 0 &&
+                  (sigma == 1 || sigma == -1), "bad extent");
+  const int64_t n_tri = 2 * n_quads + n_outside;
+  OISAT_CHECK_ARG(3 * n_tri < (int64_t)INT_MAX && n_rows * n_cols < (int64_t)INT_MAX, "bad extent");
+  cudaStream_t s = (cudaStream_t)stream;
+  OISAT_CHECK_CUDA(cudaMemsetAsync(half, 0xff, (size_t)(3 * n_tri) * sizeof(int32_t), s));
+  const int64_t work = (n_rows - 1) * (n_cols - 1) + 3 * n_outside;
+  seed_assemble_kernel<<<(unsigned)ceil_div(work, 256), 256, 0, s>>>(
+      qtri, n_rows, n_cols, sigma, otri, ohalf, 3 * n_outside, 6 * n_quads, tri, half);
+  OISAT_CHECK_LAUNCH();
+  return OISAT_OK;
+}
+
+// workspace: [owner u64 n][cand i32 3n][n_listed u32 R][n_marked u32 R] (zeroed) |
+//            [stamp i32 n] (set to -1) | [tri_list 2 x i32 n][edge_list i32 3n/2+1]
+extern "C" int64_t oisat_flip_workspace_bytes(int64_t n_tri) {
+  if (n_tri < 0) return OISAT_E_ARG;
+  return 8 * n_tri + 12 * n_tri + 8 * (int64_t)kMaxRounds + 4 * n_tri + 8 * n_tri +
+         4 * (3 * n_tri / 2 + 1) + 64;
+}
+
+extern "C" int oisat_flip_delaunay(int32_t* tri, int32_t* half, int64_t n_tri, const void* px,
+                                   const void* py, int32_t coord_dtype, void* workspace,
+                                   uint64_t* result, void* stream) {
+  OISAT_CHECK_ARG(result != nullptr, "null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  OISAT_CHECK_CUDA(cudaMemsetAsync(result, 0, 4 * sizeof(uint64_t), s));
+  if (n_tri <= 0) return OISAT_OK;
+  OISAT_CHECK_ARG(tri && half && px && py && workspace, "null pointer");
+  OISAT_CHECK_ARG(coord_dtype == OISAT_F32 || coord_dtype == OISAT_F64, "coords must be f32/f64");
+  OISAT_CHECK_ARG(3 * n_tri < (int64_t)INT_MAX, "bad extent");
+  char* w = (char*)workspace;
+  const int64_t zeroed = 20 * n_tri + 8 * (int64_t)kMaxRounds;
+  oisat_flip::Mesh m;
+  m.tri = tri;
+  m.half = half;
+  m.n_half = 3 * n_tri;
+  m.owner = (unsigned long long*)w;
+  m.cand = (int32_t*)(w + 8 * n_tri);
+  m.n_listed = (unsigned int*)(w + 20 * n_tri);
+  m.n_marked = m.n_listed + kMaxRounds;
+  m.stamp = (int32_t*)(w + zeroed);
+  m.tri_list[0] = m.stamp + n_tri;
+  m.tri_list[1] = m.stamp + 2 * n_tri;
+  m.edge_list = m.stamp + 3 * n_tri;
+  OISAT_CHECK_CUDA(cudaMemsetAsync(w, 0, (size_t)zeroed, s));
+  OISAT_CHECK_CUDA(cudaMemsetAsync(m.stamp, 0xff, (size_t)(4 * n_tri), s));
+  static int sm_count = 0, per_sm_f = 0, per_sm_d = 0;
+  if (!sm_count) {
+    int dev = 0;
+    OISAT_CHECK_CUDA(cudaGetDevice(&dev));
+    OISAT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, flip_rounds_kernel<float>, 512, 0));
+    OISAT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, flip_rounds_kernel<double>, 512, 0));
+    OISAT_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int max_rounds = kMaxRounds;
+  unsigned int tail = 2048;
+  if (const char* e = getenv("OISAT_FLIP_TAIL")) tail = (unsigned int)atoi(e);
+  unsigned long long* res = (unsigned long long*)result;
+  const int per_sm = coord_dtype == OISAT_F32 ? per_sm_f : per_sm_d;
+  OISAT_CHECK_ARG(per_sm >= 1, "flip kernel does not fit an SM");
+  // one block per SM at most (a grid barrier costs with the number of blocks), and no more
+  // blocks than there is work for in the first round
+  int64_t blocks = sm_count;
+  const int64_t want = ceil_div(m.n_half, 4 * 512);
+  if (blocks > want) blocks = want;
+  FlipCoords<float> Pf{(const float*)px, (const float*)py};
+  FlipCoords<double> Pd{(const double*)px, (const double*)py};
+  void* args_f[] = {&m, &Pf, &max_rounds, &tail, &res};
+  void* args_d[] = {&m, &Pd, &max_rounds, &tail, &res};
+  if (coord_dtype == OISAT_F32)
+    OISAT_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)flip_rounds_kernel<float>, dim3((unsigned)blocks),
+                                                 dim3(512), args_f, 0, s));
+  else
+    OISAT_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)flip_rounds_kernel<double>, dim3((unsigned)blocks),
+                                                 dim3(512), args_d, 0, s));
+  OISAT_CHECK_LAUNCH();
+  const unsigned cblocks = (unsigned)ceil_div(m.n_half, 256);
+  if (coord_dtype == OISAT_F32)
+    flip_check_kernel<float><<<cblocks, 256, 0, s>>>(tri, half, m.n_half, Pf, res);
+  else
+    flip_check_kernel<double><<<cblocks, 256, 0, s>>>(tri, half, m.n_half, Pd, res);
+  OISAT_CHECK_LAUNCH();
+  return OISAT_OK;
+}

@@ -334,6 +334,80 @@ def native_delaunay_adj(lon, lat, pinned=False, device_index=None):
     return tri[:nt], half[:nt], int(ties.value), maxabs
 
 
+def _seed_mode():
+    """OISAT_DELAUNAY=device (default): structured swaths are triangulated by K12 -- host seed
+    parts + flips on the device; host: the incremental swath builder; general: the sweep-hull."""
+    import os
+    return os.environ.get("OISAT_DELAUNAY", "device")
+
+
+def native_seed_parts(lon, lat, pinned=False, device_index=None):
+    """Host share of the device triangulation (oisat_h_delaunay_seed_parts): a dict with the
+    quad table and the triangles outside the lattice, or None when the construction declines
+    (folded lattices, ties on the hull of the seam: the incremental builder serves)."""
+    L = _lib.lib()
+    shape = np.shape(lon)
+    if not (len(shape) == 2 and min(shape) >= 2):
+        return None
+    x = np.ascontiguousarray(np.asarray(lon, dtype=np.float64).ravel())
+    y = np.ascontiguousarray(np.asarray(lat, dtype=np.float64).ravel())
+    n = x.size
+    nq = (shape[0] - 1) * (shape[1] - 1)
+    cap = 2 * n // 3 + 16                       # triangles outside the lattice (seam <= n / 3)
+    if pinned:
+        t = _dev.torch()
+        with t.cuda.device(device_index if device_index is not None else t.cuda.current_device()):
+            buf = t.empty((nq + 6 * cap,), dtype=t.int32, pin_memory=True).numpy()
+    else:
+        buf = np.empty((nq + 6 * cap,), dtype=np.int32)
+    qtri, otri, ohalf = buf[:nq], buf[nq:nq + 3 * cap], buf[nq + 3 * cap:]
+    info = np.zeros(5, dtype=np.int64)
+    nt = L.oisat_h_delaunay_seed_parts(x.ctypes.data, y.ctypes.data, shape[0], shape[1],
+                                       qtri.ctypes.data, otri.ctypes.data, ohalf.ctypes.data, cap,
+                                       info.ctypes.data)
+    if nt <= 0:
+        return None
+    n_out = int(info[2])
+    return dict(qtri=qtri, otri=otri[:3 * n_out], ohalf=ohalf[:3 * n_out], n_quads=int(info[0]),
+                n_outside=n_out, sigma=int(info[3]), n_tri=int(nt), rows=int(shape[0]),
+                cols=int(shape[1]), maxabs=float(max(np.abs(x).max(), np.abs(y).max())))
+
+
+def host_triangulation(lon, lat, pinned=False, device_index=None):
+    """What a pool thread does for one granule: ("seed", parts) when K12 will finish the
+    triangulation on the device, else ("tri", (tri, half, ties, maxabs)) from the host builders."""
+    if _seed_mode() == "device":
+        parts = native_seed_parts(lon, lat, pinned, device_index)
+        if parts is not None:
+            return "seed", parts
+    return "tri", native_delaunay_adj(lon, lat, pinned, device_index)
+
+
+def device_triangulation(parts, lonlat_dev):
+    """Queues K12 for one granule: upload of the seed parts, oisat_seed_assemble,
+    oisat_flip_delaunay.  Returns (tri, half, result) on the device; result[2:4] must be zero
+    (read it after the stream has run) for the triangulation to be the Delaunay one."""
+    L = _lib.lib()
+    t = _dev.torch()
+    dev = _dev.device()
+    s = _dev.stream()
+    lo, la = lonlat_dev
+    nt = parts["n_tri"]
+    qtri = t.from_numpy(parts["qtri"]).to(dev, non_blocking=True)
+    otri = t.from_numpy(parts["otri"]).to(dev, non_blocking=True)
+    ohalf = t.from_numpy(parts["ohalf"]).to(dev, non_blocking=True)
+    tri = _dev.empty((nt, 3), "int32")
+    half = _dev.empty((nt, 3), "int32")
+    _lib.check(L.oisat_seed_assemble(qtri.data_ptr(), parts["rows"], parts["cols"], parts["sigma"],
+                                     parts["n_quads"], otri.data_ptr(), ohalf.data_ptr(),
+                                     parts["n_outside"], tri.data_ptr(), half.data_ptr(), s))
+    work = _dev.empty((int(L.oisat_flip_workspace_bytes(nt)),), "uint8")
+    result = _dev.empty((4,), "int64")
+    _lib.check(L.oisat_flip_delaunay(tri.data_ptr(), half.data_ptr(), nt, lo.data_ptr(), la.data_ptr(),
+                                     _dev.dtype_code(lo), work.data_ptr(), result.data_ptr(), s))
+    return tri, half, result, (qtri, otri, ohalf, work)
+
+
 def locate(tri, qx, qy):
     """Containing simplex and barycentric weights of each query point, evaluated
     the way scipy's LinearNDInterpolator does (qhull._barycentric_coordinates)."""
@@ -410,11 +484,12 @@ def _plan_v0_device(lon, lat, lonlat_dev, gplan, keep_dev):
     return plan
 
 
-def _plan_v1_enqueue(tri_host, lonlat_dev, gplan, keep_dev, half_host=None, maxabs=0.0):
+def _plan_v1_enqueue(tri_host, lonlat_dev, gplan, keep_dev, half_host=None, maxabs=0.0, seed=None):
     """First half of the device part of a v1 plan, queued without waiting for anything:
-    upload of the triangulation, near-tie scan (with `half_host`, native_delaunay_adj),
-    point location (K1), per-cell validity, and the copy of the per-cell flags (n_cell
-    bytes) + tie count to pinned host memory.  Returns the state _plan_v1_finish needs."""
+    upload of the triangulation (or, with `seed`, its construction on the device: K12),
+    near-tie scan (with `half_host`, native_delaunay_adj), point location (K1), per-cell
+    validity, and the copy of the per-cell flags (n_cell bytes) + tie count to pinned host
+    memory.  Returns the state _plan_v1_finish needs."""
     L = _lib.lib()
     t = _dev.torch()
     dev = _dev.device()
@@ -422,10 +497,15 @@ def _plan_v1_enqueue(tri_host, lonlat_dev, gplan, keep_dev, half_host=None, maxa
     xs, ys = gplan.dev_axes()
     window, nn_ok = gplan.dev_tables()
     s = _dev.stream()
-    tri = t.from_numpy(tri_host).to(dev, non_blocking=True)    # asynchronous when pinned
-    ties_dev = tri_flag = None
-    if half_host is not None:
-        half = t.from_numpy(half_host).to(dev, non_blocking=True)
+    ties_dev = tri_flag = flip_dev = half = seed_keep = None
+    if seed is not None:
+        tri, half, flip_dev, seed_keep = device_triangulation(seed, lonlat_dev)
+        maxabs = seed["maxabs"]
+    else:
+        tri = t.from_numpy(tri_host).to(dev, non_blocking=True)    # asynchronous when pinned
+        if half_host is not None:
+            half = t.from_numpy(half_host).to(dev, non_blocking=True)
+    if half is not None:
         ties_dev = _dev.empty((2,), "int64")     # [near ties, kept nodes inside tied quadrilaterals]
         tri_flag = _dev.zeros((tri.shape[0],), "uint8")
         _lib.check(L.oisat_near_ties(tri.data_ptr(), half.data_ptr(), tri.shape[0], lo.data_ptr(),
@@ -450,10 +530,15 @@ def _plan_v1_enqueue(tri_host, lonlat_dev, gplan, keep_dev, half_host=None, maxa
     if ties_dev is not None:
         ties_host = t.empty((2,), dtype=t.int64, pin_memory=True)
         ties_host.copy_(ties_dev, non_blocking=True)
+    flip_host = None
+    if flip_dev is not None:
+        flip_host = t.empty((4,), dtype=t.int64, pin_memory=True)
+        flip_host.copy_(flip_dev, non_blocking=True)
     done = t.cuda.Event()
     done.record()
     return dict(tri=tri, node_tri=node_tri, ok_host=ok_host, ties_host=ties_host, done=done,
-                lonlat=lonlat_dev, code=code, keep=(tri_host, half_host, work, ok, ties_dev, tri_flag))
+                flip_host=flip_host, lonlat=lonlat_dev, code=code,
+                keep=(tri_host, half_host, half, work, ok, ties_dev, tri_flag, seed, seed_keep))
 
 
 def _plan_v1_finish(st, gplan):
@@ -461,6 +546,10 @@ def _plan_v1_finish(st, gplan):
     the stencil fill.  None when the near-tie scan found a tie (the caller takes v0)."""
     L = _lib.lib()
     st["done"].synchronize()
+    if st["flip_host"] is not None:
+        rounds, flips, bad, unsure = (int(v) for v in st["flip_host"])
+        if bad or unsure:        # an edge the filter cannot decide: the exact host builder's job
+            return "host"
     near_ties = affected = 0
     if st["ties_host"] is not None:
         near_ties, affected = int(st["ties_host"][0]), int(st["ties_host"][1])
@@ -484,8 +573,11 @@ def _plan_v1_finish(st, gplan):
                                      st["node_tri"].data_ptr(), st["tri"].data_ptr(), lo.data_ptr(),
                                      la.data_ptr(), st["code"], xs.data_ptr(), gplan.W, ys.data_ptr(), 1,
                                      vert.data_ptr(), w.data_ptr(), _dev.stream()))
-    plan = GranulePlan(gplan, cells, keep=None, dev_pairs=(vert, w), builder="v1")
+    plan = GranulePlan(gplan, cells, keep=None, dev_pairs=(vert, w),
+                       builder="v1d" if st["flip_host"] is not None else "v1")
     plan.near_ties = near_ties
+    if st["flip_host"] is not None:
+        plan.flip_rounds, plan.flips = int(st["flip_host"][0]), int(st["flip_host"][1])
     return plan
 
 
@@ -579,13 +671,24 @@ def granule_plan(lon, lat, gplan: GridPlan, radius: float, lonlat_dev=None, cach
         keep_dev = distance_mask(lonlat_dev[0], lonlat_dev[1], gplan, radius)  # async
         use_v1 = gplan.upscale and _plan_mode() != "v0"
         if use_v1:
-            tri, half, ties, maxabs = native_delaunay_adj(lon, lat)   # runs while K0 is in flight
-            if tri is None:
-                return None
-            if ties == 0 or _plan_mode() == "v1":
-                plan = _plan_v1_device(tri, lonlat_dev, gplan, keep_dev, half, maxabs)
-                if plan is None and _plan_mode() != "v0walk":
-                    plan = _plan_v0_device(lon, lat, lonlat_dev, gplan, keep_dev)   # near tie
+            kind, got = host_triangulation(lon, lat)      # runs while K0 is in flight
+            near_tie = False                               # a v1 plan was refused for a near tie
+            if kind == "seed":
+                plan = _plan_v1_finish(_plan_v1_enqueue(None, lonlat_dev, gplan, keep_dev, seed=got), gplan)
+                if isinstance(plan, str):                  # K12 met an undecidable edge
+                    plan = None
+                    kind, got = "tri", native_delaunay_adj(lon, lat)
+                else:
+                    near_tie = plan is None
+            if kind == "tri":
+                tri, half, ties, maxabs = got
+                if tri is None:
+                    return None
+                if ties == 0 or _plan_mode() == "v1":
+                    plan = _plan_v1_device(tri, lonlat_dev, gplan, keep_dev, half, maxabs)
+                    near_tie = plan is None
+            if near_tie and _plan_mode() != "v0walk":
+                plan = _plan_v0_device(lon, lat, lonlat_dev, gplan, keep_dev)
         if plan is None:
             plan = _plan_v0(lon, lat, gplan, _dev.to_host(keep_dev).astype(bool))
     if plan is not None and cache:
@@ -648,22 +751,37 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
     trace = [] if os.environ.get("OISAT_PLAN_TRACE") == "1" else None
     t_start = _time.perf_counter()
     dev_index = _dev.device().index
-    futures = {ex.submit(native_delaunay_adj, lons[i], lats[i], True, dev_index): i for i in range(n)}
+    futures = {ex.submit(host_triangulation, lons[i], lats[i], True, dev_index): i for i in range(n)}
     for fut in as_completed(futures):
         i = futures[fut]
-        tri, half, ties, maxabs = fut.result()
-        if tri is None:
-            continue
-        if ties == 0 or _plan_mode() == "v1":
-            t_a = _time.perf_counter()
-            pending.append((i, _plan_v1_enqueue(tri, lonlat_dev[i], gplan, keeps[i], half, maxabs)))
-            if trace is not None:
-                trace.append("%d:%.0f+%.1f" % (i, (t_a - t_start) * 1e3, (_time.perf_counter() - t_a) * 1e3))
+        kind, got = fut.result()
+        t_a = _time.perf_counter()
+        if kind == "seed":       # K12 finishes the triangulation on the device
+            pending.append((i, _plan_v1_enqueue(None, lonlat_dev[i], gplan, keeps[i], None, 0.0, got)))
         else:
-            out[i] = _plan_v0(lons[i], lats[i], gplan, _dev.to_host(keeps[i]).astype(bool))
+            tri, half, ties, maxabs = got
+            if tri is None:
+                continue
+            if ties == 0 or _plan_mode() == "v1":
+                pending.append((i, _plan_v1_enqueue(tri, lonlat_dev[i], gplan, keeps[i], half, maxabs)))
+            else:
+                out[i] = _plan_v0(lons[i], lats[i], gplan, _dev.to_host(keeps[i]).astype(bool))
+                continue
+        if trace is not None:
+            trace.append("%d:%.0f+%.1f" % (i, (t_a - t_start) * 1e3, (_time.perf_counter() - t_a) * 1e3))
     t_pool = _time.perf_counter()
     for i, st in pending:     # second half: kept cells on the host, stencil fill queued
         out[i] = _plan_v1_finish(st, gplan)
+        if isinstance(out[i], str):      # K12 met an edge its filter cannot decide: exact builder
+            tri, half, ties, maxabs = native_delaunay_adj(lons[i], lats[i])
+            out[i] = None
+            if tri is None:
+                continue
+            if ties == 0 or _plan_mode() == "v1":
+                out[i] = _plan_v1_device(tri, lonlat_dev[i], gplan, keeps[i], half, maxabs)
+            else:
+                out[i] = _plan_v0(lons[i], lats[i], gplan, _dev.to_host(keeps[i]).astype(bool))
+                continue
         if out[i] is None and _plan_mode() != "v0walk":      # near tie: Qhull's triangles, K1's walk
             out[i] = _plan_v0_device(lons[i], lats[i], lonlat_dev[i], gplan, keeps[i])
         if out[i] is None:

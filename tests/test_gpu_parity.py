@@ -351,6 +351,91 @@ def test_near_tie_scan_on_the_device_equals_the_host_scan():
             assert int(cnt.item()) == n_flag
 
 
+def test_device_triangulation_equals_the_host_builders(monkeypatch):
+    """K12 (oisat_seed_assemble + oisat_flip_delaunay): the assembled seed is the host
+    assembly bit for bit; after the rounds, `tri` / `half` are bit-identical to the serial
+    replay of the same rounds on the host (the set of flips of a round does not depend on
+    the order the threads ran in), no edge is left undecided, and the triangle set is the
+    incremental builder's; float32 and float64 coordinates; with the grid-wide rounds only,
+    with block 0's tail from the start, and the default mix."""
+    from oisatgmi_b200 import _dev, _lib, plan
+    from test_host_logic import _seed_swaths, _seed_whole, _flip_rounds, _tri_set
+    L = _lib.lib()
+    t = _dev.torch()
+    done = 0
+    for k, (lon, lat) in enumerate(_seed_swaths()):
+        for dt in (np.float64, np.float32):
+            lo, la = lon.astype(dt), lat.astype(dt)
+            parts = plan.native_seed_parts(lo, la)
+            if parts is None:
+                continue
+            seed = _seed_whole(lo.astype(np.float64), la.astype(np.float64))
+            d_lo, d_la = _dev.to_device(lo.ravel()), _dev.to_device(la.ravel())
+            # the seed alone
+            nt = parts["n_tri"]
+            d_tri, d_half = _dev.empty((nt, 3), "int32"), _dev.empty((nt, 3), "int32")
+            q, ot, oh = (_dev.to_device(np.ascontiguousarray(parts[n])) for n in ("qtri", "otri", "ohalf"))
+            _lib.check(L.oisat_seed_assemble(q.data_ptr(), parts["rows"], parts["cols"], parts["sigma"],
+                                             parts["n_quads"], ot.data_ptr(), oh.data_ptr(),
+                                             parts["n_outside"], d_tri.data_ptr(), d_half.data_ptr(),
+                                             _dev.stream()))
+            assert np.array_equal(d_tri.cpu().numpy(), seed[0]) and np.array_equal(d_half.cpu().numpy(), seed[1])
+            h_tri, h_half = seed[0].copy(), seed[1].copy()
+            want = _flip_rounds(lo.astype(np.float64), la.astype(np.float64), h_tri, h_half)
+            ref, ties, path = plan.native_delaunay_path(lo, la)
+            for tail in ("0", "1000000000", None):
+                if tail is None:
+                    monkeypatch.delenv("OISAT_FLIP_TAIL", raising=False)
+                else:
+                    monkeypatch.setenv("OISAT_FLIP_TAIL", tail)
+                tri, half, res, _keep = plan.device_triangulation(parts, (d_lo, d_la))
+                t.cuda.synchronize()
+                res = res.cpu().numpy()
+                assert list(res) == list(want), (k, dt, tail, res, want)
+                assert res[2] == 0 and res[3] == 0
+                assert np.array_equal(tri.cpu().numpy(), h_tri) and np.array_equal(half.cpu().numpy(), h_half)
+            assert _tri_set(tri.cpu().numpy()) == _tri_set(ref)
+            done += 1
+    assert done >= 12
+
+
+def test_plans_from_the_device_triangulation_equal_the_host_ones(monkeypatch):
+    """granule_plans with OISAT_DELAUNAY=device (K12) against OISAT_DELAUNAY=host (incremental
+    builder): same kept cells; the same stencil per cell up to the rotation of a triangle's
+    vertices (weights to 1e-12); builder tag 'v1d'.  Full OMI-sized granules, one of them
+    crossing the date line."""
+    from oisatgmi_b200 import plan
+    import synth
+    coords = synth.ctm_coordinates()
+    gplan = plan.grid_plan(coords, 0.25)
+    lons, lats = [], []
+    for node in (10.0, 175.0, -120.0):
+        lat, lon = synth.swath_geolocation(1644, 60, node_lon_deg=node)[:2]
+        lons.append(lon)
+        lats.append(lat)
+    out = {}
+    for mode in ("device", "host"):
+        monkeypatch.setenv("OISAT_DELAUNAY", mode)
+        plan.clear_caches()
+        gplan = plan.grid_plan(coords, 0.25)
+        out[mode] = plan.granule_plans(lons, lats, gplan, 2 * 0.25)
+    for a, b in zip(out["device"], out["host"]):
+        assert a is not None and b is not None
+        assert a.builder == "v1d" and b.builder == "v1", (a.builder, b.builder)
+        assert a.flips > 1000 and a.flip_rounds < 400
+        assert np.array_equal(a.cells, b.cells)
+        va, wa = a.vert.reshape(len(a.cells), -1, 3), a.w.reshape(len(a.cells), -1, 3)
+        vb, wb = b.vert.reshape(len(b.cells), -1, 3), b.w.reshape(len(b.cells), -1, 3)
+        ia, ib = np.argsort(va, axis=2, kind="stable"), np.argsort(vb, axis=2, kind="stable")
+        va, wa = np.take_along_axis(va, ia, 2), np.take_along_axis(wa, ia, 2)
+        vb, wb = np.take_along_axis(vb, ib, 2), np.take_along_axis(wb, ib, 2)
+        same = (va == vb).all(axis=2)
+        # a mesh node exactly on an edge may sit in either triangle: its weight for the
+        # vertex that differs is 0 within rounding
+        assert same.mean() > 0.9999
+        np.testing.assert_allclose(wa[same], wb[same], rtol=0, atol=1e-12)
+
+
 def test_knee_on_the_device_equals_the_host_kneedle():
     """oisat_oi_knee (one thread on the device) against kneedle.knee_index on saturating
     curves with and without wiggles (several local maxima of the difference curve), curves

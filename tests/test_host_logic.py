@@ -337,6 +337,167 @@ def test_lattice_delaunay_randomised_against_qhull():
     assert checked >= 40
 
 
+def _seed_whole(x, y, flags=0):
+    """oisat_h_delaunay_seed on a 2-D lattice: (tri, half, info) or None when it declines."""
+    import ctypes as C
+    L = _lib.lib()
+    xs, ys = np.ascontiguousarray(x.ravel(), dtype=np.float64), np.ascontiguousarray(y.ravel(), dtype=np.float64)
+    n = xs.size
+    tri, half = np.empty((2 * n, 3), np.int32), np.empty((2 * n, 3), np.int32)
+    info, ties = np.zeros(5, np.int64), C.c_int64(0)
+    nt = L.oisat_h_delaunay_seed(xs.ctypes.data, ys.ctypes.data, x.shape[0], x.shape[1], tri.ctypes.data,
+                                 2 * n, half.ctypes.data, C.byref(ties), flags, info.ctypes.data)
+    assert nt >= 0
+    return (tri[:nt].copy(), half[:nt].copy(), info) if nt else None
+
+
+def _flip_rounds(x, y, tri, half, max_rounds=4096):
+    L = _lib.lib()
+    xs, ys = np.ascontiguousarray(x.ravel(), dtype=np.float64), np.ascontiguousarray(y.ravel(), dtype=np.float64)
+    res = np.zeros(4, np.int64)
+    assert L.oisat_h_flip_rounds(xs.ctypes.data, ys.ctypes.data, tri.ctypes.data, half.ctypes.data,
+                                 len(tri), max_rounds, res.ctypes.data) == 0
+    return res
+
+
+def _assemble_numpy(parts):
+    """What oisat_seed_assemble does (k12_flip.cu), thread by thread, in numpy."""
+    rows, cols, sg, base = parts["rows"], parts["cols"], parts["sigma"], 6 * parts["n_quads"]
+    qc = cols - 1
+    nt = parts["n_tri"]
+    tri, half = np.full(3 * nt, -1, np.int32), np.full(3 * nt, -1, np.int32)
+    q = parts["qtri"].reshape(rows - 1, qc)
+
+    def slot(t, side):
+        t0, t1 = 3 * t, 3 * t + 3
+        return ((t0, t0 + 2, t1, t1 + 1) if sg > 0 else (t0 + 2, t0, t1 + 2, t1 + 1))[side]
+    for r in range(rows - 1):
+        for c in range(qc):
+            t = q[r, c]
+            if t < 0:
+                continue
+            a = r * cols + c
+            b, cc, d = a + 1, a + cols, a + cols + 1
+            t0, t1 = 3 * t, 3 * t + 3
+            if sg > 0:
+                tri[t0:t0 + 6] = (a, b, cc, b, d, cc)
+                half[t0 + 1], half[t1 + 2] = t1 + 2, t0 + 1
+            else:
+                tri[t0:t0 + 6] = (a, cc, b, b, cc, d)
+                half[t0 + 1], half[t1] = t1, t0 + 1
+            if r > 0 and q[r - 1, c] >= 0:
+                half[slot(t, 0)] = slot(q[r - 1, c], 3)
+            if c > 0 and q[r, c - 1] >= 0:
+                half[slot(t, 1)] = slot(q[r, c - 1], 2)
+            if c + 1 < qc and q[r, c + 1] >= 0:
+                half[slot(t, 2)] = slot(q[r, c + 1], 1)
+            if r + 2 < rows and q[r + 1, c] >= 0:
+                half[slot(t, 3)] = slot(q[r + 1, c], 0)
+    for j in range(3 * parts["n_outside"]):
+        tri[base + j] = parts["otri"][j]
+        g = parts["ohalf"][j]
+        half[base + j] = g
+        if 0 <= g < base:
+            half[g] = base + j
+    return tri.reshape(-1, 3), half.reshape(-1, 3)
+
+
+def _seed_swaths():
+    rng = np.random.default_rng(5)
+    swaths = []
+    for geo in (synth.regional_geo(cases.REGION),                       # mid-latitude piece
+                dict(node_lon_deg=172.0, u0_deg=10, u1_deg=25),         # date-line crossing
+                dict(node_lon_deg=179.0, u0_deg=-40, u1_deg=40),        # running along the date line
+                dict(node_lon_deg=30.0, u0_deg=60, u1_deg=120)):        # over the pole: lat turns round
+        lat, lon = synth.swath_geolocation(150, 40, rng=rng, **geo)
+        swaths.append((lon.astype(np.float64), lat.astype(np.float64)))
+    lon, lat = swaths[0]
+    swaths.append((lon[:, ::-1].copy(), lat[:, ::-1].copy()))           # mirrored handedness
+    swaths.append((lon.T.copy(), lat.T.copy()))                         # long axis second
+    swaths.append((lon.astype(np.float32).astype(np.float64), lat.astype(np.float32).astype(np.float64)))
+    gx, gy = np.meshgrid(np.arange(23.0), np.arange(17.0))              # jittered regular lattice
+    swaths.append((gx + rng.uniform(-0.3, 0.3, gx.shape), gy + rng.uniform(-0.3, 0.3, gy.shape)))
+    return swaths
+
+
+def test_lattice_seed_plus_flip_rounds_is_the_delaunay_triangulation():
+    """K12's construction without a device: the seed (oisat_h_delaunay_seed: lattice quads +
+    exact triangulation of the seam) is a valid triangulation of the hull with consistent twin
+    pointers; the rounds of independent flips (oisat_h_flip_rounds, the device's per-edge code
+    run serially) end with no undecided edge and give the incremental builder's triangle set;
+    serial Lawson flips (flags bit 0) give the same; the PARTS the device receives assemble
+    (numpy model of oisat_seed_assemble) to the very arrays of the host assembly."""
+    seeded = 0
+    for lon, lat in _seed_swaths():
+        ref, ties, path = plan.native_delaunay_path(lon, lat)
+        got = _seed_whole(lon, lat)
+        if got is None:
+            continue
+        seeded += 1
+        tri, half, info = got
+        assert len(tri) == len(ref) and _valid_triangulation(lon.ravel(), lat.ravel(), tri)
+        h, t = half.ravel(), tri.ravel()
+        inner = np.flatnonzero(h >= 0)
+        nxt = lambda e: e - e % 3 + (e + 1) % 3   # noqa: E731
+        assert np.array_equal(h[h[inner]], inner)
+        assert np.array_equal(t[inner], t[nxt(h[inner])]) and np.array_equal(t[nxt(inner)], t[h[inner]])
+        parts = plan.native_seed_parts(lon, lat)
+        assert parts is not None and parts["n_tri"] == len(tri)
+        atri, ahalf = _assemble_numpy(parts)
+        assert np.array_equal(atri, tri) and np.array_equal(ahalf, half)
+        res = _flip_rounds(lon, lat, tri, half)
+        assert res[2] == 0 and res[3] == 0 and res[0] < 400, res
+        assert _tri_set(tri) == _tri_set(ref), lon.shape
+        h = half.ravel()
+        inner = np.flatnonzero(h >= 0)
+        assert np.array_equal(h[h[inner]], inner)
+        law = _seed_whole(lon, lat, flags=1)
+        assert _tri_set(law[0]) == _tri_set(ref) and abs(law[2][3] - res[1]) <= 0.01 * res[1]
+    assert seeded >= 6
+
+
+def test_lattice_seed_declines_or_is_exact_on_random_lattices():
+    """The randomised lattice sweep of the incremental builder's test (warps, shears, folds,
+    float32 coordinates): the seed either declines (folds, repeated points) or, with the
+    replayed rounds, reproduces the incremental builder's triangulation; an exactly regular
+    lattice (co-circular quads everywhere) is reported as undecidable, never as Delaunay."""
+    rng = np.random.default_rng(2024)
+    done = 0
+    for trial in range(40):
+        rows, cols = int(rng.integers(2, 41)), int(rng.integers(2, 24))
+        i, j = np.meshgrid(np.arange(rows, dtype=np.float64), np.arange(cols, dtype=np.float64), indexing="ij")
+        ax, ay = rng.uniform(0.05, 3.0, 2)
+        x = ax * j + rng.uniform(-1.5, 1.5) * i
+        y = ay * i + rng.uniform(-0.5, 0.5) * j
+        amp = rng.uniform(0.0, 0.45) * min(ax, ay)
+        x = x + amp * np.sin(0.9 * i + rng.uniform(0, 6)) * np.cos(0.7 * j)
+        y = y + amp * np.cos(0.8 * j + rng.uniform(0, 6))
+        if trial % 5 == 0:
+            y = np.abs(y - 0.6 * y.max()) + 0.013 * i
+        x = x + rng.uniform(-1e-3, 1e-3, x.shape)
+        y = y + rng.uniform(-1e-3, 1e-3, y.shape)
+        got = _seed_whole(x, y)
+        if got is None:
+            continue
+        tri, half, info = got
+        assert _valid_triangulation(x.ravel(), y.ravel(), tri), trial
+        res = _flip_rounds(x, y, tri, half)
+        ref, ties, path = plan.native_delaunay_path(x, y)
+        if ties == 0 and res[3] == 0:
+            assert res[2] == 0 and _tri_set(tri) == _tri_set(ref), trial
+            done += 1
+    assert done >= 15
+    gx, gy = np.meshgrid(np.arange(13.0), np.arange(9.0))
+    got = _seed_whole(gx, gy)
+    if got is not None:
+        res = _flip_rounds(gx, gy, got[0], got[1])
+        assert res[3] > 0 and res[2] == 0
+    # a cut-off run says so
+    lon, lat = _seed_swaths()[0]
+    tri, half, _ = _seed_whole(lon, lat)
+    assert _flip_rounds(lon, lat, tri, half, max_rounds=2)[2] > 0
+
+
 def _near_ties_numpy(x, y, tri, half):
     """count_near_ties (csrc/delaunay.cpp) restated with numpy from (tri, half)."""
     x = np.asarray(x, np.float64).ravel()
@@ -417,6 +578,7 @@ def test_granule_plans_routes_ties_and_failures(monkeypatch):
     monkeypatch.setattr(plan, "distance_mask", lambda lo, la, g, r: np.ones(4, np.uint8))
     monkeypatch.setattr(plan, "native_delaunay_adj", fake_adj)
     monkeypatch.setattr(plan, "_plan_v1_enqueue", lambda tri, ll, g, keep, half, m: dict(kind=int(np.ravel(ll[0])[0])))
+    monkeypatch.setenv("OISAT_DELAUNAY", "host")
     monkeypatch.setattr(plan, "_plan_v1_finish", lambda st, g: None if st["kind"] == 2 else ("v1", st["kind"]))
     monkeypatch.setattr(plan, "_plan_v0", lambda lon, lat, g, keep: calls.append(int(lon[0, 0])) or ("v0", int(lon[0, 0])))
     monkeypatch.setenv("OISAT_PLAN", "auto")
