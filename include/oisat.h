@@ -142,6 +142,18 @@ int oisat_seed_assemble(const int32_t* qtri, int64_t n_rows, int64_t n_cols, int
                         int64_t n_quads, const int32_t* otri, const int32_t* ohalf,
                         int64_t n_outside, int32_t* tri, int32_t* half, void* stream);
 int64_t oisat_flip_workspace_bytes(int64_t n_tri);
+/* several meshes (the granules of a day) through the rounds together -- a round costs two
+ * barriers whatever it holds; items: HOST array; workspace: oisat_flip_workspace_bytes of the
+ * total triangle count; result[4 * n_items], rounds and flips being those of the batch */
+typedef struct oisat_flip_item {
+  int32_t* tri;
+  int32_t* half;
+  int64_t n_tri;
+  const void* px;
+  const void* py;
+} oisat_flip_item;
+int oisat_flip_delaunay_batch(const oisat_flip_item* items, int32_t n_items, int32_t coord_dtype,
+                              void* workspace, uint64_t* result, void* stream);
 int oisat_flip_delaunay(int32_t* tri, int32_t* half, int64_t n_tri, const void* px,
                         const void* py, int32_t coord_dtype, void* workspace, uint64_t* result,
                         void* stream);

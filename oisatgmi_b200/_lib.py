@@ -44,6 +44,11 @@ class FusedArgs(C.Structure):
     ]
 
 
+class FlipItem(C.Structure):
+    """struct oisat_flip_item"""
+    _fields_ = [("tri", vp), ("half", vp), ("n_tri", i64), ("px", vp), ("py", vp)]
+
+
 class PackItem(C.Structure):
     """struct oisat_pack_item"""
     _fields_ = [("sw", vp), ("p_mid", vp), ("vcd", vp), ("sigma", vp), ("trop", vp), ("qflag", vp),
@@ -65,6 +70,7 @@ PROTOTYPES = {
     "oisat_seed_assemble": (C.c_int, [vp, i64, i64, i32, i64, vp, vp, i64, vp, vp, vp]),
     "oisat_flip_workspace_bytes": (i64, [i64]),
     "oisat_flip_delaunay": (C.c_int, [vp, vp, i64, vp, vp, i32, vp, vp, vp]),
+    "oisat_flip_delaunay_batch": (C.c_int, [vp, i32, i32, vp, vp, vp]),
     "oisat_near_ties": (C.c_int, [vp, vp, i64, vp, vp, i32, f64, vp, vp, vp]),
     "oisat_flagged_nodes": (C.c_int, [vp, i64, vp, vp, vp]),
     "oisat_locate": (C.c_int, [vp, i64, vp, vp, i32, vp, i64, vp, i64, vp, vp, vp, vp]),

@@ -676,8 +676,8 @@ extern "C" int oisat_h_flip_rounds(const double* h_x, const double* h_y, int32_t
       list0((size_t)n_tri), list1((size_t)n_tri), edges((size_t)(3 * n_tri / 2 + 1));
   std::vector<unsigned long long> owner((size_t)n_tri, 0ull);
   std::vector<unsigned int> n_listed((size_t)max_rounds, 0u), n_marked((size_t)max_rounds, 0u);
-  oisat_flip::Mesh m{h_tri, h_half, 3 * n_tri, stamp.data(), cand.data(), owner.data(),
-                     {list0.data(), list1.data()}, edges.data(), n_listed.data(), n_marked.data()};
+  oisat_flip::Mesh m{h_tri, h_half, 3 * n_tri, stamp.data(), cand.data(), owner.data(), 0};
+  oisat_flip::Lists l{{list0.data(), list1.data()}, edges.data(), n_listed.data(), n_marked.data()};
   auto P = [&](int v, int axis) { return axis ? h_y[v] : h_x[v]; };
   struct HostOps {
     unsigned long long max(unsigned long long* p, unsigned long long v) const {
@@ -692,14 +692,14 @@ extern "C" int oisat_h_flip_rounds(const double* h_x, const double* h_y, int32_t
   for (; round < max_rounds; ++round) {
     const int r = (int)round;
     if (r == 0)
-      for (int64_t e = 0; e < m.n_half; ++e) oisat_flip::mark_edge(m, (int32_t)e, r, P, ops);
+      for (int64_t e = 0; e < m.n_half; ++e) oisat_flip::mark_edge(m, l, (int32_t)e, r, P, ops);
     else
       for (unsigned int i = 0; i < n_listed[(size_t)r - 1]; ++i) {
         const int32_t t = ((r & 1) ? list1 : list0)[i];
-        for (int e = 0; e < 3; ++e) oisat_flip::mark_edge(m, 3 * t + e, r, P, ops);
+        for (int e = 0; e < 3; ++e) oisat_flip::mark_edge(m, l, 3 * t + e, r, P, ops);
       }
     for (unsigned int i = 0; i < n_marked[(size_t)r]; ++i)
-      flips += oisat_flip::apply_edge(m, edges[i], r, ops);
+      flips += oisat_flip::apply_edge(m, l, edges[i], r, ops);
     if (n_marked[(size_t)r] == 0) { ++round; break; }
   }
   int64_t bad = 0, unsure = 0;

@@ -74,15 +74,19 @@ OISAT_FLIP_HD unsigned long long claim_key(int round, int a) {
          (unsigned long long)scramble((unsigned)a, (unsigned)round);
 }
 
-struct Mesh {
+struct Mesh {                   // one granule; every index in these arrays is local to it
   int32_t* tri;                 // 3 per triangle, counter-clockwise
   int32_t* half;                // twin half-edge, -1 on the hull
   int64_t n_half;               // 3 * triangles
   int32_t* stamp;               // per triangle: last round that changed it (-1 at the start)
   int32_t* cand;                // per half-edge: round + 1 in which it was last marked
   unsigned long long* owner;    // per triangle: highest claim
-  int32_t* tri_list[2];         // triangles to look at in round r: tri_list[r & 1], n_tri each
-  int32_t* edge_list;           // edges marked in the current round, n_half / 2 + 1
+  int32_t tri_base;             // number of its first triangle in the batch (the lists' numbering)
+};
+
+struct Lists {                  // work lists of a batch of meshes that go through the rounds together
+  int32_t* tri_list[2];         // triangles to look at in round r: tri_list[r & 1]
+  int32_t* edge_list;           // edges marked in the current round (at most half of the half-edges)
   unsigned int* n_listed;       // per round r: triangles listed FOR round r + 1
   unsigned int* n_marked;       // per round r: edges marked
 };
@@ -93,7 +97,8 @@ struct Mesh {
 
 // edge e of a listed triangle (or any half-edge in round 0)
 template <class Coords, class Ops>
-OISAT_FLIP_HD void mark_edge(const Mesh& m, int32_t e, int round, const Coords& P, const Ops& ops) {
+OISAT_FLIP_HD void mark_edge(const Mesh& m, const Lists& l, int32_t e, int round, const Coords& P,
+                             const Ops& ops) {
   const int32_t b = m.half[e];
   if (b < 0) return;
   // an edge between two listed triangles is the lower half-edge's (everything is listed in round 0)
@@ -110,31 +115,31 @@ OISAT_FLIP_HD void mark_edge(const Mesh& m, int32_t e, int round, const Coords& 
   if (n1 >= 0) ops.max(&m.owner[n1 / 3], key);
   if (n2 >= 0) ops.max(&m.owner[n2 / 3], key);
   m.cand[ia] = round + 1;
-  m.edge_list[ops.add(&m.n_marked[round], 1u)] = ia;
+  l.edge_list[ops.add(&l.n_marked[round], 1u)] = ia + 3 * m.tri_base;
 }
 
 template <class Ops>
-OISAT_FLIP_HD void touch(const Mesh& m, int t, int round, const Ops& ops) {
+OISAT_FLIP_HD void touch(const Mesh& m, const Lists& l, int t, int round, const Ops& ops) {
   if (ops.exch(&m.stamp[t], round) != round)
-    ((round & 1) ? m.tri_list[0] : m.tri_list[1])[ops.add(&m.n_listed[round], 1u)] = t;
+    ((round & 1) ? l.tri_list[0] : l.tri_list[1])[ops.add(&l.n_listed[round], 1u)] = t + m.tri_base;
 }
 
-// returns 1 when the marked edge a was flipped.  Nothing of a triangle is read before its
-// ownership is established: the owner of a triangle may be rewriting it in this very step
-// (half[a] can even become -1 under a loser's feet).  A marked edge that loses lists its own
-// triangle, so that it is tested again in the next round although nothing around it may
-// have changed.
+// returns 1 when the marked edge ia (local number) was flipped.  Nothing of a triangle is read
+// before its ownership is established: the owner of a triangle may be rewriting it in this
+// very step (half[a] can even become -1 under a loser's feet).  A marked edge that loses
+// lists its own triangle, so that it is tested again in the next round although nothing
+// around it may have changed.
 template <class Ops>
-OISAT_FLIP_HD int apply_edge(const Mesh& m, int32_t ia, int round, const Ops& ops) {
+OISAT_FLIP_HD int apply_edge(const Mesh& m, const Lists& l, int32_t ia, int round, const Ops& ops) {
   const unsigned long long key = claim_key(round, ia);
   const int ta = ia / 3;
-  if (m.owner[ta] != key) { touch(m, ta, round, ops); return 0; }
+  if (m.owner[ta] != key) { touch(m, l, ta, round, ops); return 0; }
   const int32_t b = m.half[ia];
-  if (m.owner[b / 3] != key) { touch(m, ta, round, ops); return 0; }
+  if (m.owner[b / 3] != key) { touch(m, l, ta, round, ops); return 0; }
   const int ar = prv(ia), bl = prv(b);
   const int32_t hbl = m.half[bl], har = m.half[ar];
   if ((hbl >= 0 && m.owner[hbl / 3] != key) || (har >= 0 && m.owner[har / 3] != key)) {
-    touch(m, ta, round, ops);
+    touch(m, l, ta, round, ops);
     return 0;
   }
   const int32_t p0 = m.tri[ar], p1 = m.tri[bl];
@@ -146,8 +151,8 @@ OISAT_FLIP_HD int apply_edge(const Mesh& m, int32_t ia, int round, const Ops& op
   if (har >= 0) m.half[har] = b;
   m.half[ar] = bl;
   m.half[bl] = ar;
-  touch(m, ta, round, ops);
-  touch(m, b / 3, round, ops);
+  touch(m, l, ta, round, ops);
+  touch(m, l, b / 3, round, ops);
   return 1;
 }
 

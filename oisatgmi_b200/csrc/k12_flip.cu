@@ -91,39 +91,63 @@ seed_assemble_kernel(const int32_t* __restrict__ qtri, int64_t rows, int64_t col
   if (g >= 0 && g < base) half[g] = (int32_t)(base + j);
 }
 
+// A batch of meshes (the granules of a day) goes through the rounds together: a round costs
+// two barriers and a chain of dependent loads whatever the number of edges in it, so fifteen
+// granules cost what one costs.  The table is a kernel parameter (constant bank).
+constexpr int kMaxBatch = 32;
+constexpr int kMaxRounds = 4096;
+
+struct Batch {
+  int n;
+  int32_t tri_end[kMaxBatch];        // running total of triangles: mesh g owns [tri_end[g-1], tri_end[g])
+  oisat_flip::Mesh mesh[kMaxBatch];
+  const void* x[kMaxBatch];
+  const void* y[kMaxBatch];
+};
+
+__device__ __forceinline__ int mesh_of(const Batch& b, int32_t t) {
+  int g = 0;
+  while (g + 1 < b.n && t >= b.tri_end[g]) ++g;
+  return g;
+}
+
 // The rounds.  While a round has more than `tail` triangles to look at, the whole grid works
 // on it (two grid barriers per round); the long tail of short rounds -- an OMI granule needs
-// ~97 rounds, 80 of them with fewer than 500 flips -- is run by block 0 alone with block
-// barriers, the other blocks leave.  result[0] = rounds run, result[1] = flips.
+// ~80-100 rounds, most of them with fewer than 500 flips -- is run by block 0 alone with block
+// barriers, the other blocks leave.  result[0] = rounds run, result[1] = flips (whole batch).
 template <typename T>
 __global__ void __launch_bounds__(512)
-flip_rounds_kernel(oisat_flip::Mesh m, FlipCoords<T> P, int max_rounds, unsigned int tail,
-                   unsigned long long* __restrict__ result) {
+flip_rounds_kernel(const __grid_constant__ Batch b, oisat_flip::Lists l, int max_rounds,
+                   unsigned int tail, unsigned long long* __restrict__ result) {
   cg::grid_group grid = cg::this_grid();
   int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   const DeviceOps ops;
+  const int64_t n_tri = b.tri_end[b.n - 1];
   bool solo = gridDim.x == 1;
   int round = 0;
   unsigned int flips = 0;
   for (; round < max_rounds; ++round) {
-    if (round == 0) {
-      for (int64_t e = tid; e < m.n_half; e += nthreads) oisat_flip::mark_edge(m, (int32_t)e, 0, P, ops);
-    } else {
-      const int64_t n3 = 3 * (int64_t)*(volatile unsigned int*)&m.n_listed[round - 1];
-      const int32_t* list = (round & 1) ? m.tri_list[1] : m.tri_list[0];
-      for (int64_t i = tid; i < n3; i += nthreads) {
-        const int64_t k = i / 3;
-        oisat_flip::mark_edge(m, 3 * list[k] + (int32_t)(i - 3 * k), round, P, ops);
-      }
+    const int64_t n_items = round == 0 ? n_tri : (int64_t)*(volatile unsigned int*)&l.n_listed[round - 1];
+    const int32_t* list = (round & 1) ? l.tri_list[1] : l.tri_list[0];
+    for (int64_t i = tid; i < 3 * n_items; i += nthreads) {
+      const int64_t k = i / 3;
+      const int32_t t = round == 0 ? (int32_t)k : list[k];
+      const int g = mesh_of(b, t);
+      const oisat_flip::Mesh& m = b.mesh[g];
+      const FlipCoords<T> P{(const T*)b.x[g], (const T*)b.y[g]};
+      oisat_flip::mark_edge(m, l, 3 * (t - m.tri_base) + (int32_t)(i - 3 * k), round, P, ops);
     }
     if (solo) __syncthreads(); else grid.sync();
-    const int64_t n_marked = *(volatile unsigned int*)&m.n_marked[round];
+    const int64_t n_marked = *(volatile unsigned int*)&l.n_marked[round];
     if (n_marked == 0) { ++round; break; }
-    for (int64_t i = tid; i < n_marked; i += nthreads)
-      flips += oisat_flip::apply_edge(m, m.edge_list[i], round, ops);
+    for (int64_t i = tid; i < n_marked; i += nthreads) {
+      const int32_t e = l.edge_list[i];
+      const oisat_flip::Mesh& m = b.mesh[mesh_of(b, e / 3)];
+      flips += oisat_flip::apply_edge(m, l, e - 3 * m.tri_base, round, ops);
+    }
     if (solo) __syncthreads(); else grid.sync();
-    if (!solo && *(volatile unsigned int*)&m.n_listed[round] <= tail) {
+    if (!solo && *(volatile unsigned int*)&l.n_listed[round] <= tail) {
       if (blockIdx.x != 0) break;
       solo = true;
       tid = threadIdx.x;
@@ -135,23 +159,26 @@ flip_rounds_kernel(oisat_flip::Mesh m, FlipCoords<T> P, int max_rounds, unsigned
   if (blockIdx.x == 0 && threadIdx.x == 0) result[0] = (unsigned long long)round;
 }
 
-// every edge once more: result[2] = edges certainly not Delaunay (only when the rounds were
-// cut off), result[3] = edges the filter cannot decide
+// every edge once more, per mesh g: result[4 g + 2] = edges certainly not Delaunay (only when
+// the rounds were cut off), result[4 g + 3] = edges the filter cannot decide; the batch's
+// rounds and flips are copied to every mesh's result[4 g + 0 / 1]
 template <typename T>
 __global__ void __launch_bounds__(256)
-flip_check_kernel(const int32_t* __restrict__ tri, const int32_t* __restrict__ half, int64_t n_half,
-                  FlipCoords<T> P, unsigned long long* __restrict__ result) {
-  const int64_t a = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  const int c = a < n_half ? oisat_flip::check_edge(tri, half, a, P) : 0;
-  const unsigned int bad = __reduce_add_sync(0xffffffffu, (unsigned int)(c & 1));
-  const unsigned int unsure = __reduce_add_sync(0xffffffffu, (unsigned int)((c >> 1) & 1));
-  if ((threadIdx.x & 31) == 0) {
-    if (bad) atomicAdd(&result[2], (unsigned long long)bad);
-    if (unsure) atomicAdd(&result[3], (unsigned long long)unsure);
+flip_check_kernel(const __grid_constant__ Batch b, unsigned long long* __restrict__ result) {
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t n_half = 3 * (int64_t)b.tri_end[b.n - 1];
+  if (e < b.n && e > 0) {
+    result[4 * e] = result[0];
+    result[4 * e + 1] = result[1];
   }
+  if (e >= n_half) return;
+  const int g = mesh_of(b, (int32_t)(e / 3));
+  const oisat_flip::Mesh& m = b.mesh[g];
+  const FlipCoords<T> P{(const T*)b.x[g], (const T*)b.y[g]};
+  const int c = oisat_flip::check_edge(m.tri, m.half, e - 3 * (int64_t)m.tri_base, P);
+  if (c & 1) atomicAdd(&result[4 * g + 2], 1ull);
+  if (c & 2) atomicAdd(&result[4 * g + 3], 1ull);
 }
-
-constexpr int kMaxRounds = 4096;
 
 }  // namespace
 }  // namespace oisat
@@ -176,75 +203,110 @@ extern "C" int oisat_seed_assemble(const int32_t* qtri, int64_t n_rows, int64_t 
   return OISAT_OK;
 }
 
-// workspace: [owner u64 n][cand i32 3n][n_listed u32 R][n_marked u32 R] (zeroed) |
-//            [stamp i32 n] (set to -1) | [tri_list 2 x i32 n][edge_list i32 3n/2+1]
+// workspace for N triangles in all: [owner u64 N][cand i32 3N][n_listed u32 R][n_marked u32 R]
+// (zeroed) | [stamp i32 N] (set to -1) | [tri_list 2 x i32 N][edge_list i32 3N/2+1]
 extern "C" int64_t oisat_flip_workspace_bytes(int64_t n_tri) {
   if (n_tri < 0) return OISAT_E_ARG;
   return 8 * n_tri + 12 * n_tri + 8 * (int64_t)kMaxRounds + 4 * n_tri + 8 * n_tri +
          4 * (3 * n_tri / 2 + 1) + 64;
 }
 
+namespace {
+int flip_chunk(const oisat_flip_item* items, int n_items, int32_t coord_dtype, void* workspace,
+               uint64_t* result, cudaStream_t s) {
+  Batch b;
+  b.n = n_items;
+  int64_t N = 0;
+  for (int g = 0; g < n_items; ++g) N += items[g].n_tri;
+  OISAT_CHECK_ARG(3 * N < (int64_t)INT_MAX, "bad extent");
+  char* w = (char*)workspace;
+  const int64_t zeroed = 20 * N + 8 * (int64_t)kMaxRounds;
+  unsigned long long* owner = (unsigned long long*)w;
+  int32_t* cand = (int32_t*)(w + 8 * N);
+  oisat_flip::Lists l;
+  l.n_listed = (unsigned int*)(w + 20 * N);
+  l.n_marked = l.n_listed + kMaxRounds;
+  int32_t* stamp = (int32_t*)(w + zeroed);
+  l.tri_list[0] = stamp + N;
+  l.tri_list[1] = stamp + 2 * N;
+  l.edge_list = stamp + 3 * N;
+  int64_t base = 0;
+  for (int g = 0; g < n_items; ++g) {
+    oisat_flip::Mesh& m = b.mesh[g];
+    m.tri = items[g].tri;
+    m.half = items[g].half;
+    m.n_half = 3 * items[g].n_tri;
+    m.stamp = stamp + base;
+    m.cand = cand + 3 * base;
+    m.owner = owner + base;
+    m.tri_base = (int32_t)base;
+    b.x[g] = items[g].px;
+    b.y[g] = items[g].py;
+    base += items[g].n_tri;
+    b.tri_end[g] = (int32_t)base;
+  }
+  OISAT_CHECK_CUDA(cudaMemsetAsync(w, 0, (size_t)zeroed, s));
+  OISAT_CHECK_CUDA(cudaMemsetAsync(stamp, 0xff, (size_t)(4 * N), s));
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0, per_sm_f = 0, per_sm_d = 0;
+    OISAT_CHECK_CUDA(cudaGetDevice(&dev));
+    OISAT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, flip_rounds_kernel<float>, 512, 0));
+    OISAT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, flip_rounds_kernel<double>, 512, 0));
+    OISAT_CHECK_ARG(per_sm_f >= 1 && per_sm_d >= 1, "flip kernel does not fit an SM");
+    OISAT_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int max_rounds = kMaxRounds;
+  unsigned int tail = 512;
+  if (const char* e = getenv("OISAT_FLIP_TAIL")) tail = (unsigned int)atoi(e);
+  unsigned long long* res = (unsigned long long*)result;
+  // one block per SM at most (a grid barrier costs with the number of blocks), and no more
+  // blocks than there is work for in the first round
+  int64_t blocks = sm_count;
+  const int64_t want = ceil_div(3 * N, 4 * 512);
+  if (blocks > want) blocks = want;
+  void* args[] = {&b, &l, &max_rounds, &tail, &res};
+  const void* fn = coord_dtype == OISAT_F32 ? (const void*)flip_rounds_kernel<float>
+                                            : (const void*)flip_rounds_kernel<double>;
+  OISAT_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(512), args, 0, s));
+  OISAT_CHECK_LAUNCH();
+  const unsigned cblocks = (unsigned)ceil_div(3 * N, 256);
+  if (coord_dtype == OISAT_F32)
+    flip_check_kernel<float><<<cblocks, 256, 0, s>>>(b, res);
+  else
+    flip_check_kernel<double><<<cblocks, 256, 0, s>>>(b, res);
+  OISAT_CHECK_LAUNCH();
+  return OISAT_OK;
+}
+}  // namespace
+
+extern "C" int oisat_flip_delaunay_batch(const oisat_flip_item* items, int32_t n_items,
+                                         int32_t coord_dtype, void* workspace, uint64_t* result,
+                                         void* stream) {
+  if (n_items <= 0) return OISAT_OK;
+  OISAT_CHECK_ARG(items && result && workspace, "null pointer");
+  OISAT_CHECK_ARG(coord_dtype == OISAT_F32 || coord_dtype == OISAT_F64, "coords must be f32/f64");
+  cudaStream_t s = (cudaStream_t)stream;
+  OISAT_CHECK_CUDA(cudaMemsetAsync(result, 0, (size_t)n_items * 4 * sizeof(uint64_t), s));
+  for (int g = 0; g < n_items; ++g)
+    OISAT_CHECK_ARG(items[g].n_tri >= 1 && items[g].tri && items[g].half && items[g].px && items[g].py,
+                    "bad item");
+  for (int g0 = 0; g0 < n_items; g0 += kMaxBatch) {
+    const int n = n_items - g0 < kMaxBatch ? n_items - g0 : kMaxBatch;
+    const int rc = flip_chunk(items + g0, n, coord_dtype, workspace, result + 4 * g0, s);
+    if (rc != OISAT_OK) return rc;
+  }
+  return OISAT_OK;
+}
+
 extern "C" int oisat_flip_delaunay(int32_t* tri, int32_t* half, int64_t n_tri, const void* px,
                                    const void* py, int32_t coord_dtype, void* workspace,
                                    uint64_t* result, void* stream) {
   OISAT_CHECK_ARG(result != nullptr, "null pointer");
-  cudaStream_t s = (cudaStream_t)stream;
-  OISAT_CHECK_CUDA(cudaMemsetAsync(result, 0, 4 * sizeof(uint64_t), s));
-  if (n_tri <= 0) return OISAT_OK;
-  OISAT_CHECK_ARG(tri && half && px && py && workspace, "null pointer");
-  OISAT_CHECK_ARG(coord_dtype == OISAT_F32 || coord_dtype == OISAT_F64, "coords must be f32/f64");
-  OISAT_CHECK_ARG(3 * n_tri < (int64_t)INT_MAX, "bad extent");
-  char* w = (char*)workspace;
-  const int64_t zeroed = 20 * n_tri + 8 * (int64_t)kMaxRounds;
-  oisat_flip::Mesh m;
-  m.tri = tri;
-  m.half = half;
-  m.n_half = 3 * n_tri;
-  m.owner = (unsigned long long*)w;
-  m.cand = (int32_t*)(w + 8 * n_tri);
-  m.n_listed = (unsigned int*)(w + 20 * n_tri);
-  m.n_marked = m.n_listed + kMaxRounds;
-  m.stamp = (int32_t*)(w + zeroed);
-  m.tri_list[0] = m.stamp + n_tri;
-  m.tri_list[1] = m.stamp + 2 * n_tri;
-  m.edge_list = m.stamp + 3 * n_tri;
-  OISAT_CHECK_CUDA(cudaMemsetAsync(w, 0, (size_t)zeroed, s));
-  OISAT_CHECK_CUDA(cudaMemsetAsync(m.stamp, 0xff, (size_t)(4 * n_tri), s));
-  static int sm_count = 0, per_sm_f = 0, per_sm_d = 0;
-  if (!sm_count) {
-    int dev = 0;
-    OISAT_CHECK_CUDA(cudaGetDevice(&dev));
-    OISAT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, flip_rounds_kernel<float>, 512, 0));
-    OISAT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, flip_rounds_kernel<double>, 512, 0));
-    OISAT_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  if (n_tri <= 0) {
+    OISAT_CHECK_CUDA(cudaMemsetAsync(result, 0, 4 * sizeof(uint64_t), (cudaStream_t)stream));
+    return OISAT_OK;
   }
-  int max_rounds = kMaxRounds;
-  unsigned int tail = 2048;
-  if (const char* e = getenv("OISAT_FLIP_TAIL")) tail = (unsigned int)atoi(e);
-  unsigned long long* res = (unsigned long long*)result;
-  const int per_sm = coord_dtype == OISAT_F32 ? per_sm_f : per_sm_d;
-  OISAT_CHECK_ARG(per_sm >= 1, "flip kernel does not fit an SM");
-  // one block per SM at most (a grid barrier costs with the number of blocks), and no more
-  // blocks than there is work for in the first round
-  int64_t blocks = sm_count;
-  const int64_t want = ceil_div(m.n_half, 4 * 512);
-  if (blocks > want) blocks = want;
-  FlipCoords<float> Pf{(const float*)px, (const float*)py};
-  FlipCoords<double> Pd{(const double*)px, (const double*)py};
-  void* args_f[] = {&m, &Pf, &max_rounds, &tail, &res};
-  void* args_d[] = {&m, &Pd, &max_rounds, &tail, &res};
-  if (coord_dtype == OISAT_F32)
-    OISAT_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)flip_rounds_kernel<float>, dim3((unsigned)blocks),
-                                                 dim3(512), args_f, 0, s));
-  else
-    OISAT_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)flip_rounds_kernel<double>, dim3((unsigned)blocks),
-                                                 dim3(512), args_d, 0, s));
-  OISAT_CHECK_LAUNCH();
-  const unsigned cblocks = (unsigned)ceil_div(m.n_half, 256);
-  if (coord_dtype == OISAT_F32)
-    flip_check_kernel<float><<<cblocks, 256, 0, s>>>(tri, half, m.n_half, Pf, res);
-  else
-    flip_check_kernel<double><<<cblocks, 256, 0, s>>>(tri, half, m.n_half, Pd, res);
-  OISAT_CHECK_LAUNCH();
-  return OISAT_OK;
+  const oisat_flip_item item{tri, half, n_tri, px, py};
+  return oisat_flip_delaunay_batch(&item, 1, coord_dtype, workspace, result, stream);
 }

@@ -105,6 +105,19 @@ def finalize_and_oi(acc, n_cell, sensor, gas, error_ctm):
                 increment_OI=inc, error_OI=err, **extra)
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream():
+    """One side stream per device for host -> device copies that should not queue in front
+    of kernels (add_day)."""
+    t = _dev.torch()
+    d = t.cuda.current_device()
+    if d not in _COPY_STREAMS:
+        _COPY_STREAMS[d] = t.cuda.Stream(device=d)
+    return _COPY_STREAMS[d]
+
+
 class MonthPipeline:
     def __init__(self, ctm_data, grid_size, flag_thresh, sensor="OMI", gas="NO2", error_ctm=50.0,
                  process_group=None, interpolator_type=1):
@@ -252,10 +265,28 @@ class MonthPipeline:
             for k in ("lon", "lat"):          # the plan builders need these first
                 g.dev[k] = g.host[k].to(dev, non_blocking=True)
             staged.append(g)
+        # the bulk of the reader arrays travels on a copy stream of its own: the plan kernels
+        # queued below need only lon / lat and would otherwise sit behind 24 MB per granule
+        t = _dev.torch()
+        main = t.cuda.current_stream()
+        pinned = all(h is None or h.is_pinned() for g in staged for h in g.host.values())
+        side = _copy_stream() if pinned else None
         for g in staged:
             for k, h in g.host.items():
                 if k not in g.dev:
-                    g.dev[k] = None if h is None else h.to(dev, non_blocking=True)
+                    g.dev[k] = None if h is None else (
+                        t.empty(h.shape, dtype=h.dtype, device=dev) if side is not None
+                        else h.to(dev, non_blocking=True))
+        copied = None
+        if side is not None:
+            side.wait_stream(main)          # the destinations were allocated on `main`
+            with t.cuda.stream(side):
+                for g in staged:
+                    for k, h in g.host.items():
+                        if k not in ("lon", "lat") and h is not None:
+                            g.dev[k].copy_(h, non_blocking=True)
+                copied = t.cuda.Event()
+                copied.record()
         lons = [np.asarray(s.longitude_center) for s in sats]
         lats = [np.asarray(s.latitude_center) for s in sats]
         lonlat = [(g.dev["lon"], g.dev["lat"]) for g in staged]
@@ -266,6 +297,8 @@ class MonthPipeline:
             plans = [(_plan.nearest_plan(lons[i], lats[i], self.gplan, radius, lonlat_dev=lonlat[i])
                       if self.interpolator_type == 4 or _plan.triangulable(lons[i], lats[i])
                       else None) for i in range(len(sats))]
+        if copied is not None:
+            main.wait_event(copied)          # whatever is queued from here on sees the arrays
         kept = 0
         for g, sat, plan in zip(staged, sats, plans):
             g.plan = plan

@@ -383,15 +383,11 @@ def host_triangulation(lon, lat, pinned=False, device_index=None):
     return "tri", native_delaunay_adj(lon, lat, pinned, device_index)
 
 
-def device_triangulation(parts, lonlat_dev):
-    """Queues K12 for one granule: upload of the seed parts, oisat_seed_assemble,
-    oisat_flip_delaunay.  Returns (tri, half, result) on the device; result[2:4] must be zero
-    (read it after the stream has run) for the triangulation to be the Delaunay one."""
+def seed_assemble_device(parts):
+    """Queues the upload of the seed parts and oisat_seed_assemble: (tri, half, keep-alive)."""
     L = _lib.lib()
     t = _dev.torch()
     dev = _dev.device()
-    s = _dev.stream()
-    lo, la = lonlat_dev
     nt = parts["n_tri"]
     qtri = t.from_numpy(parts["qtri"]).to(dev, non_blocking=True)
     otri = t.from_numpy(parts["otri"]).to(dev, non_blocking=True)
@@ -400,12 +396,41 @@ def device_triangulation(parts, lonlat_dev):
     half = _dev.empty((nt, 3), "int32")
     _lib.check(L.oisat_seed_assemble(qtri.data_ptr(), parts["rows"], parts["cols"], parts["sigma"],
                                      parts["n_quads"], otri.data_ptr(), ohalf.data_ptr(),
-                                     parts["n_outside"], tri.data_ptr(), half.data_ptr(), s))
-    work = _dev.empty((int(L.oisat_flip_workspace_bytes(nt)),), "uint8")
-    result = _dev.empty((4,), "int64")
-    _lib.check(L.oisat_flip_delaunay(tri.data_ptr(), half.data_ptr(), nt, lo.data_ptr(), la.data_ptr(),
-                                     _dev.dtype_code(lo), work.data_ptr(), result.data_ptr(), s))
-    return tri, half, result, (qtri, otri, ohalf, work)
+                                     parts["n_outside"], tri.data_ptr(), half.data_ptr(), _dev.stream()))
+    return tri, half, (qtri, otri, ohalf)
+
+
+def flip_batch_device(meshes):
+    """Queues oisat_flip_delaunay_batch for [(tri, half, (lon_dev, lat_dev)), ...] -- the
+    granules of a day go through the rounds of flips together.  Returns (result (n, 4) int64
+    on the device: rounds and flips of the batch, then per mesh the edges left non-Delaunay
+    and the edges the filter cannot decide, keep-alive).  Coordinates of one dtype."""
+    L = _lib.lib()
+    n = len(meshes)
+    items = (_lib.FlipItem * n)()
+    total = 0
+    code = _dev.dtype_code(meshes[0][2][0])
+    for k, (tri, half, (lo, la)) in enumerate(meshes):
+        if _dev.dtype_code(lo) != code:
+            raise _lib.OisatError("flip batch: coordinates of mixed dtypes")
+        items[k] = _lib.FlipItem(tri.data_ptr(), half.data_ptr(), tri.shape[0], lo.data_ptr(), la.data_ptr())
+        total += tri.shape[0]
+    per_chunk = max(sum(m[0].shape[0] for m in meshes[c:c + 32]) for c in range(0, n, 32))
+    work = _dev.empty((int(L.oisat_flip_workspace_bytes(per_chunk)),), "uint8")
+    result = _dev.empty((n, 4), "int64")
+    import ctypes as C
+    _lib.check(L.oisat_flip_delaunay_batch(C.cast(items, C.c_void_p), n, code, work.data_ptr(),
+                                           result.data_ptr(), _dev.stream()))
+    return result, work
+
+
+def device_triangulation(parts, lonlat_dev):
+    """K12 for one granule: seed parts -> (tri, half, result[4], keep-alive) on the device;
+    result[2:4] must be zero (read it after the stream has run) for the triangulation to be
+    the Delaunay one."""
+    tri, half, keep = seed_assemble_device(parts)
+    result, work = flip_batch_device([(tri, half, lonlat_dev)])
+    return tri, half, result[0], (keep, work)
 
 
 def locate(tri, qx, qy):
@@ -484,9 +509,12 @@ def _plan_v0_device(lon, lat, lonlat_dev, gplan, keep_dev):
     return plan
 
 
-def _plan_v1_enqueue(tri_host, lonlat_dev, gplan, keep_dev, half_host=None, maxabs=0.0, seed=None):
+def _plan_v1_enqueue(tri_host, lonlat_dev, gplan, keep_dev, half_host=None, maxabs=0.0, seed=None,
+                     mesh=None):
     """First half of the device part of a v1 plan, queued without waiting for anything:
-    upload of the triangulation (or, with `seed`, its construction on the device: K12),
+    upload of the triangulation (or, with `seed`, its construction on the device: K12; or,
+    with `mesh` = (tri, half, maxabs, flip_host_row, keep-alive), a triangulation K12 has
+    already been queued for as part of a batch),
     near-tie scan (with `half_host`, native_delaunay_adj), point location (K1), per-cell
     validity, and the copy of the per-cell flags (n_cell bytes) + tie count to pinned host
     memory.  Returns the state _plan_v1_finish needs."""
@@ -497,8 +525,10 @@ def _plan_v1_enqueue(tri_host, lonlat_dev, gplan, keep_dev, half_host=None, maxa
     xs, ys = gplan.dev_axes()
     window, nn_ok = gplan.dev_tables()
     s = _dev.stream()
-    ties_dev = tri_flag = flip_dev = half = seed_keep = None
-    if seed is not None:
+    ties_dev = tri_flag = flip_dev = flip_host = half = seed_keep = None
+    if mesh is not None:
+        tri, half, maxabs, flip_host, seed_keep = mesh
+    elif seed is not None:
         tri, half, flip_dev, seed_keep = device_triangulation(seed, lonlat_dev)
         maxabs = seed["maxabs"]
     else:
@@ -530,7 +560,6 @@ def _plan_v1_enqueue(tri_host, lonlat_dev, gplan, keep_dev, half_host=None, maxa
     if ties_dev is not None:
         ties_host = t.empty((2,), dtype=t.int64, pin_memory=True)
         ties_host.copy_(ties_dev, non_blocking=True)
-    flip_host = None
     if flip_dev is not None:
         flip_host = t.empty((4,), dtype=t.int64, pin_memory=True)
         flip_host.copy_(flip_dev, non_blocking=True)
@@ -741,6 +770,7 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
     from concurrent.futures import as_completed
     out = [None] * n
     pending = []
+    seeded = []
     ex = _plan_pool(workers)
     # The first half of a granule's device part (uploads, near-tie scan, point location,
     # flags to pinned memory) is queued as soon as ITS triangulation is done, while the
@@ -757,7 +787,7 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
         kind, got = fut.result()
         t_a = _time.perf_counter()
         if kind == "seed":       # K12 finishes the triangulation on the device
-            pending.append((i, _plan_v1_enqueue(None, lonlat_dev[i], gplan, keeps[i], None, 0.0, got)))
+            seeded.append((i, got) + seed_assemble_device(got))
         else:
             tri, half, ties, maxabs = got
             if tri is None:
@@ -769,6 +799,21 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
                 continue
         if trace is not None:
             trace.append("%d:%.0f+%.1f" % (i, (t_a - t_start) * 1e3, (_time.perf_counter() - t_a) * 1e3))
+    if seeded:
+        # the seeds of the whole batch go through the rounds of flips together (one launch:
+        # a round costs its two barriers whatever it holds), then each granule's device part
+        t = _dev.torch()
+        groups = {}
+        for k, sd in enumerate(seeded):
+            groups.setdefault(_dev.dtype_code(lonlat_dev[sd[0]][0]), []).append(k)
+        for ks in groups.values():
+            result, work = flip_batch_device([(seeded[k][2], seeded[k][3], lonlat_dev[seeded[k][0]]) for k in ks])
+            flip_host = t.empty((len(ks), 4), dtype=t.int64, pin_memory=True)
+            flip_host.copy_(result, non_blocking=True)
+            for row, k in enumerate(ks):
+                i, parts, tri, half, keep = seeded[k]
+                mesh = (tri, half, parts["maxabs"], flip_host[row], (keep, work, result, parts))
+                pending.append((i, _plan_v1_enqueue(None, lonlat_dev[i], gplan, keeps[i], mesh=mesh)))
     t_pool = _time.perf_counter()
     for i, st in pending:     # second half: kept cells on the host, stencil fill queued
         out[i] = _plan_v1_finish(st, gplan)

@@ -363,6 +363,7 @@ def test_device_triangulation_equals_the_host_builders(monkeypatch):
     L = _lib.lib()
     t = _dev.torch()
     done = 0
+    meshes = []
     for k, (lon, lat) in enumerate(_seed_swaths()):
         for dt in (np.float64, np.float32):
             lo, la = lon.astype(dt), lat.astype(dt)
@@ -392,11 +393,22 @@ def test_device_triangulation_equals_the_host_builders(monkeypatch):
                 t.cuda.synchronize()
                 res = res.cpu().numpy()
                 assert list(res) == list(want), (k, dt, tail, res, want)
+                meshes.append((parts, tri, half, (d_lo, d_la), h_tri, h_half)) if tail is None else None
                 assert res[2] == 0 and res[3] == 0
                 assert np.array_equal(tri.cpu().numpy(), h_tri) and np.array_equal(half.cpu().numpy(), h_half)
             assert _tri_set(tri.cpu().numpy()) == _tri_set(ref)
             done += 1
     assert done >= 12
+    # the same meshes as ONE batch (per coordinate dtype): every mesh ends as it did alone
+    for code in (np.float64, np.float32):
+        group = [m for m in meshes if m[3][0].cpu().numpy().dtype == code]
+        fresh = [plan.seed_assemble_device(m[0]) for m in group]
+        result, _work = plan.flip_batch_device([(f[0], f[1], m[3]) for f, m in zip(fresh, group)])
+        t.cuda.synchronize()
+        result = result.cpu().numpy()
+        assert (result[:, 2:] == 0).all() and len(set(result[:, 0])) == 1 and result[0, 0] < 400
+        for f, m in zip(fresh, group):
+            assert np.array_equal(f[0].cpu().numpy(), m[4]) and np.array_equal(f[1].cpu().numpy(), m[5])
 
 
 def test_plans_from_the_device_triangulation_equal_the_host_ones(monkeypatch):
@@ -424,8 +436,9 @@ def test_plans_from_the_device_triangulation_equal_the_host_ones(monkeypatch):
         assert a.builder == "v1d" and b.builder == "v1", (a.builder, b.builder)
         assert a.flips > 1000 and a.flip_rounds < 400
         assert np.array_equal(a.cells, b.cells)
-        va, wa = a.vert.reshape(len(a.cells), -1, 3), a.w.reshape(len(a.cells), -1, 3)
-        vb, wb = b.vert.reshape(len(b.cells), -1, 3), b.w.reshape(len(b.cells), -1, 3)
+        # host accessors are stencil-major (3 * nwin, n_cells), entry 3 k + j = vertex j of window node k
+        va, wa = a.vert.T.reshape(len(a.cells), -1, 3), a.w.T.reshape(len(a.cells), -1, 3)
+        vb, wb = b.vert.T.reshape(len(b.cells), -1, 3), b.w.T.reshape(len(b.cells), -1, 3)
         ia, ib = np.argsort(va, axis=2, kind="stable"), np.argsort(vb, axis=2, kind="stable")
         va, wa = np.take_along_axis(va, ia, 2), np.take_along_axis(wa, ia, 2)
         vb, wb = np.take_along_axis(vb, ib, 2), np.take_along_axis(wb, ib, 2)

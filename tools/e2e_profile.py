@@ -51,7 +51,8 @@ def main():
         t2 = time.perf_counter()
         if it == 2:
             print("add_day returned after %.1f ms, drained after %.1f ms" % ((ta - t0) * 1e3, (t1 - t0) * 1e3))
-            pstats.Stats(pra).sort_stats("cumulative").print_stats(25)
+            if os.environ.get("OISAT_PLAN_TRACE") != "1":
+                pstats.Stats(pra).sort_stats("cumulative").print_stats(25)
         out = p.results_to_host(p.run())
         torch.cuda.synchronize()
         t3 = time.perf_counter()
