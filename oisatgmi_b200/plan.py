@@ -748,40 +748,55 @@ def _plan_pool(workers):
     return ex
 
 
-def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonlat_dev=None):
-    """Plans for a batch of granules (lists of lon/lat arrays): K0 for all of them,
-    the native triangulations on a thread pool (the C call releases the GIL), then
-    the device part granule by granule."""
+def _plan_workers(n, workers=None):
     import os
-    from concurrent.futures import ThreadPoolExecutor
-    n = len(lons)
-    if lonlat_dev is None:
-        lonlat_dev = [(_dev.to_device(coord_array(lons[i])), _dev.to_device(coord_array(lats[i])))
-                      for i in range(n)]
-    keeps = [distance_mask(lo, la, gplan, radius) for lo, la in lonlat_dev]
-    if not gplan.upscale or _plan_mode() == "v0":
-        return [granule_plan(lons[i], lats[i], gplan, radius, lonlat_dev=lonlat_dev[i], cache=False)
-                for i in range(n)]
     if workers is None:
         # one process per GPU: the ranks of a node share its cores
         local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
         workers = max(1, (os.cpu_count() or 1) // local)
-    workers = max(1, min(n, workers))
+    return max(1, min(n, workers))
+
+
+def submit_triangulations(lons, lats, gplan: GridPlan, workers=None):
+    """Puts the host share of the plans of a batch on the thread pool and returns at once
+    ({future: index}, or None when this grid does not take builder v1): the caller can queue
+    uploads and K0 while the pool works, then hand the futures to granule_plans."""
+    if not gplan.upscale or _plan_mode() == "v0":
+        return None
+    n = len(lons)
+    ex = _plan_pool(_plan_workers(n, workers))
+    dev_index = _dev.device().index
+    return {ex.submit(host_triangulation, lons[i], lats[i], True, dev_index): i for i in range(n)}
+
+
+def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonlat_dev=None,
+                  futures=None):
+    """Plans for a batch of granules (lists of lon/lat arrays): K0 for all of them,
+    the native triangulations on a thread pool (the C call releases the GIL; `futures`:
+    already submitted, submit_triangulations), then the device part granule by granule."""
+    import os
+    n = len(lons)
+    import time as _time
+    t_start = _time.perf_counter()
+    if futures is None:
+        futures = submit_triangulations(lons, lats, gplan, workers)
+    if lonlat_dev is None:
+        lonlat_dev = [(_dev.to_device(coord_array(lons[i])), _dev.to_device(coord_array(lats[i])))
+                      for i in range(n)]
+    keeps = [distance_mask(lo, la, gplan, radius) for lo, la in lonlat_dev]
+    if futures is None:
+        return [granule_plan(lons[i], lats[i], gplan, radius, lonlat_dev=lonlat_dev[i], cache=False)
+                for i in range(n)]
     from concurrent.futures import as_completed
     out = [None] * n
     pending = []
     seeded = []
-    ex = _plan_pool(workers)
     # The first half of a granule's device part (uploads, near-tie scan, point location,
     # flags to pinned memory) is queued as soon as ITS triangulation is done, while the
     # others are still on the pool -- and without waiting for the GPU: with a
     # synchronisation per granule the 15 device parts of a day (2 ms each) ran one after
     # the other behind the slowest triangulation.
-    import time as _time
     trace = [] if os.environ.get("OISAT_PLAN_TRACE") == "1" else None
-    t_start = _time.perf_counter()
-    dev_index = _dev.device().index
-    futures = {ex.submit(host_triangulation, lons[i], lats[i], True, dev_index): i for i in range(n)}
     for fut in as_completed(futures):
         i = futures[fut]
         kind, got = fut.result()
