@@ -36,8 +36,15 @@ struct DeviceOps {
   __device__ __forceinline__ unsigned long long max(unsigned long long* p, unsigned long long v) const {
     return atomicMax(p, v);
   }
+  // list appends: the threads of a warp that arrive here together reserve their slots with ONE
+  // atomic (every caller adds 1 to the same counter of the round).  Millions of returning
+  // atomics on a single address were most of the kernel's time: they are served one after
+  // the other by one L2 slice.
   __device__ __forceinline__ unsigned int add(unsigned int* p, unsigned int v) const {
-    return atomicAdd(p, v);
+    const cg::coalesced_group g = cg::coalesced_threads();
+    unsigned int base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(p, v * g.size());
+    return g.shfl(base, 0) + v * g.thread_rank();
   }
   __device__ __forceinline__ int32_t exch(int32_t* p, int32_t v) const { return atomicExch(p, v); }
 };
@@ -96,6 +103,7 @@ seed_assemble_kernel(const int32_t* __restrict__ qtri, int64_t rows, int64_t col
 // granules cost what one costs.  The table is a kernel parameter (constant bank).
 constexpr int kMaxBatch = 32;
 constexpr int kMaxRounds = 4096;
+constexpr int kFlipThreads = 1024;   // one block per SM: 64 registers per thread
 
 struct Batch {
   int n;
@@ -116,7 +124,7 @@ __device__ __forceinline__ int mesh_of(const Batch& b, int32_t t) {
 // ~80-100 rounds, most of them with fewer than 500 flips -- is run by block 0 alone with block
 // barriers, the other blocks leave.  result[0] = rounds run, result[1] = flips (whole batch).
 template <typename T>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(kFlipThreads)
 flip_rounds_kernel(const __grid_constant__ Batch b, oisat_flip::Lists l, int max_rounds,
                    unsigned int tail, unsigned long long* __restrict__ result) {
   cg::grid_group grid = cg::this_grid();
@@ -251,8 +259,8 @@ int flip_chunk(const oisat_flip_item* items, int n_items, int32_t coord_dtype, v
   if (!sm_count) {
     int dev = 0, per_sm_f = 0, per_sm_d = 0;
     OISAT_CHECK_CUDA(cudaGetDevice(&dev));
-    OISAT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, flip_rounds_kernel<float>, 512, 0));
-    OISAT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, flip_rounds_kernel<double>, 512, 0));
+    OISAT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, flip_rounds_kernel<float>, kFlipThreads, 0));
+    OISAT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, flip_rounds_kernel<double>, kFlipThreads, 0));
     OISAT_CHECK_ARG(per_sm_f >= 1 && per_sm_d >= 1, "flip kernel does not fit an SM");
     OISAT_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
@@ -263,12 +271,12 @@ int flip_chunk(const oisat_flip_item* items, int n_items, int32_t coord_dtype, v
   // one block per SM at most (a grid barrier costs with the number of blocks), and no more
   // blocks than there is work for in the first round
   int64_t blocks = sm_count;
-  const int64_t want = ceil_div(3 * N, 4 * 512);
+  const int64_t want = ceil_div(3 * N, 4 * kFlipThreads);
   if (blocks > want) blocks = want;
   void* args[] = {&b, &l, &max_rounds, &tail, &res};
   const void* fn = coord_dtype == OISAT_F32 ? (const void*)flip_rounds_kernel<float>
                                             : (const void*)flip_rounds_kernel<double>;
-  OISAT_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(512), args, 0, s));
+  OISAT_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(kFlipThreads), args, 0, s));
   OISAT_CHECK_LAUNCH();
   const unsigned cblocks = (unsigned)ceil_div(3 * N, 256);
   if (coord_dtype == OISAT_F32)

@@ -191,24 +191,39 @@ locate_mid_kernel(const int32_t* __restrict__ tri, Coords<T> P, const double* __
 // Pass 3, thread = mesh node.  The few kept nodes that no rasterised triangle claimed
 // (they sit in a hull pocket, or outside the hull) are tested against the short
 // list of large triangles; node-centric, so the large boxes are never rasterised.
+// A block that has such a node works out the triangles' geometry once, in shared memory
+// (a chunk of 256 triangles at a time), instead of every node re-deriving it from the
+// vertex table (three dependent loads and a division per triangle and node).
 template <typename T>
 __global__ void __launch_bounds__(256)
 locate_big_kernel(const int32_t* __restrict__ tri, Coords<T> P, const double* __restrict__ xs,
                   int64_t W, const double* __restrict__ ys, int64_t H,
                   const uint8_t* __restrict__ keep, int32_t* __restrict__ node_tri,
                   const int32_t* __restrict__ counts, const int32_t* __restrict__ big_list) {
+  __shared__ TriGeom geom[256];
+  __shared__ int32_t index[256];
   const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= W * H || !keep[f] || node_tri[f] != INT_MAX) return;
+  const bool open = f < W * H && keep[f] && node_tri[f] == INT_MAX;
+  if (!__syncthreads_or(open)) return;
   const int n_big = counts[1];
-  const double qx = xs[f % W], qy = ys[f / W];
+  const double qx = open ? xs[f % W] : 0.0, qy = open ? ys[f / W] : 0.0;
   int32_t best = INT_MAX;
-  for (int k = 0; k < n_big; ++k) {
-    const int32_t t = big_list[k];
-    const int32_t v0 = tri[3 * (int64_t)t], v1 = tri[3 * (int64_t)t + 1], v2 = tri[3 * (int64_t)t + 2];
-    const TriGeom g = tri_geom(P.px(v0), P.py(v0), P.px(v1), P.py(v1), P.px(v2), P.py(v2));
-    double c[3];
-    bary(g, qx, qy, c);
-    if (inside(c) && t < best) best = t;
+  for (int k0 = 0; k0 < n_big; k0 += 256) {
+    const int n = n_big - k0 < 256 ? n_big - k0 : 256;
+    __syncthreads();
+    if ((int)threadIdx.x < n) {
+      const int32_t t = big_list[k0 + threadIdx.x];
+      const int32_t v0 = tri[3 * (int64_t)t], v1 = tri[3 * (int64_t)t + 1], v2 = tri[3 * (int64_t)t + 2];
+      geom[threadIdx.x] = tri_geom(P.px(v0), P.py(v0), P.px(v1), P.py(v1), P.px(v2), P.py(v2));
+      index[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (open)
+      for (int k = 0; k < n; ++k) {
+        double c[3];
+        bary(geom[k], qx, qy, c);
+        if (inside(c) && index[k] < best) best = index[k];
+      }
   }
   if (best != INT_MAX) node_tri[f] = best;
 }

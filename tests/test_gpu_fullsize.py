@@ -88,7 +88,7 @@ def test_tropomi_scale_plan_builders_agree(monkeypatch):
     g = _granule(6)
     monkeypatch.setenv("OISAT_PLAN", "auto")
     p1 = _plan.granule_plan(g.longitude_center, g.latitude_center, gpl, 0.2, cache=False)
-    assert p1.builder == "v1"
+    assert p1.builder == "v1d"          # triangulation finished on the device (K12)
     monkeypatch.setenv("OISAT_PLAN", "v0")
     p0 = _plan.granule_plan(g.longitude_center, g.latitude_center, gpl, 0.2, cache=False)
     assert p0.builder == "v0"
@@ -114,7 +114,7 @@ def test_tropomi_scale_isolated_near_tie_does_not_need_qhull(monkeypatch):
     gpl = _plan.grid_plan(synth.ctm_coordinates(None), 0.10)
     monkeypatch.setenv("OISAT_PLAN", "auto")
     p1 = _plan.granule_plan(lon, lat, gpl, 0.2, cache=False)
-    assert p1.builder == "v1" and p1.near_ties == ties
+    assert p1.builder == "v1d" and p1.near_ties == ties
     monkeypatch.setenv("OISAT_PLAN", "v0")
     p0 = _plan.granule_plan(lon, lat, gpl, 0.2, cache=False)
     assert p0.builder == "v0"
@@ -184,7 +184,7 @@ def test_near_tie_with_a_kept_node_takes_qhull_triangles_and_device_walk(monkeyp
     monkeypatch.setenv("OISAT_PLAN", "v0")
     p0 = _plan.granule_plan(lon, lat, gpl, 0.5, cache=False)
     assert p0.builder == "v0"
-    if p1.builder == "v1":
+    if p1.builder in ("v1", "v1d"):
         pytest.skip("this build of the synthetic orbit has no affected near tie")
     assert p1.builder == "v0q"
     assert np.array_equal(p0.cells, p1.cells)

@@ -256,12 +256,15 @@ def test_empty_and_all_masked_granules():
         interpolator.interpolator(5, 0.25, c["granules"][0], c["coords"])
 
 
+@pytest.mark.parametrize("delaunay", ["device", "host"])
 @pytest.mark.parametrize("name", ["omi_no2", "tropomi_no2"])
-def test_gpu_plan_builder_equals_host_plan(name, monkeypatch):
-    """Builder v1 (native Delaunay + K1 point location on the GPU) against builder
-    v0 (Qhull + scipy's walk, what the reference itself runs): same kept cells, same
-    triangle per window node, weights to rounding."""
+def test_gpu_plan_builder_equals_host_plan(name, delaunay, monkeypatch):
+    """Builder v1 (native Delaunay -- finished on the device by K12, or built on the host --
+    + K1 point location on the GPU) against builder v0 (Qhull + scipy's walk, what the
+    reference itself runs): same kept cells, same triangle per window node, weights to
+    rounding."""
     from oisatgmi_b200 import plan
+    monkeypatch.setenv("OISAT_DELAUNAY", delaunay)
     c = cases.amf_case(name)
     gpl = plan.grid_plan(c["coords"], c["grid_size"])
     for g in c["granules"]:
@@ -271,7 +274,7 @@ def test_gpu_plan_builder_equals_host_plan(name, monkeypatch):
         monkeypatch.setenv("OISAT_PLAN", "auto")
         p1 = plan.granule_plan(g.longitude_center, g.latitude_center, gpl, 2 * c["grid_size"],
                                cache=False)
-        assert p0.builder == "v0" and p1.builder == "v1"
+        assert p0.builder == "v0" and p1.builder == ("v1d" if delaunay == "device" else "v1")
         assert np.array_equal(p0.cells, p1.cells)                       # bit-exact masks
         S, n = p0.vert.shape
         # same triangle per node (vertex order inside a triangle is free)
