@@ -54,5 +54,34 @@ def main():
                   % (tail, e0.elapsed_time(e1) / reps, r[0], r[1], r[2], r[3]))
 
 
+def batch(kind="omi", n=15):
+    """The granules of a day through the rounds together (what plan.granule_plans does)."""
+    nt, nx = (1644, 60) if kind == "omi" else (4172, 450)
+    t = _dev.torch()
+    rng = np.random.default_rng(4)
+    parts, coords = [], []
+    for k in range(n):
+        lat, lon = synth.swath_geolocation(nt, nx, node_lon_deg=-170.0 + 24.0 * k, rng=rng)
+        parts.append(plan.native_seed_parts(lon, lat, pinned=True))
+        coords.append((_dev.to_device(lon.ravel()), _dev.to_device(lat.ravel())))
+    for tail in ("0", "512", "4096", "16384"):
+        os.environ["OISAT_FLIP_TAIL"] = tail
+        times = []
+        for rep in range(4):
+            meshes = [plan.seed_assemble_device(p) for p in parts]
+            t.cuda.synchronize()
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            e0.record()
+            result, work = plan.flip_batch_device([(m[0], m[1], c) for m, c in zip(meshes, coords)])
+            e1.record()
+            t.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        r = result.cpu().numpy()
+        print("batch of %d %s granules, tail %-6s: %.3f ms (min of 3 after warm-up); rounds %d flips %d "
+              "bad %d undecided %d" % (n, kind, tail, min(times[1:]), r[0, 0], r[0, 1], r[:, 2].sum(),
+                                       r[:, 3].sum()))
+
+
 if __name__ == "__main__":
     main()
+    batch(sys.argv[1] if len(sys.argv) > 1 else "omi", 15 if (len(sys.argv) < 2 or sys.argv[1] == "omi") else 14)
