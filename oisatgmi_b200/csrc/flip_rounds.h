@@ -95,27 +95,54 @@ struct Lists {                  // work lists of a batch of meshes that go throu
 // old value); int32_t exch(int32_t*, v) (returns the old value) -- atomics on the device
 // Coords: double operator()(int vertex, int axis)
 
-// edge e of a listed triangle (or any half-edge in round 0)
+// The test of one edge in three steps, so that a device thread can have the loads of several
+// edges in flight before it decides any of them (a step is a chain of dependent loads:
+// twin -> vertices -> coordinates -> claims).
+struct Quad {
+  int32_t ia, ib;               // the edge's half-edges, ia < ib; ia < 0: nothing to test
+  int32_t pr, pl, p0, p1;       // ia runs pr -> pl; p0 is opposite in ia's triangle, p1 in ib's
+};
+
+// edge e of a listed triangle (or any half-edge in round 0): who tests it, and its vertices
+OISAT_FLIP_HD Quad mark_prepare(const Mesh& m, int32_t e, int round) {
+  Quad q;
+  q.ia = -1;
+  const int32_t b = m.half[e];
+  if (b < 0) return q;
+  // an edge between two listed triangles is the lower half-edge's (everything is listed in round 0)
+  if (b < e && (round == 0 || m.stamp[b / 3] == round - 1)) return q;
+  q.ia = e < b ? e : b;
+  q.ib = e < b ? b : e;
+  q.pr = m.tri[q.ia];
+  q.pl = m.tri[nxt(q.ia)];
+  q.p0 = m.tri[prv(q.ia)];
+  q.p1 = m.tri[prv(q.ib)];
+  return q;
+}
+
+template <class Coords>
+OISAT_FLIP_HD bool mark_decide(const Quad& q, const Coords& P) {
+  return incircle_filter(P(q.pr, 0), P(q.pr, 1), P(q.pl, 0), P(q.pl, 1), P(q.p0, 0), P(q.p0, 1),
+                         P(q.p1, 0), P(q.p1, 1)) > 0;
+}
+
+template <class Ops>
+OISAT_FLIP_HD void mark_claim(const Mesh& m, const Lists& l, const Quad& q, int round, const Ops& ops) {
+  const unsigned long long key = claim_key(round, q.ia);
+  ops.max(&m.owner[q.ia / 3], key);
+  ops.max(&m.owner[q.ib / 3], key);
+  const int32_t n1 = m.half[prv(q.ib)], n2 = m.half[prv(q.ia)];
+  if (n1 >= 0) ops.max(&m.owner[n1 / 3], key);
+  if (n2 >= 0) ops.max(&m.owner[n2 / 3], key);
+  m.cand[q.ia] = round + 1;
+  l.edge_list[ops.add(&l.n_marked[round], 1u)] = q.ia + 3 * m.tri_base;
+}
+
 template <class Coords, class Ops>
 OISAT_FLIP_HD void mark_edge(const Mesh& m, const Lists& l, int32_t e, int round, const Coords& P,
                              const Ops& ops) {
-  const int32_t b = m.half[e];
-  if (b < 0) return;
-  // an edge between two listed triangles is the lower half-edge's (everything is listed in round 0)
-  if (b < e && (round == 0 || m.stamp[b / 3] == round - 1)) return;
-  const int ia = e < b ? e : b, ib = e < b ? b : e;
-  const int al = nxt(ia), ar = prv(ia), bl = prv(ib);
-  const int32_t pr = m.tri[ia], pl = m.tri[al], p0 = m.tri[ar], p1 = m.tri[bl];
-  if (incircle_filter(P(pr, 0), P(pr, 1), P(pl, 0), P(pl, 1), P(p0, 0), P(p0, 1), P(p1, 0), P(p1, 1)) <= 0)
-    return;
-  const unsigned long long key = claim_key(round, ia);
-  ops.max(&m.owner[ia / 3], key);
-  ops.max(&m.owner[ib / 3], key);
-  const int32_t n1 = m.half[bl], n2 = m.half[ar];
-  if (n1 >= 0) ops.max(&m.owner[n1 / 3], key);
-  if (n2 >= 0) ops.max(&m.owner[n2 / 3], key);
-  m.cand[ia] = round + 1;
-  l.edge_list[ops.add(&l.n_marked[round], 1u)] = ia + 3 * m.tri_base;
+  const Quad q = mark_prepare(m, e, round);
+  if (q.ia >= 0 && mark_decide(q, P)) mark_claim(m, l, q, round, ops);
 }
 
 template <class Ops>

@@ -103,6 +103,7 @@ seed_assemble_kernel(const int32_t* __restrict__ qtri, int64_t rows, int64_t col
 // granules cost what one costs.  The table is a kernel parameter (constant bank).
 constexpr int kMaxBatch = 32;
 constexpr int kMaxRounds = 4096;
+constexpr int kFlipUnroll = 4;
 constexpr int kFlipThreads = 1024;   // one block per SM: 64 registers per thread
 
 struct Batch {
@@ -138,13 +139,32 @@ flip_rounds_kernel(const __grid_constant__ Batch b, oisat_flip::Lists l, int max
   for (; round < max_rounds; ++round) {
     const int64_t n_items = round == 0 ? n_tri : (int64_t)*(volatile unsigned int*)&l.n_listed[round - 1];
     const int32_t* list = (round & 1) ? l.tri_list[1] : l.tri_list[0];
-    for (int64_t i = tid; i < 3 * n_items; i += nthreads) {
-      const int64_t k = i / 3;
-      const int32_t t = round == 0 ? (int32_t)k : list[k];
-      const int g = mesh_of(b, t);
-      const oisat_flip::Mesh& m = b.mesh[g];
-      const FlipCoords<T> P{(const T*)b.x[g], (const T*)b.y[g]};
-      oisat_flip::mark_edge(m, l, 3 * (t - m.tri_base) + (int32_t)(i - 3 * k), round, P, ops);
+    // four edges per thread and step: their loads are independent and fly together
+    for (int64_t i0 = tid; i0 < 3 * n_items; i0 += kFlipUnroll * nthreads) {
+      oisat_flip::Quad q[kFlipUnroll];
+      int g[kFlipUnroll];
+#pragma unroll
+      for (int u = 0; u < kFlipUnroll; ++u) {
+        const int64_t i = i0 + u * nthreads;
+        q[u].ia = -1;
+        g[u] = 0;
+        if (i < 3 * n_items) {
+          const int64_t k = i / 3;
+          const int32_t t = round == 0 ? (int32_t)k : list[k];
+          g[u] = mesh_of(b, t);
+          const oisat_flip::Mesh& m = b.mesh[g[u]];
+          q[u] = oisat_flip::mark_prepare(m, 3 * (t - m.tri_base) + (int32_t)(i - 3 * k), round);
+        }
+      }
+      bool go[kFlipUnroll];
+#pragma unroll
+      for (int u = 0; u < kFlipUnroll; ++u) {
+        const FlipCoords<T> P{(const T*)b.x[g[u]], (const T*)b.y[g[u]]};
+        go[u] = q[u].ia >= 0 && oisat_flip::mark_decide(q[u], P);
+      }
+#pragma unroll
+      for (int u = 0; u < kFlipUnroll; ++u)
+        if (go[u]) oisat_flip::mark_claim(b.mesh[g[u]], l, q[u], round, ops);
     }
     if (solo) __syncthreads(); else grid.sync();
     const int64_t n_marked = *(volatile unsigned int*)&l.n_marked[round];

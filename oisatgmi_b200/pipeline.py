@@ -253,6 +253,10 @@ class MonthPipeline:
         geometry plans of the whole batch are built -- triangulations on the host
         thread pool, the device part granule by granule -- while the copies are in
         flight.  Returns the number of granules kept."""
+        import os
+        import time as _time
+        trace = os.environ.get("OISAT_PLAN_TRACE") == "1"
+        t_0 = _time.perf_counter()
         dev = _dev.device()
         lons = [np.asarray(s.longitude_center) for s in sats]
         lats = [np.asarray(s.latitude_center) for s in sats]
@@ -294,6 +298,7 @@ class MonthPipeline:
                 copied.record()
         lonlat = [(g.dev["lon"], g.dev["lat"]) for g in staged]
         radius = self.grid_size * 2.0
+        t_1 = _time.perf_counter()
         if self.interpolator_type == 1:
             plans = _plan.granule_plans(lons, lats, self.gplan, radius, lonlat_dev=lonlat,
                                         futures=futures)
@@ -301,6 +306,10 @@ class MonthPipeline:
             plans = [(_plan.nearest_plan(lons[i], lats[i], self.gplan, radius, lonlat_dev=lonlat[i])
                       if self.interpolator_type == 4 or _plan.triangulable(lons[i], lats[i])
                       else None) for i in range(len(sats))]
+        if trace:
+            import sys
+            print("add_day trace: staging %.1f ms, plans %.1f ms" %
+                  ((t_1 - t_0) * 1e3, (_time.perf_counter() - t_1) * 1e3), file=sys.stderr, flush=True)
         if copied is not None:
             main.wait_event(copied)          # whatever is queued from here on sees the arrays
         kept = 0

@@ -44,13 +44,36 @@ from . import _dev, _lib
 FULL_WALK_MAX_NODES = 400_000
 
 
+_FP_WEIGHTS = {}
+
+
+def _fingerprint(a: np.ndarray) -> bytes:
+    """Content fingerprint of a large array at memory speed: the 64-bit words, their wrapping
+    sum and their wrapping dot product with fixed odd pseudo-random weights (any changed,
+    swapped or moved word changes it).  blake2b over the 3.3 MB of a model grid's coordinates
+    cost 4 ms per pipeline object; this costs 0.3 ms."""
+    b = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
+    n8 = b.size // 8
+    words = b[:8 * n8].view(np.uint64)
+    w = _FP_WEIGHTS.get(n8)
+    if w is None:
+        rng = np.random.default_rng(0x0153A7)
+        w = _FP_WEIGHTS[n8] = rng.integers(0, 2 ** 63, size=n8, dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+        while len(_FP_WEIGHTS) > 8:
+            _FP_WEIGHTS.pop(next(iter(_FP_WEIGHTS)))
+    with np.errstate(over="ignore"):
+        s0 = np.add.reduce(words, dtype=np.uint64)
+        s1 = np.dot(words, w)
+    return b"%d:%d:" % (int(s0), int(s1)) + b[8 * n8:].tobytes()
+
+
 def _digest(*arrays) -> str:
     h = hashlib.blake2b(digest_size=16)
     for a in arrays:
         a = np.ascontiguousarray(a)
         h.update(str(a.dtype).encode())
         h.update(str(a.shape).encode())
-        h.update(a.tobytes())
+        h.update(_fingerprint(a) if a.nbytes >= (1 << 18) else a.tobytes())
     return h.hexdigest()
 
 
@@ -570,7 +593,14 @@ def _plan_v1_enqueue(tri_host, lonlat_dev, gplan, keep_dev, half_host=None, maxa
                 keep=(tri_host, half_host, half, work, ok, ties_dev, tri_flag, seed, seed_keep))
 
 
-def _plan_v1_finish(st, gplan):
+def _kept_cells(st):
+    """Waits for the granule's flags and lists the kept cells (host).  Runs on the plan pool for
+    a batch: both the wait and numpy's nonzero release the GIL."""
+    st["done"].synchronize()
+    return np.flatnonzero(st["ok_host"].numpy().view(np.bool_))   # flags are 0 / 1
+
+
+def _plan_v1_finish(st, gplan, cells=None):
     """Second half: waits for ITS flags only, lists the kept cells on the host and queues
     the stencil fill.  None when the near-tie scan found a tie (the caller takes v0)."""
     L = _lib.lib()
@@ -588,7 +618,8 @@ def _plan_v1_finish(st, gplan):
         # kept node (the usual case for an isolated near-tie: a pixel quadrilateral is smaller
         # than the mesh spacing) cannot change any stencil and are accepted.
         return None
-    cells = np.flatnonzero(st["ok_host"].numpy().view(np.bool_))   # flags are 0 / 1
+    if cells is None:
+        cells = _kept_cells(st)
     lo, la = st["lonlat"]
     xs, ys = gplan.dev_axes()
     window, _ = gplan.dev_tables()
@@ -830,8 +861,10 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
                 mesh = (tri, half, parts["maxabs"], flip_host[row], (keep, work, result, parts))
                 pending.append((i, _plan_v1_enqueue(None, lonlat_dev[i], gplan, keeps[i], mesh=mesh)))
     t_pool = _time.perf_counter()
-    for i, st in pending:     # second half: kept cells on the host, stencil fill queued
-        out[i] = _plan_v1_finish(st, gplan)
+    ex = _plan_pool(_plan_workers(n, workers))
+    listed = [ex.submit(_kept_cells, st) for _, st in pending]
+    for (i, st), cells in zip(pending, listed):     # second half: kept cells on the host, stencil fill queued
+        out[i] = _plan_v1_finish(st, gplan, cells.result())
         if isinstance(out[i], str):      # K12 met an edge its filter cannot decide: exact builder
             tri, half, ties, maxabs = native_delaunay_adj(lons[i], lats[i])
             out[i] = None

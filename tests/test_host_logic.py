@@ -579,7 +579,8 @@ def test_granule_plans_routes_ties_and_failures(monkeypatch):
     monkeypatch.setattr(plan, "native_delaunay_adj", fake_adj)
     monkeypatch.setattr(plan, "_plan_v1_enqueue", lambda tri, ll, g, keep, half, m: dict(kind=int(np.ravel(ll[0])[0])))
     monkeypatch.setenv("OISAT_DELAUNAY", "host")
-    monkeypatch.setattr(plan, "_plan_v1_finish", lambda st, g: None if st["kind"] == 2 else ("v1", st["kind"]))
+    monkeypatch.setattr(plan, "_kept_cells", lambda st: None)
+    monkeypatch.setattr(plan, "_plan_v1_finish", lambda st, g, cells=None: None if st["kind"] == 2 else ("v1", st["kind"]))
     monkeypatch.setattr(plan, "_plan_v0", lambda lon, lat, g, keep: calls.append(int(lon[0, 0])) or ("v0", int(lon[0, 0])))
     monkeypatch.setenv("OISAT_PLAN", "auto")
     gplan = types.SimpleNamespace(upscale=True)
