@@ -103,7 +103,7 @@ seed_assemble_kernel(const int32_t* __restrict__ qtri, int64_t rows, int64_t col
 // granules cost what one costs.  The table is a kernel parameter (constant bank).
 constexpr int kMaxBatch = 32;
 constexpr int kMaxRounds = 4096;
-constexpr int kFlipUnroll = 4;
+constexpr int kFlipUnroll = 1;      // 4 measured slower (3.22 vs 3.00 ms per day batch): the step is not latency bound per thread
 constexpr int kFlipThreads = 1024;   // one block per SM: 64 registers per thread
 
 struct Batch {
@@ -139,7 +139,6 @@ flip_rounds_kernel(const __grid_constant__ Batch b, oisat_flip::Lists l, int max
   for (; round < max_rounds; ++round) {
     const int64_t n_items = round == 0 ? n_tri : (int64_t)*(volatile unsigned int*)&l.n_listed[round - 1];
     const int32_t* list = (round & 1) ? l.tri_list[1] : l.tri_list[0];
-    // four edges per thread and step: their loads are independent and fly together
     for (int64_t i0 = tid; i0 < 3 * n_items; i0 += kFlipUnroll * nthreads) {
       oisat_flip::Quad q[kFlipUnroll];
       int g[kFlipUnroll];
@@ -285,6 +284,10 @@ int flip_chunk(const oisat_flip_item* items, int n_items, int32_t coord_dtype, v
     OISAT_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
   int max_rounds = kMaxRounds;
+  if (const char* e = getenv("OISAT_FLIP_MAX_ROUNDS")) {   // profiling: cost of the first k rounds
+    max_rounds = atoi(e);
+    if (max_rounds < 1 || max_rounds > kMaxRounds) max_rounds = kMaxRounds;
+  }
   unsigned int tail = 512;
   if (const char* e = getenv("OISAT_FLIP_TAIL")) tail = (unsigned int)atoi(e);
   unsigned long long* res = (unsigned long long*)result;

@@ -308,8 +308,14 @@ class MonthPipeline:
                       else None) for i in range(len(sats))]
         if trace:
             import sys
-            print("add_day trace: staging %.1f ms, plans %.1f ms" %
-                  ((t_1 - t_0) * 1e3, (_time.perf_counter() - t_1) * 1e3), file=sys.stderr, flush=True)
+            t_2 = _time.perf_counter()
+            done = copied.query() if copied is not None else True
+            if copied is not None:
+                copied.synchronize()
+            print("add_day trace: staging %.1f ms, plans %.1f ms; bulk copies %s when the plans were "
+                  "(waited %.1f ms more)" % ((t_1 - t_0) * 1e3, (t_2 - t_1) * 1e3,
+                                            "done" if done else "NOT done", (_time.perf_counter() - t_2) * 1e3),
+                  file=sys.stderr, flush=True)
         if copied is not None:
             main.wait_event(copied)          # whatever is queued from here on sees the arrays
         kept = 0

@@ -64,8 +64,12 @@ def batch(kind="omi", n=15):
         lat, lon = synth.swath_geolocation(nt, nx, node_lon_deg=-170.0 + 24.0 * k, rng=rng)
         parts.append(plan.native_seed_parts(lon, lat, pinned=True))
         coords.append((_dev.to_device(lon.ravel()), _dev.to_device(lat.ravel())))
-    for tail in ("0", "512", "4096", "16384"):
+    for tail, cut in (("0", None), ("512", None), ("4096", None), ("512", 1), ("512", 2), ("512", 4),
+                      ("512", 8), ("512", 16), ("512", 32), ("512", 64)):
         os.environ["OISAT_FLIP_TAIL"] = tail
+        os.environ.pop("OISAT_FLIP_MAX_ROUNDS", None)
+        if cut is not None:
+            os.environ["OISAT_FLIP_MAX_ROUNDS"] = str(cut)
         times = []
         for rep in range(4):
             meshes = [plan.seed_assemble_device(p) for p in parts]
@@ -77,9 +81,10 @@ def batch(kind="omi", n=15):
             t.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
         r = result.cpu().numpy()
-        print("batch of %d %s granules, tail %-6s: %.3f ms (min of 3 after warm-up); rounds %d flips %d "
-              "bad %d undecided %d" % (n, kind, tail, min(times[1:]), r[0, 0], r[0, 1], r[:, 2].sum(),
-                                       r[:, 3].sum()))
+        print("batch of %d %s granules, tail %-6s%s: %.3f ms (min of 3 after warm-up); rounds %d flips %d "
+              "bad %d undecided %d" % (n, kind, tail, "" if cut is None else " cut after %d rounds" % cut,
+                                       min(times[1:]), r[0, 0], r[0, 1], r[:, 2].sum(), r[:, 3].sum()))
+    os.environ.pop("OISAT_FLIP_MAX_ROUNDS", None)
 
 
 if __name__ == "__main__":
