@@ -410,7 +410,8 @@ def main():
     e2e = None
     if not args.no_e2e:
         e2e_times, h2d, d2h = [], 0, 0
-        parts = {"new_pipeline_s": [], "upload_and_plan_s": [], "tables_s": [], "kernels_d2h_s": []}
+        parts = {"new_pipeline_s": [], "upload_and_plan_s": [], "of_which_drain_s": [], "tables_s": [],
+                 "kernels_d2h_s": []}
         for it in range(args.e2e_steps + 1):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -430,6 +431,7 @@ def main():
                         batch.append(gg)
                         bhosts.append(hosts[i])
                 p2.add_day(batch, hosts=bhosts)
+            t_ret = time.perf_counter()
             torch.cuda.synchronize()
             t1 = time.perf_counter()
             p2.allocate()
@@ -442,6 +444,7 @@ def main():
                 e2e_times.append(dt)
                 parts["new_pipeline_s"].append(t_pipe - t0)
                 parts["upload_and_plan_s"].append(t1 - t_pipe)
+                parts["of_which_drain_s"].append(t1 - t_ret)
                 parts["tables_s"].append(t2 - t1)
                 parts["kernels_d2h_s"].append(t0 + dt - t2)
             h2d = p2.input_bytes() + p2.plan_bytes()

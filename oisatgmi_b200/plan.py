@@ -822,14 +822,38 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
     out = [None] * n
     pending = []
     seeded = []
+    seen = set()
     # The first half of a granule's device part (uploads, near-tie scan, point location,
     # flags to pinned memory) is queued as soon as ITS triangulation is done, while the
     # others are still on the pool -- and without waiting for the GPU: with a
     # synchronisation per granule the 15 device parts of a day (2 ms each) ran one after
     # the other behind the slowest triangulation.
     trace = [] if os.environ.get("OISAT_PLAN_TRACE") == "1" else None
+
+    def flush():
+        # The seeds that have arrived go through the rounds of flips together (one launch: a
+        # round costs its two barriers whatever it holds), then each granule's device part.
+        if not seeded:
+            return
+        t = _dev.torch()
+        groups = {}
+        for k, sd in enumerate(seeded):
+            groups.setdefault(_dev.dtype_code(lonlat_dev[sd[0]][0]), []).append(k)
+        for ks in groups.values():
+            result, work = flip_batch_device([(seeded[k][2], seeded[k][3], lonlat_dev[seeded[k][0]]) for k in ks])
+            flip_host = t.empty((len(ks), 4), dtype=t.int64, pin_memory=True)
+            flip_host.copy_(result, non_blocking=True)
+            for row, k in enumerate(ks):
+                i, parts, tri, half, keep = seeded[k]
+                mesh = (tri, half, parts["maxabs"], flip_host[row], (keep, work, result, parts))
+                pending.append((i, _plan_v1_enqueue(None, lonlat_dev[i], gplan, keeps[i], mesh=mesh)))
+        del seeded[:]
+
+    left = len(futures)
     for fut in as_completed(futures):
         i = futures[fut]
+        left -= 1
+        seen.add(fut)
         kind, got = fut.result()
         t_a = _time.perf_counter()
         if kind == "seed":       # K12 finishes the triangulation on the device
@@ -845,21 +869,12 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
                 continue
         if trace is not None:
             trace.append("%d:%.0f+%.1f" % (i, (t_a - t_start) * 1e3, (_time.perf_counter() - t_a) * 1e3))
-    if seeded:
-        # the seeds of the whole batch go through the rounds of flips together (one launch:
-        # a round costs its two barriers whatever it holds), then each granule's device part
-        t = _dev.torch()
-        groups = {}
-        for k, sd in enumerate(seeded):
-            groups.setdefault(_dev.dtype_code(lonlat_dev[sd[0]][0]), []).append(k)
-        for ks in groups.values():
-            result, work = flip_batch_device([(seeded[k][2], seeded[k][3], lonlat_dev[seeded[k][0]]) for k in ks])
-            flip_host = t.empty((len(ks), 4), dtype=t.int64, pin_memory=True)
-            flip_host.copy_(result, non_blocking=True)
-            for row, k in enumerate(ks):
-                i, parts, tri, half, keep = seeded[k]
-                mesh = (tri, half, parts["maxabs"], flip_host[row], (keep, work, result, parts))
-                pending.append((i, _plan_v1_enqueue(None, lonlat_dev[i], gplan, keeps[i], mesh=mesh)))
+        # do not let the device idle behind the slowest seed of the day (a date-line crosser takes
+        # twice as long on the host): when nothing else is ready, half a day's worth of seeds is
+        # a batch of its own
+        if left and len(seeded) >= max(4, n // 2) and not any(f.done() and f not in seen for f in futures):
+            flush()
+    flush()
     t_pool = _time.perf_counter()
     ex = _plan_pool(_plan_workers(n, workers))
     listed = [ex.submit(_kept_cells, st) for _, st in pending]
