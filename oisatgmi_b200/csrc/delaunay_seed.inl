@@ -255,8 +255,14 @@ struct SeedBuilder {
     for (int64_t r = 1; r < rows; ++r) take(r, cols - 1);
     for (int64_t c = cols - 2; c >= 0; --c) take(rows - 1, c);
     for (int64_t r = rows - 2; r >= 1; --r) take(r, 0);
-    for (int64_t r = 1; r + 1 < rows; ++r)
-      for (int64_t c = 1; c + 1 < cols; ++c) take(r, c);
+    // the rest line by line, one side of the map after the other: the two lips of a date-line
+    // tear are a map width apart, and a chain that alternates between them makes every
+    // insertion walk across the slivers that span the gap (5 ms instead of 1.4 for such a granule)
+    const double xmid = 0.5 * (xmin + xmax);
+    for (int side = 0; side < 2; ++side)
+      for (int64_t r = 1; r + 1 < rows; ++r)
+        for (int64_t c = 1; c + 1 < cols; ++c)
+          if (seam[(size_t)(r * cols + c)] == 1 && (x[r * cols + c] < xmid) == (side == 0)) take(r, c);
     const int64_t m = (int64_t)seq.size();
     ord.clear();
     hint.clear();
