@@ -453,14 +453,30 @@ def main():
             h2d = p2.input_bytes() + p2.plan_bytes()
             d2h = sum(v.nbytes for v in out.values() if hasattr(v, "nbytes"))
             day_px = p2.n_pixels()
+            builders = {}
+            for g in p2.granules:
+                b = getattr(g.plan, "builder", "?")
+                builders[b] = builders.get(b, 0) + 1
             del p2
         e2e_s = float(np.mean(e2e_times))
         e2e_val = day_px / e2e_s
+        # granules of this rank's day whose plan needed Qhull itself (builder v0q / v0: a near tie
+        # with a kept mesh node in its quadrilateral, 0.3 s each): with several ranks the slowest
+        # one sets the step, so the line says how many ranks had such a granule
+        fallback = sum(n for b, n in builders.items() if b in ("v0", "v0q"))
+        ranks_with_fallback = int(fallback > 0)
+        own_s = float(np.mean(parts["new_pipeline_s"]) + np.mean(parts["upload_and_plan_s"]))
         if world > 1:
             import torch.distributed as dist
             tv = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
             dist.all_reduce(tv, op=dist.ReduceOp.MAX)
             e2e_val = day_px * world / float(tv.item())
+            fv = torch.tensor([float(fallback > 0), float(fallback)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(fv, op=dist.ReduceOp.SUM)
+            ranks_with_fallback, fallback = int(fv[0].item()), int(fv[1].item())
+            ov = torch.tensor([own_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(ov, op=dist.ReduceOp.MIN)
+            own_s = float(ov.item())
         e2e = {"value": e2e_val, "unit": "px/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h),
                "batch": "%d day(s) = %d granules per step from pinned host memory; includes geometry-plan "
@@ -471,6 +487,9 @@ def main():
                         % (args.e2e_days, args.e2e_days * len(day), os.cpu_count() or 1),
                "s_per_step": e2e_s, "steps": len(e2e_times),
                "s_each_step": [round(float(v), 5) for v in e2e_times],
+               "plan_builders_rank0": builders, "granules_needing_qhull": fallback,
+               "ranks_with_such_a_granule": ranks_with_fallback,
+               "fastest_rank_upload_and_plan_s": own_s,
                "breakdown_s": {k: float(np.mean(v)) for k, v in parts.items()}}
 
     cpu = None
