@@ -67,6 +67,15 @@ class _DeviceVector:
         return a if dtype is None else a.astype(dtype)
 
 
+class _HostBlock(dict):
+    """host_arrays(pin=True): field -> view into one page-locked block (`block`; `offsets` of the
+    views; the first `head` bytes hold lon and lat, which the plan builders need first)."""
+
+    def __init__(self):
+        super().__init__()
+        self.block, self.offsets, self.head = None, {}, 0
+
+
 class _Granule:
     __slots__ = ("n_px", "nlev", "has_trop", "dev", "plan", "slot", "time", "host")
 
@@ -207,13 +216,29 @@ class MonthPipeline:
             "pmid": sat.pressure_mid, "sw": sat.scattering_weights,
             "trop": sat.tropopause if has_trop else None,
         }
-        out = {}
-        for k, a in src.items():
-            if a is None:
+        if not pin:
+            return {k: (None if a is None else t.from_numpy(np.ascontiguousarray(a).reshape(-1)))
+                    for k, a in src.items()}
+        # page-locked: ONE block per granule with the arrays as views into it (256-byte
+        # aligned, lon / lat first), so that add_day moves a granule with two copies
+        # instead of nine (the ~100 small copy calls of a day were 2 ms of its host time)
+        out = _HostBlock()
+        arrays = {k: np.ascontiguousarray(a).reshape(-1) for k, a in src.items() if a is not None}
+        off = 0
+        for k, a in arrays.items():
+            out.offsets[k] = off
+            off = (off + a.nbytes + 255) // 256 * 256
+            if k == "lat":
+                out.head = off
+        out.block = t.empty((off,), dtype=t.uint8, pin_memory=True)
+        for k in src:
+            if src[k] is None:
                 out[k] = None
                 continue
-            h = t.from_numpy(np.ascontiguousarray(a).reshape(-1))
-            out[k] = h.pin_memory() if pin else h
+            a = arrays[k]
+            view = out.block[out.offsets[k]:out.offsets[k] + a.nbytes].view(t.from_numpy(a[:0]).dtype)
+            view.numpy()[...] = a
+            out[k] = view
         return out
 
     def add_granule(self, sat, plan=None, host=None, pin=False):
@@ -258,6 +283,7 @@ class MonthPipeline:
         trace = os.environ.get("OISAT_PLAN_TRACE") == "1"
         t_0 = _time.perf_counter()
         dev = _dev.device()
+        t = _dev.torch()
         lons = [np.asarray(s.longitude_center) for s in sats]
         lats = [np.asarray(s.latitude_center) for s in sats]
         # the host share of the plans starts first: it needs nothing from the device
@@ -271,14 +297,23 @@ class MonthPipeline:
             g.nlev = np.shape(sat.pressure_mid)[0]
             g.has_trop = g.host["trop"] is not None
             g.dev = {}
-            for k in ("lon", "lat"):          # the plan builders need these first
-                g.dev[k] = g.host[k].to(dev, non_blocking=True)
+            if isinstance(g.host, _HostBlock):
+                # one device block per granule, the fields are views; lon / lat (its head) now
+                g.dev_block = t.empty(g.host.block.shape, dtype=t.uint8, device=dev)
+                g.dev_block[:g.host.head].copy_(g.host.block[:g.host.head], non_blocking=True)
+                for k, h in g.host.items():
+                    g.dev[k] = None if h is None else (
+                        g.dev_block[g.host.offsets[k]:g.host.offsets[k] + h.numel() * h.element_size()]
+                        .view(h.dtype))
+            else:
+                for k in ("lon", "lat"):          # the plan builders need these first
+                    g.dev[k] = g.host[k].to(dev, non_blocking=True)
             staged.append(g)
         # the bulk of the reader arrays travels on a copy stream of its own: the plan kernels
         # queued below need only lon / lat and would otherwise sit behind 24 MB per granule
-        t = _dev.torch()
         main = t.cuda.current_stream()
-        pinned = all(h is None or h.is_pinned() for g in staged for h in g.host.values())
+        blocks = all(isinstance(g.host, _HostBlock) for g in staged)
+        pinned = blocks or all(h is None or h.is_pinned() for g in staged for h in g.host.values())
         side = _copy_stream() if pinned else None
         for g in staged:
             for k, h in g.host.items():
@@ -291,6 +326,9 @@ class MonthPipeline:
             side.wait_stream(main)          # the destinations were allocated on `main`
             with t.cuda.stream(side):
                 for g in staged:
+                    if isinstance(g.host, _HostBlock):
+                        g.dev_block[g.host.head:].copy_(g.host.block[g.host.head:], non_blocking=True)
+                        continue
                     for k, h in g.host.items():
                         if k not in ("lon", "lat") and h is not None:
                             g.dev[k].copy_(h, non_blocking=True)
