@@ -77,7 +77,7 @@ class _HostBlock(dict):
 
 
 class _Granule:
-    __slots__ = ("n_px", "nlev", "has_trop", "dev", "plan", "slot", "time", "host")
+    __slots__ = ("n_px", "nlev", "has_trop", "dev", "plan", "slot", "time", "host", "dev_block")
 
 
 def finalize_and_oi(acc, n_cell, sensor, gas, error_ctm):
