@@ -818,11 +818,9 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
     if futures is None:
         return [granule_plan(lons[i], lats[i], gplan, radius, lonlat_dev=lonlat_dev[i], cache=False)
                 for i in range(n)]
-    from concurrent.futures import as_completed
     out = [None] * n
     pending = []
     seeded = []
-    seen = set()
     # The first half of a granule's device part (uploads, near-tie scan, point location,
     # flags to pinned memory) is queued as soon as ITS triangulation is done, while the
     # others are still on the pool -- and without waiting for the GPU: with a
@@ -849,11 +847,8 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
                 pending.append((i, _plan_v1_enqueue(None, lonlat_dev[i], gplan, keeps[i], mesh=mesh)))
         del seeded[:]
 
-    left = len(futures)
-    for fut in as_completed(futures):
+    def handle(fut):
         i = futures[fut]
-        left -= 1
-        seen.add(fut)
         kind, got = fut.result()
         t_a = _time.perf_counter()
         if kind == "seed":       # K12 finishes the triangulation on the device
@@ -861,39 +856,65 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
         else:
             tri, half, ties, maxabs = got
             if tri is None:
-                continue
+                return
             if ties == 0 or _plan_mode() == "v1":
                 pending.append((i, _plan_v1_enqueue(tri, lonlat_dev[i], gplan, keeps[i], half, maxabs)))
             else:
                 out[i] = _plan_v0(lons[i], lats[i], gplan, _dev.to_host(keeps[i]).astype(bool))
-                continue
+                return
         if trace is not None:
             trace.append("%d:%.0f+%.1f" % (i, (t_a - t_start) * 1e3, (_time.perf_counter() - t_a) * 1e3))
-        # do not let the device idle behind the slowest seed of the day (a date-line crosser takes
-        # twice as long on the host): when nothing else is ready, half a day's worth of seeds is
-        # a batch of its own
-        if left and len(seeded) >= max(4, n // 2) and not any(f.done() and f not in seen for f in futures):
-            flush()
-    flush()
-    t_pool = _time.perf_counter()
-    ex = _plan_pool(_plan_workers(n, workers))
-    listed = [ex.submit(_kept_cells, st) for _, st in pending]
-    for (i, st), cells in zip(pending, listed):     # second half: kept cells on the host, stencil fill queued
-        out[i] = _plan_v1_finish(st, gplan, cells.result())
+
+    def finalize(i, st):
+        # second half: kept cells on the host, stencil fill queued
+        out[i] = _plan_v1_finish(st, gplan)
         if isinstance(out[i], str):      # K12 met an edge its filter cannot decide: exact builder
             tri, half, ties, maxabs = native_delaunay_adj(lons[i], lats[i])
             out[i] = None
             if tri is None:
-                continue
+                return
             if ties == 0 or _plan_mode() == "v1":
                 out[i] = _plan_v1_device(tri, lonlat_dev[i], gplan, keeps[i], half, maxabs)
             else:
                 out[i] = _plan_v0(lons[i], lats[i], gplan, _dev.to_host(keeps[i]).astype(bool))
-                continue
+                return
         if out[i] is None and _plan_mode() != "v0walk":      # near tie: Qhull's triangles, K1's walk
             out[i] = _plan_v0_device(lons[i], lats[i], lonlat_dev[i], gplan, keeps[i])
         if out[i] is None:
             out[i] = _plan_v0(lons[i], lats[i], gplan, _dev.to_host(keeps[i]).astype(bool))
+
+    def finish_ready():
+        # granules whose device part has run are finished while the host would otherwise wait
+        # for the slower seeds of the day
+        for k, (i, st) in enumerate(pending):
+            ev = st.get("done")
+            if ev is not None and ev.query():
+                del pending[k]
+                finalize(i, st)
+                return True
+        return False
+
+    from concurrent.futures import wait, FIRST_COMPLETED
+    not_done = set(futures)
+    while not_done:
+        ready = [f for f in not_done if f.done()]
+        if ready:
+            for f in ready:
+                not_done.discard(f)
+                handle(f)
+            continue
+        # nothing has arrived: do not let the device idle behind the slowest seed of the day (a
+        # date-line crosser takes twice as long on the host) -- half a day's worth of seeds is a
+        # batch of its own -- and use the wait for the finished granules' second halves
+        if len(seeded) >= max(4, n // 2):
+            flush()
+        elif not finish_ready():
+            wait(not_done, timeout=0.0005, return_when=FIRST_COMPLETED)
+    flush()
+    t_pool = _time.perf_counter()
+    for i, st in list(pending):
+        finalize(i, st)
+    del pending[:]
     if trace is not None:
         import sys
         print("granule_plans trace: pool %.1f ms, finish %.1f ms; (granule:ready+enqueue ms) %s" %
