@@ -827,6 +827,15 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
     # synchronisation per granule the 15 device parts of a day (2 ms each) ran one after
     # the other behind the slowest triangulation.
     trace = [] if os.environ.get("OISAT_PLAN_TRACE") == "1" else None
+    marks = []
+
+    def mark(label):
+        if trace is not None:
+            e = _dev.torch().cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((label, (_time.perf_counter() - t_start) * 1e3, e))
+
+    mark("K0 queued")
 
     def flush():
         # The seeds that have arrived go through the rounds of flips together (one launch: a
@@ -839,12 +848,15 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
             groups.setdefault(_dev.dtype_code(lonlat_dev[sd[0]][0]), []).append(k)
         for ks in groups.values():
             result, work = flip_batch_device([(seeded[k][2], seeded[k][3], lonlat_dev[seeded[k][0]]) for k in ks])
+            mark("flips of %d queued behind" % len(ks))
             flip_host = t.empty((len(ks), 4), dtype=t.int64, pin_memory=True)
             flip_host.copy_(result, non_blocking=True)
+            mark("flips of %d" % len(ks))
             for row, k in enumerate(ks):
                 i, parts, tri, half, keep = seeded[k]
                 mesh = (tri, half, parts["maxabs"], flip_host[row], (keep, work, result, parts))
                 pending.append((i, _plan_v1_enqueue(None, lonlat_dev[i], gplan, keeps[i], mesh=mesh)))
+        mark("K1 of the batch")
         del seeded[:]
 
     def handle(fut):
@@ -917,6 +929,11 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
     del pending[:]
     if trace is not None:
         import sys
+        mark("end")
+        _dev.torch().cuda.synchronize()
+        print("granule_plans device marks (label: host ms / device ms): " +
+              "; ".join("%s: %.1f / %.1f" % (lab, th, marks[0][2].elapsed_time(e) + marks[0][1])
+                        for lab, th, e in marks), file=sys.stderr, flush=True)
         print("granule_plans trace: pool %.1f ms, finish %.1f ms; (granule:ready+enqueue ms) %s" %
               ((t_pool - t_start) * 1e3, (_time.perf_counter() - t_pool) * 1e3, " ".join(trace)),
               file=sys.stderr, flush=True)
