@@ -18,9 +18,10 @@ accumulation, (all-reduce when N > 1), means, bias correction, the 99-factor OI
 sweep, the knee on the host and the OI update.  `value` = L2 pixels / s with the
 reader arrays and the geometry plans already in HBM.  `e2e` = the same metric
 for one DAY batch from host memory, everything included: pinned host -> device
-copies of the reader arrays, geometry plans built from scratch while those are in
-flight (native Delaunay on all host cores, K0/K1 on the GPU), all kernels, device
--> host copy of the gridded results.
+copies of the reader arrays (on a copy stream), geometry plans built from scratch
+while those are in flight (host: quad classification and seam triangulation on all
+cores; device: K0, the flips that finish the triangulation (K12), K1), all kernels,
+device -> host copy of the gridded results.
 """
 from __future__ import annotations
 
