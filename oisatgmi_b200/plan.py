@@ -440,13 +440,11 @@ def flip_batch_device(meshes):
     L = _lib.lib()
     n = len(meshes)
     items = (_lib.FlipItem * n)()
-    total = 0
     code = _dev.dtype_code(meshes[0][2][0])
     for k, (tri, half, (lo, la)) in enumerate(meshes):
         if _dev.dtype_code(lo) != code:
             raise _lib.OisatError("flip batch: coordinates of mixed dtypes")
         items[k] = _lib.FlipItem(tri.data_ptr(), half.data_ptr(), tri.shape[0], lo.data_ptr(), la.data_ptr())
-        total += tri.shape[0]
     per_chunk = max(sum(m[0].shape[0] for m in meshes[c:c + 32]) for c in range(0, n, 32))
     work = _dev.empty((int(L.oisat_flip_workspace_bytes(per_chunk)),), "uint8")
     result = _dev.empty((n, 4), "int64")
@@ -603,8 +601,7 @@ def _plan_v1_enqueue(tri_host, lonlat_dev, gplan, keep_dev, half_host=None, maxa
 
 
 def _kept_cells(st):
-    """Waits for the granule's flags and lists the kept cells (host).  Runs on the plan pool for
-    a batch: both the wait and numpy's nonzero release the GIL."""
+    """Waits for the granule's flags and lists the kept cells (host)."""
     st["done"].synchronize()
     return np.flatnonzero(st["ok_host"].numpy().view(np.bool_))   # flags are 0 / 1
 
@@ -615,7 +612,7 @@ def _plan_v1_finish(st, gplan, cells=None):
     L = _lib.lib()
     st["done"].synchronize()
     if st["flip_host"] is not None:
-        rounds, flips, bad, unsure = (int(v) for v in st["flip_host"])
+        bad, unsure = int(st["flip_host"][2]), int(st["flip_host"][3])
         if bad or unsure:        # an edge the filter cannot decide: the exact host builder's job
             return "host"
     near_ties = affected = 0
