@@ -120,7 +120,7 @@ int64_t oisat_h_delaunay_swath_adj(const double* h_x, const double* h_y, int64_t
  *   seeded quad (-1: not seeded); h_otri / h_ohalf (3 per triangle, out_capacity triangles):
  *   the triangles outside the lattice and their twin half-edges in the numbering of the
  *   result; info[5] = {seeded quads, seam vertices, outside triangles, sigma, declining
- *   check}.  Returns the number of triangles, 0 when the construction does not apply (the
+ *   check}; *max_abs_coord (may be NULL): the largest |coordinate|.  Returns the number of triangles, 0 when the construction does not apply (the
  *   caller uses oisat_h_delaunay_swath_adj), negative OISAT_E_* on bad arguments.
  * HOST: oisat_h_delaunay_seed -- the same construction whole on the host (flags bit 0: with
  *   Lawson's flips; bit 1: with the near-tie scan), and oisat_h_flip_rounds, the device
@@ -132,7 +132,8 @@ int64_t oisat_h_delaunay_swath_adj(const double* h_x, const double* h_y, int64_t
  *   caller must take the exact host builder.  workspace: oisat_flip_workspace_bytes. */
 int64_t oisat_h_delaunay_seed_parts(const double* h_x, const double* h_y, int64_t n_rows,
                                     int64_t n_cols, int32_t* h_qtri, int32_t* h_otri,
-                                    int32_t* h_ohalf, int64_t out_capacity, int64_t* info);
+                                    int32_t* h_ohalf, int64_t out_capacity, int64_t* info,
+                                    double* max_abs_coord);
 int64_t oisat_h_delaunay_seed(const double* h_x, const double* h_y, int64_t n_rows,
                               int64_t n_cols, int32_t* h_tri, int64_t tri_capacity,
                               int32_t* h_half, int64_t* n_ties, int32_t flags, int64_t* info);

@@ -64,7 +64,7 @@ PROTOTYPES = {
     "oisat_h_delaunay": (i64, [vp, vp, i64, vp, i64, C.POINTER(i64)]),
     "oisat_h_delaunay_swath": (i64, [vp, vp, i64, i64, vp, i64, C.POINTER(i64), C.POINTER(i32)]),
     "oisat_h_delaunay_swath_adj": (i64, [vp, vp, i64, i64, vp, i64, vp, C.POINTER(i64), C.POINTER(i32)]),
-    "oisat_h_delaunay_seed_parts": (i64, [vp, vp, i64, i64, vp, vp, vp, i64, vp]),
+    "oisat_h_delaunay_seed_parts": (i64, [vp, vp, i64, i64, vp, vp, vp, i64, vp, vp]),
     "oisat_h_delaunay_seed": (i64, [vp, vp, i64, i64, vp, i64, vp, C.POINTER(i64), i32, vp]),
     "oisat_h_flip_rounds": (C.c_int, [vp, vp, vp, vp, i64, i64, vp]),
     "oisat_seed_assemble": (C.c_int, [vp, i64, i64, i32, i64, vp, vp, i64, vp, vp, vp]),

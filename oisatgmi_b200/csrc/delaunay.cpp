@@ -636,12 +636,13 @@ extern "C" int64_t oisat_h_delaunay_seed(const double* h_x, const double* h_y, i
 // receives, per lattice quad, the index of the first of its two triangles (-1: the quad is
 // not part of the seed); h_otri / h_ohalf (3 per triangle, out_capacity triangles) the
 // triangles outside the lattice and their twins in the numbering of the result.  info
-// receives {seeded quads, seam vertices, outside triangles, sigma, declining check}.
+// receives {seeded quads, seam vertices, outside triangles, sigma, declining check},
+// *max_abs_coord (may be NULL) the largest |coordinate| (oisat_near_ties scales with it).
 // Returns the number of triangles of the seed, 0 when the construction does not apply.
 extern "C" int64_t oisat_h_delaunay_seed_parts(const double* h_x, const double* h_y, int64_t n_rows,
                                                int64_t n_cols, int32_t* h_qtri, int32_t* h_otri,
                                                int32_t* h_ohalf, int64_t out_capacity,
-                                               int64_t* info) {
+                                               int64_t* info, double* max_abs_coord) {
   if (!h_x || !h_y || !h_qtri || !h_otri || !h_ohalf || !info || n_rows < 1 || n_cols < 1 ||
       n_rows * n_cols > (int64_t)0x3fffffff)
     return OISAT_E_ARG;
@@ -653,6 +654,7 @@ extern "C" int64_t oisat_h_delaunay_seed_parts(const double* h_x, const double* 
   const int rc = g.seed();
   info[0] = g.n_quads; info[1] = g.n_seam; info[2] = g.n_outside; info[3] = g.sigma;
   info[4] = g.why * 100 - g.rec_fail;
+  if (max_abs_coord) *max_abs_coord = g.maxabs;
   // (exact ties met while triangulating the SEAM do not matter: that triangulation only has
   // to be valid, not Delaunay; a tie of the final mesh leaves an edge the device's filter
   // cannot decide and is reported there)

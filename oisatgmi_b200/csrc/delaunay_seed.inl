@@ -35,7 +35,7 @@ struct SeedBuilder {
   const double* y;
   int64_t rows = 0, cols = 0, n = 0;
   int sigma = 0;                         // +1: (r,c) -> (r,c+1) -> (r+1,c) is counter-clockwise
-  std::vector<uint8_t> quad, seam, edge_is_seam;
+  std::vector<uint8_t> quad, seam, edge_is_seam, pad;
   std::vector<int8_t> o1, o2;
   std::vector<int32_t> qtri, seq, ord, hint, label, newidx, queue, stack, crossed;
   std::vector<int32_t> otri, ohalf;      // the triangles outside the lattice (result numbering)
@@ -43,6 +43,7 @@ struct SeedBuilder {
   LatticeBuilder sub;                    // triangulation of the seam vertices
   int64_t ntri = 0, ties = 0, flips = 0, n_quads = 0, n_seam = 0, n_outside = 0;
   int rec_fail = 0;
+  double maxabs = 0.0;                   // largest |coordinate| (the near-tie scan scales with it)
   int why = 0;                           // which check declined (diagnostic)
 
   static int32_t next(int32_t e) { return e % 3 == 2 ? e - 2 : e + 1; }
@@ -184,28 +185,53 @@ struct SeedBuilder {
     if (rows < 2 || cols < 2) return why = -1;
     n = rows * cols;
     if (n > (int64_t)0x1fffffff) return why = -1;
-    double xmin = x[0], xmax = x[0];
-    for (int64_t i = 0; i < n; ++i) {
-      if (!(std::fabs(x[i]) <= 1e300) || !(std::fabs(y[i]) <= 1e300)) return why = -1;
+    double xmin = x[0], xmax = x[0], amax = 0.0;
+    for (int64_t i = 0; i < n; ++i) {       // (NaN fails both comparisons below)
       xmin = std::min(xmin, x[i]);
       xmax = std::max(xmax, x[i]);
+      amax = std::max(amax, std::max(std::fabs(x[i]), std::fabs(y[i])));
     }
+    bool finite = amax <= 1e300;
+    for (int64_t i = 0; finite && i < n; i += 4096) {   // max() drops NaN operands: look for them
+      double sum = 0.0;
+      const int64_t e = std::min(n, i + 4096);
+      for (int64_t k = i; k < e; ++k) sum += x[k] * 0.0 + y[k] * 0.0;
+      finite = sum == 0.0;
+    }
+    if (!finite) return why = -1;
+    maxabs = amax;
     const double reach = 0.5 * (xmax - xmin);
     const int64_t qc = cols - 1, nq = (rows - 1) * qc;
     // ---- 1. quads
     o1.resize((size_t)nq);
     o2.resize((size_t)nq);
     int64_t pos = 0, neg = 0;
-    for (int64_t r = 0; r + 1 < rows; ++r)
+    for (int64_t r = 0; r + 1 < rows; ++r) {
+      // the floating-point filter of orient2d for a whole line of quads, no branches (the loop
+      // vectorises); the few signs it cannot certify (0 here) are decided exactly below
+      const double* xa = x + r * cols;
+      const double* ya = y + r * cols;
+      const double* xc = xa + cols;
+      const double* yc = ya + cols;
+      int8_t* q1 = o1.data() + r * qc;
+      int8_t* q2 = o2.data() + r * qc;
       for (int64_t c = 0; c < qc; ++c) {
-        const int64_t a = r * cols + c, b = a + 1, cc = a + cols, d = cc + 1;
-        const int s1 = orient2d(x[a], y[a], x[b], y[b], x[cc], y[cc]);
-        const int s2 = orient2d(x[b], y[b], x[d], y[d], x[cc], y[cc]);
-        o1[(size_t)(r * qc + c)] = (int8_t)s1;
-        o2[(size_t)(r * qc + c)] = (int8_t)s2;
-        pos += (s1 > 0) + (s2 > 0);
-        neg += (s1 < 0) + (s2 < 0);
+        // (a, b, cc) and (b, d, cc) with a = (r, c), b = (r, c + 1), cc = (r + 1, c), d = (r + 1, c + 1)
+        const double l1 = (xa[c] - xc[c]) * (ya[c + 1] - yc[c]), r1 = (ya[c] - yc[c]) * (xa[c + 1] - xc[c]);
+        const double l2 = (xa[c + 1] - xc[c]) * (yc[c + 1] - yc[c]), r2 = (ya[c + 1] - yc[c]) * (xc[c + 1] - xc[c]);
+        const double d1 = l1 - r1, d2 = l2 - r2;
+        const bool k1 = std::fabs(d1) > kOrientBound * (std::fabs(l1) + std::fabs(r1));
+        const bool k2 = std::fabs(d2) > kOrientBound * (std::fabs(l2) + std::fabs(r2));
+        q1[c] = (int8_t)(k1 ? ((d1 > 0.0) - (d1 < 0.0)) : 0);
+        q2[c] = (int8_t)(k2 ? ((d2 > 0.0) - (d2 < 0.0)) : 0);
       }
+      for (int64_t c = 0; c < qc; ++c) {
+        if (q1[c] == 0) q1[c] = (int8_t)orient2d(xa[c], ya[c], xa[c + 1], ya[c + 1], xc[c], yc[c]);
+        if (q2[c] == 0) q2[c] = (int8_t)orient2d(xa[c + 1], ya[c + 1], xc[c + 1], yc[c + 1], xc[c], yc[c]);
+        pos += (q1[c] > 0) + (q2[c] > 0);
+        neg += (q1[c] < 0) + (q2[c] < 0);
+      }
+    }
     sigma = pos >= neg ? 1 : -1;
     double area_lat = 0.0;
     quad.assign((size_t)nq, 0);
@@ -229,19 +255,30 @@ struct SeedBuilder {
     // ---- 2. seam vertices and seam edges
     seam.assign((size_t)n, 0);
     n_seam = 0;
-    for (int64_t r = 0; r < rows; ++r)
-      for (int64_t c = 0; c < cols; ++c)
-        if (!(valid(r - 1, c - 1) && valid(r - 1, c) && valid(r, c - 1) && valid(r, c))) {
-          seam[(size_t)(r * cols + c)] = 1;
-          ++n_seam;
-        }
-    if (n_seam * 3 > n) return why = -3;        // more seam than lattice: not worth seeding
     int64_t n_seam_edges = 0;
-    for (int64_t r = 0; r < rows; ++r)
-      for (int64_t c = 0; c < cols; ++c) {
-        if (c + 1 < cols && valid(r, c) != valid(r - 1, c)) ++n_seam_edges;
-        if (r + 1 < rows && valid(r, c) != valid(r, c - 1)) ++n_seam_edges;
+    {
+      // quad validity with a ring of zeros around it: pad[(r + 1) * pc + (c + 1)] = valid(r, c)
+      const int64_t pc = qc + 2;
+      pad.assign((size_t)((rows + 1) * pc), 0);
+      for (int64_t r = 0; r + 1 < rows; ++r)
+        std::copy(quad.begin() + r * qc, quad.begin() + (r + 1) * qc, pad.begin() + (r + 1) * pc + 1);
+      for (int64_t r = 0; r < rows; ++r) {
+        const uint8_t* up = pad.data() + r * pc;          // quads (r - 1, .)
+        const uint8_t* dn = up + pc;                      // quads (r, .)
+        uint8_t* sv = seam.data() + r * cols;
+        int64_t ns = 0, ne = 0;
+        for (int64_t c = 0; c < cols; ++c) {              // quads (., c - 1) at [c], (., c) at [c + 1]
+          const uint8_t v = (uint8_t)!(up[c] & up[c + 1] & dn[c] & dn[c + 1]);
+          sv[c] = v;
+          ns += v;
+          ne += (c + 1 < cols) & (dn[c + 1] != up[c + 1]);   // edge (r, c) - (r, c + 1)
+          ne += (r + 1 < rows) & (dn[c + 1] != dn[c]);       // edge (r, c) - (r + 1, c)
+        }
+        n_seam += ns;
+        n_seam_edges += ne;
       }
+    }
+    if (n_seam * 3 > n) return why = -3;        // more seam than lattice: not worth seeding
     // ---- 3. the seam vertices as a chain: outline first, then the rest line by line;
     //         inserted coarse to fine along the chain (every 2^L-th, L descending), each
     //         next to a chain neighbour inserted before it
@@ -329,12 +366,12 @@ struct SeedBuilder {
     //          cross-track steps have seam vertices close by on both sides: not Delaunay edges.
     //          They are put in by flipping away the edges that cross them (Sloan 1993); the
     //          result is still a triangulation of the seam vertices, which is all the seed needs.
-    for (int64_t r = 0; r < rows; ++r)
-      for (int64_t c = 0; c < cols; ++c) {
-        const int32_t u = (int32_t)(r * cols + c);
-        if (c + 1 < cols && valid(r, c) != valid(r - 1, c) && !recover(u, u + 1)) return why = -8;
-        if (r + 1 < rows && valid(r, c) != valid(r, c - 1) && !recover(u, u + (int32_t)cols)) return why = -8;
-      }
+    for (int64_t k = 0; k < m; ++k) {            // both ends of a seam edge are seam vertices
+      const int32_t u = seq[(size_t)k];
+      const int64_t r = u / cols, c = u % cols;
+      if (c + 1 < cols && valid(r, c) != valid(r - 1, c) && !recover(u, u + 1)) return why = -8;
+      if (r + 1 < rows && valid(r, c) != valid(r, c - 1) && !recover(u, u + (int32_t)cols)) return why = -8;
+    }
     // ---- 5. inside / outside
     const int64_t T = sub.ntri;
     label.assign((size_t)T, 0);

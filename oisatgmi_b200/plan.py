@@ -385,15 +385,16 @@ def native_seed_parts(lon, lat, pinned=False, device_index=None):
         buf = np.empty((nq + 6 * cap,), dtype=np.int32)
     qtri, otri, ohalf = buf[:nq], buf[nq:nq + 3 * cap], buf[nq + 3 * cap:]
     info = np.zeros(5, dtype=np.int64)
+    maxabs = np.zeros(1, dtype=np.float64)
     nt = L.oisat_h_delaunay_seed_parts(x.ctypes.data, y.ctypes.data, shape[0], shape[1],
                                        qtri.ctypes.data, otri.ctypes.data, ohalf.ctypes.data, cap,
-                                       info.ctypes.data)
+                                       info.ctypes.data, maxabs.ctypes.data)
     if nt <= 0:
         return None
     n_out = int(info[2])
     return dict(pinned=bool(pinned), qtri=qtri, otri=otri[:3 * n_out], ohalf=ohalf[:3 * n_out], n_quads=int(info[0]),
                 n_outside=n_out, sigma=int(info[3]), n_tri=int(nt), rows=int(shape[0]),
-                cols=int(shape[1]), maxabs=float(max(np.abs(x).max(), np.abs(y).max())))
+                cols=int(shape[1]), maxabs=float(maxabs[0]))
 
 
 def host_triangulation(lon, lat, pinned=False, device_index=None):
