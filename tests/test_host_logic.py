@@ -592,6 +592,28 @@ def test_granule_plans_routes_ties_and_failures(monkeypatch):
     assert plan._plan_pool(3) is plan._plan_pool(3)
 
 
+def test_cache_keys_see_every_change_of_a_large_array():
+    """plan._digest keys the cached grid plans; arrays of a model grid's size are fingerprinted
+    at memory speed (word sum + dot product with fixed odd weights) instead of hashed: one
+    changed bit, two swapped elements, another dtype or shape must still change the key, equal
+    content must not."""
+    rng = np.random.default_rng(3)
+    a = rng.normal(size=(361, 576))
+    b = rng.normal(size=(361, 576)).astype(np.float32)
+    d = plan._digest(a, b)
+    assert d == plan._digest(a.copy(), b.copy())
+    a1 = a.copy()
+    a1[200, 300] = np.nextafter(a1[200, 300], np.inf)
+    a2 = a.copy()
+    a2[5, 6], a2[5, 7] = a[5, 7], a[5, 6]
+    b1 = b.copy()
+    b1[-1, -1] += np.float32(1.0)              # the odd tail word of a float32 array
+    for changed in ((a1, b), (a2, b), (a, b1), (a.reshape(576, 361), b), (a.astype(np.float32), b), (b, a)):
+        assert plan._digest(*changed) != d
+    small = np.arange(12.0)
+    assert plan._digest(small) == plan._digest(small.copy()) != plan._digest(small[::-1])
+
+
 def test_ext_fields_match_the_oracle_restatement():
     """oisatgmi_b200.ext_output (GEOS ExtData form of the scaling factors, tools/convert2EXT.py)
     against oracle.output.ext_fields, which is pinned to the unmodified script where the
