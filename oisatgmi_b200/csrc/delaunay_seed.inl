@@ -445,6 +445,29 @@ struct SeedBuilder {
       }
     }
     if (!(std::fabs(area_in - area_lat) <= 1e-9 * std::max(area_lat, 1e-300))) return why = -11;
+    // ---- 7. every point must be a vertex of the seed.  A pixel that does not sit where the
+    //         lattice puts it -- inside somebody else's quad: its own four quads are folded and
+    //         dropped -- is a seam vertex whose triangles are all labelled "inside" and go away
+    //         with them; the seed would be a valid triangulation of the OTHER points.  Two
+    //         counts catch that and anything like it: a seam vertex must be a corner of a seeded
+    //         quad or of an outside triangle (and must have been inserted: a repeated point is
+    //         not), and the triangles must be as many as Euler's formula allows for n vertices
+    //         and h hull edges, T = 2 n - 2 - h.
+    for (int64_t k = 0; k < 3 * n_outside; ++k) seam[(size_t)otri[(size_t)k]] = 3;
+    int64_t hull_edges = n_seam_edges;
+    for (int64_t k = 0; k < 3 * n_outside; ++k) {
+      const int32_t g = ohalf[(size_t)k];
+      if (g < 0) ++hull_edges;
+      else if (g < 6 * n_quads) --hull_edges;     // a seam edge with an outside triangle behind it
+    }
+    for (int64_t k = 0; k < m; ++k) {
+      const int32_t v = seq[(size_t)k];
+      if (sub.vtri[(size_t)v] < 0) return why = -12;
+      if (seam[(size_t)v] == 3) continue;
+      const int64_t r = v / cols, c = v % cols;
+      if (!(valid(r - 1, c - 1) || valid(r - 1, c) || valid(r, c - 1) || valid(r, c))) return why = -12;
+    }
+    if (ntri != 2 * n - 2 - hull_edges) return why = -13;
     ties = sub.ties;
     flips = 0;
     return 0;

@@ -498,6 +498,76 @@ def test_lattice_seed_declines_or_is_exact_on_random_lattices():
     assert _flip_rounds(lon, lat, tri, half, max_rounds=2)[2] > 0
 
 
+def test_lattice_seed_never_loses_a_point():
+    """A pixel that does not sit where the lattice puts it (moved into somebody else's quad: its
+    own four quads are folded and dropped) used to vanish from the seed -- all the triangles of
+    the seam triangulation around it are labelled "inside" and replaced by lattice quads that do
+    not know it.  The construction must decline such lattices (or get them right), and a
+    randomised sweep over swath pieces, warped / folded / jittered lattices and displaced or
+    repeated pixels must never give a triangulation other than the incremental builder's."""
+    rng = np.random.default_rng(12)
+    gx, gy = np.meshgrid(np.arange(19.0), np.arange(13.0))
+    lon, lat = gx + rng.uniform(-0.3, 0.3, gx.shape), gy + rng.uniform(-0.3, 0.3, gy.shape)
+    lon[7, 12] = lon[0, 0] + 0.4                       # row 7, but at the left edge of the map
+    got = _seed_whole(lon, lat)
+    ref, ties, path = plan.native_delaunay_path(lon, lat)
+    assert ties == 0 and len(ref) == 2 * lon.size - 2 - (len(ref) * 3 - 2 * _interior_edges(ref))
+    if got is not None:
+        res = _flip_rounds(lon, lat, got[0], got[1])
+        assert res[3] == 0 and _tri_set(got[0]) == _tri_set(ref)
+    checked = declined = 0
+    for trial in range(400):
+        kind = trial % 4
+        if kind == 0:
+            lat, lon = synth.swath_geolocation(int(rng.integers(2, 120)), int(rng.integers(2, 40)),
+                                               node_lon_deg=float(rng.uniform(-180, 180)),
+                                               u0_deg=float(rng.uniform(-85, 60)), u1_deg=float(rng.uniform(61, 140)),
+                                               rng=rng)
+        elif kind == 1:
+            u0 = float(rng.uniform(-80, 70))
+            lat, lon = synth.swath_geolocation(int(rng.integers(2, 100)), int(rng.integers(2, 40)),
+                                               node_lon_deg=float(rng.uniform(160, 200)), u0_deg=u0,
+                                               u1_deg=u0 + float(rng.uniform(1, 30)), rng=rng)
+        elif kind == 2:
+            rows, cols = int(rng.integers(2, 40)), int(rng.integers(2, 30))
+            i, j = np.meshgrid(np.arange(rows, dtype=float), np.arange(cols, dtype=float), indexing="ij")
+            lon = (rng.uniform(0.05, 3) * j + rng.uniform(-1.5, 1.5) * i
+                   + rng.uniform(0, 0.4) * np.sin(0.9 * i) * np.cos(0.7 * j) + rng.uniform(-1e-3, 1e-3, i.shape))
+            lat = rng.uniform(0.05, 3) * i + rng.uniform(-0.5, 0.5) * j + rng.uniform(-1e-3, 1e-3, i.shape)
+            if rng.random() < 0.3:
+                lat = np.abs(lat - 0.6 * lat.max()) + 0.013 * i
+        else:
+            rows, cols = int(rng.integers(2, 25)), int(rng.integers(2, 25))
+            gx, gy = np.meshgrid(np.arange(cols, dtype=float), np.arange(rows, dtype=float))
+            lon = gx + rng.uniform(-0.3, 0.3, gx.shape)
+            lat = gy + (rng.uniform(-0.3, 0.3, gy.shape) if rng.random() < 0.5 else 0.0)
+            if rng.random() < 0.5:                     # a displaced (sometimes repeated) pixel
+                r, c = int(rng.integers(0, rows)), int(rng.integers(0, cols))
+                lon[r, c] = lon[0, 0] + (0.0 if rng.random() < 0.3 else 0.37)
+        lon, lat = np.asarray(lon, dtype=np.float64), np.asarray(lat, dtype=np.float64)
+        if trial % 3 == 0:
+            lon, lat = lon.astype(np.float32).astype(np.float64), lat.astype(np.float32).astype(np.float64)
+        got = _seed_whole(lon, lat)
+        assert (got is None) == (plan.native_seed_parts(lon, lat) is None)
+        if got is None:
+            declined += 1
+            continue
+        tri, half, _ = got
+        assert _valid_triangulation(lon.ravel(), lat.ravel(), tri), trial
+        res = _flip_rounds(lon, lat, tri, half)
+        ref, ties, path = plan.native_delaunay_path(lon, lat)
+        if res[3] == 0 and ties == 0 and ref is not None:
+            assert res[2] == 0 and _tri_set(tri) == _tri_set(ref), (trial, kind, lon.shape)
+            checked += 1
+    assert checked >= 150 and declined >= 20
+
+
+def _interior_edges(tri):
+    e = np.sort(np.concatenate((tri[:, [0, 1]], tri[:, [1, 2]], tri[:, [2, 0]])), axis=1)
+    _, cnt = np.unique(e, axis=0, return_counts=True)
+    return int((cnt == 2).sum())
+
+
 def _near_ties_numpy(x, y, tri, half):
     """count_near_ties (csrc/delaunay.cpp) restated with numpy from (tri, half)."""
     x = np.asarray(x, np.float64).ravel()
