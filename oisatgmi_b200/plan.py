@@ -815,9 +815,11 @@ def submit_triangulations(lons, lats, gplan: GridPlan, workers=None):
 
 def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonlat_dev=None,
                   futures=None):
-    """Plans for a batch of granules (lists of lon/lat arrays): K0 for all of them,
-    the native triangulations on a thread pool (the C call releases the GIL; `futures`:
-    already submitted, submit_triangulations), then the device part granule by granule."""
+    """Plans for a batch of granules (lists of lon/lat arrays), as an event loop: K0 for all of
+    them; the host shares of the triangulations on a thread pool (the C calls release the GIL;
+    `futures`: already submitted, submit_triangulations); the seeds that have arrived are flipped
+    on the device as batches (K12), each granule's device part follows its batch, and granules
+    whose device part has run get their second half while the host waits for slower seeds."""
     import os
     n = len(lons)
     import time as _time
@@ -861,7 +863,6 @@ def granule_plans(lons, lats, gplan: GridPlan, radius: float, workers=None, lonl
             groups.setdefault(_dev.dtype_code(lonlat_dev[sd[0]][0]), []).append(k)
         for ks in groups.values():
             result, work = flip_batch_device([(seeded[k][2], seeded[k][3], lonlat_dev[seeded[k][0]]) for k in ks])
-            mark("flips of %d queued behind" % len(ks))
             flip_host = t.empty((len(ks), 4), dtype=t.int64, pin_memory=True)
             flip_host.copy_(result, non_blocking=True)
             mark("flips of %d" % len(ks))
